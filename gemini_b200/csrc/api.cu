@@ -1,0 +1,734 @@
+// C ABI of libgemini_b200 (include/gemini_b200.h): argument checking, host<->device staging and
+// handle lifetimes.  All arithmetic happens in the kernels of msm.cu / fr.cu; there is no CPU path.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+#include "fr.cuh"
+#include "msm.cuh"
+
+namespace gm {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace gm
+
+using namespace gm;
+
+struct ResultSlot {  // device-side result area of a context
+  XYZZ acc;
+  Jacobian out;
+};
+
+struct gm_msm_stream {
+  gm_ctx* ctx = nullptr;
+  const gm_srs* srs = nullptr;
+  size_t chunk_cap = 0;
+  XYZZ* d_acc = nullptr;
+  DevBuf scal[2], pts_raw[2], pts[2];
+  cudaEvent_t copied[2] = {}, consumed[2] = {};
+  bool used[2] = {false, false};
+  unsigned turn = 0;
+};
+
+struct gm_sumcheck {
+  gm_ctx* ctx = nullptr;
+  Fr* f[2] = {nullptr, nullptr};
+  Fr* g[2] = {nullptr, nullptr};
+  int cur = 0;
+  size_t nf = 0, ng = 0;
+  Fr twist;
+  size_t round = 0, tot_rounds = 0;
+  int flavour = 0;
+  Fr* d_partials = nullptr;
+  unsigned int* d_ticket = nullptr;
+  Fr* d_out = nullptr;   // 2 Fr
+  Fr* h_out = nullptr;   // pinned, 2 Fr
+};
+
+static size_t ceil_log2(size_t x) {  // ark_std::log2
+  size_t r = 0;
+  while (((size_t)1 << r) < x) r++;
+  return r;
+}
+
+static inline void fr_from_u64(Fr& dst, const uint64_t* src) { memcpy(dst.v, src, 32); }
+
+extern "C" {
+
+const char* gm_last_error(void) { return g_err; }
+int gm_abi_version(void) { return 1; }
+
+int gm_init(int device_id, gm_ctx** out_ctx) {
+  GM_ARG(out_ctx != nullptr, "out_ctx is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); libgemini_b200 has no CPU fallback", cudaGetErrorString(e));
+    return GM_ERR_CUDA;
+  }
+  GM_ARG(device_id >= 0 && device_id < count, "device_id out of range");
+  GM_CUDA(cudaSetDevice(device_id));
+  gm_ctx* ctx = new (std::nothrow) gm_ctx();
+  if (!ctx) return GM_ERR_OOM;
+  ctx->device = device_id;
+  cudaDeviceProp prop;
+  GM_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  ctx->sm_count = prop.multiProcessorCount;
+  GM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  GM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev) GM_CUDA(cudaEventCreate(&ev));
+  ctx->pinned_bytes = 4096;
+  GM_CUDA(cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault));
+  *out_ctx = ctx;
+  return GM_OK;
+}
+
+int gm_shutdown(gm_ctx* ctx) {
+  if (!ctx) return GM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->msm.release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->d_result) cudaFree(ctx->d_result);
+  if (ctx->d_flush) cudaFree(ctx->d_flush);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return GM_OK;
+}
+
+uint64_t gm_launch_count(const gm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+float gm_last_device_ms(const gm_ctx* ctx, int phase) { return (ctx && phase >= 0 && phase < 4) ? ctx->last_ms[phase] : -1.f; }
+int gm_device_synchronize(gm_ctx* ctx) {
+  GM_ARG(ctx, "ctx is NULL");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+int gm_timer_start(gm_ctx* ctx) {
+  GM_ARG(ctx, "ctx is NULL");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+  return GM_OK;
+}
+int gm_timer_stop(gm_ctx* ctx, float* out_ms) {
+  GM_ARG(ctx && out_ms, "NULL argument");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+  GM_CUDA(cudaEventSynchronize(ctx->ev[7]));
+  GM_CUDA(cudaEventElapsedTime(out_ms, ctx->ev[6], ctx->ev[7]));
+  return GM_OK;
+}
+int gm_l2_flush(gm_ctx* ctx) {
+  GM_ARG(ctx, "ctx is NULL");
+  GM_TRY(set_device(ctx));
+  const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
+  if (!ctx->d_flush) GM_CUDA(cudaMalloc(&ctx->d_flush, bytes));
+  GM_CUDA(cudaMemsetAsync(ctx->d_flush, 0x5a, bytes, ctx->stream));
+  return GM_OK;
+}
+
+// ---- raw buffers -------------------------------------------------------------------------
+int gm_dev_alloc(gm_ctx* ctx, size_t bytes, void** out_dev) {
+  GM_ARG(ctx && out_dev, "NULL argument");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaMalloc(out_dev, bytes ? bytes : 16));
+  return GM_OK;
+}
+int gm_dev_free(gm_ctx* ctx, void* dev) {
+  GM_ARG(ctx, "ctx is NULL");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  GM_CUDA(cudaFree(dev));
+  return GM_OK;
+}
+int gm_dev_upload(gm_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  GM_ARG(ctx, "ctx is NULL");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+int gm_dev_download(gm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  GM_ARG(ctx, "ctx is NULL");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+int gm_fr_random_dev(gm_ctx* ctx, void* out_dev, size_t n, uint64_t seed) {
+  GM_ARG(ctx && (out_dev || n == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  GM_TRY(fr_random_dev(ctx, reinterpret_cast<Fr*>(out_dev), n, seed));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+// ---- SRS ---------------------------------------------------------------------------------
+static int srs_alloc(gm_ctx* ctx, size_t n, gm_srs** out) {
+  gm_srs* s = new (std::nothrow) gm_srs();
+  if (!s) return GM_ERR_OOM;
+  s->ctx = ctx;
+  s->n = n;
+  cudaError_t e = cudaMalloc(&s->d_points, std::max<size_t>(n, 1) * sizeof(Affine));
+  if (e != cudaSuccess) {
+    delete s;
+    set_error("cudaMalloc of %zu SRS points failed: %s", n, cudaGetErrorString(e));
+    return GM_ERR_OOM;
+  }
+  *out = s;
+  return GM_OK;
+}
+
+static int upload_points(gm_ctx* ctx, const void* points, size_t n, size_t stride, long inf_offset, DevBuf& raw, Affine* d_out,
+                         cudaStream_t copy_on) {
+  GM_ARG(stride >= 96, "stride_bytes must be >= 96");
+  GM_ARG(inf_offset < (long)stride, "inf_offset outside the record");
+  GM_ARG(inf_offset < 0 || inf_offset >= 96, "inf_offset overlaps the coordinates");
+  if (n == 0) return GM_OK;
+  if (stride == 96 && inf_offset < 0) {
+    GM_CUDA(cudaMemcpyAsync(d_out, points, n * 96, cudaMemcpyHostToDevice, copy_on));
+    return GM_OK;
+  }
+  GM_TRY(raw.reserve(n * stride));
+  GM_CUDA(cudaMemcpyAsync(raw.p, points, n * stride, cudaMemcpyHostToDevice, copy_on));
+  return GM_OK;
+}
+
+int gm_srs_load_g1(gm_ctx* ctx, const void* points, size_t n, size_t stride_bytes, long inf_offset, gm_srs** out_srs) {
+  GM_ARG(ctx && out_srs && (points || n == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_srs* s = nullptr;
+  GM_TRY(srs_alloc(ctx, n, &s));
+  DevBuf raw;
+  int rc = upload_points(ctx, points, n, stride_bytes, inf_offset, raw, reinterpret_cast<Affine*>(s->d_points), ctx->stream);
+  if (rc == GM_OK && raw.p) rc = srs_pack(ctx, raw.as<uint8_t>(), n, stride_bytes, inf_offset, reinterpret_cast<Affine*>(s->d_points));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  raw.release();
+  if (rc != GM_OK || e != cudaSuccess) {
+    if (rc == GM_OK) { set_error("srs load: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+    gm_srs_free(s);
+    return rc;
+  }
+  *out_srs = s;
+  return GM_OK;
+}
+
+int gm_srs_generate_g1(gm_ctx* ctx, size_t n, uint64_t first_multiple, gm_srs** out_srs) {
+  GM_ARG(ctx && out_srs, "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_srs* s = nullptr;
+  GM_TRY(srs_alloc(ctx, n, &s));
+  int rc = srs_generate(ctx, n, first_multiple, reinterpret_cast<Affine*>(s->d_points));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc != GM_OK || e != cudaSuccess) {
+    if (rc == GM_OK) { set_error("srs generate: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+    gm_srs_free(s);
+    return rc;
+  }
+  *out_srs = s;
+  return GM_OK;
+}
+
+int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** out_srs) {
+  GM_ARG(ctx && out_srs && point_xy, "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_srs* s = nullptr;
+  GM_TRY(srs_alloc(ctx, n, &s));
+  Affine p;
+  memcpy(&p, point_xy, 96);
+  int rc = srs_fill(ctx, p, n, reinterpret_cast<Affine*>(s->d_points));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc != GM_OK || e != cudaSuccess) {
+    if (rc == GM_OK) { set_error("srs fill: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+    gm_srs_free(s);
+    return rc;
+  }
+  *out_srs = s;
+  return GM_OK;
+}
+
+size_t gm_srs_len(const gm_srs* srs) { return srs ? srs->n : 0; }
+
+int gm_srs_read(gm_ctx* ctx, const gm_srs* srs, size_t offset, size_t n, uint64_t* out_xy) {
+  GM_ARG(ctx && srs && out_xy, "NULL argument");
+  GM_ARG(offset <= srs->n && n <= srs->n - offset, "range outside the SRS");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaMemcpyAsync(out_xy, reinterpret_cast<const Affine*>(srs->d_points) + offset, n * sizeof(Affine),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+int gm_srs_free(gm_srs* srs) {
+  if (!srs) return GM_OK;
+  if (srs->ctx) {
+    cudaSetDevice(srs->ctx->device);
+    cudaStreamSynchronize(srs->ctx->stream);
+  }
+  if (srs->owned && srs->d_points) cudaFree(srs->d_points);
+  delete srs;
+  return GM_OK;
+}
+
+// ---- MSM ---------------------------------------------------------------------------------
+static int ensure_result(gm_ctx* ctx, ResultSlot** slot) {
+  if (!ctx->d_result) GM_CUDA(cudaMalloc(&ctx->d_result, sizeof(ResultSlot)));
+  *slot = reinterpret_cast<ResultSlot*>(ctx->d_result);
+  return GM_OK;
+}
+
+static void record_phases(gm_ctx* ctx) {
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ctx->last_ms[2], ctx->ev[3], ctx->ev[4]);
+  cudaEventElapsedTime(&ctx->last_ms[3], ctx->ev[4], ctx->ev[5]);
+}
+
+static int msm_common(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scalars, size_t n, bool bigint, uint64_t out[18]) {
+  ResultSlot* slot;
+  GM_TRY(ensure_result(ctx, &slot));
+  GM_TRY(msm_acc_reset(ctx, &slot->acc));
+  GM_TRY(msm_accumulate(ctx, d_bases, d_scalars, n, bigint, &slot->acc));
+  GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
+  GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->pinned, sizeof(Jacobian));
+  if (n) record_phases(ctx); else cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  return GM_OK;
+}
+
+int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
+                  int scalars_are_bigint, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && srs && out_jacobian && (scalars_dev || n == 0), "NULL argument");
+  GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
+  GM_TRY(set_device(ctx));
+  n = std::min(n, srs->n - base_offset);  // msm_unchecked truncates to the shorter input
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  return msm_common(ctx, reinterpret_cast<const Affine*>(srs->d_points) + base_offset,
+                    reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0, out_jacobian);
+}
+
+int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+              int scalars_are_bigint, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && srs && out_jacobian && (scalars || n == 0), "NULL argument");
+  GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
+  GM_TRY(set_device(ctx));
+  n = std::min(n, srs->n - base_offset);
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
+  if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return msm_common(ctx, reinterpret_cast<const Affine*>(srs->d_points) + base_offset, ctx->msm.scalars.as<uint32_t>(), n,
+                    scalars_are_bigint != 0, out_jacobian);
+}
+
+int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t bases_len, const uint64_t* scalars,
+                      size_t scalars_len, uint64_t out_jacobian[18], size_t* out_min_len) {
+  GM_ARG(ctx && srs && out_jacobian, "NULL argument");
+  GM_ARG(base_offset <= srs->n && bases_len <= srs->n - base_offset, "bases range outside the SRS");
+  if (bases_len != scalars_len) {
+    if (out_min_len) *out_min_len = std::min(bases_len, scalars_len);
+    set_error("msm: bases.len() = %zu != scalars.len() = %zu", bases_len, scalars_len);
+    return GM_ERR_LENGTH;
+  }
+  return gm_msm_g1(ctx, srs, base_offset, scalars, scalars_len, 0, out_jacobian);
+}
+
+int gm_msm_g1_hostbases(gm_ctx* ctx, const void* points, size_t stride_bytes, long inf_offset, const uint64_t* scalars,
+                        size_t n, int scalars_are_bigint, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && out_jacobian && ((points && scalars) || n == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  MsmScratch& S = ctx->msm;
+  GM_TRY(S.bases_tmp.reserve(std::max<size_t>(n, 1) * sizeof(Affine)));
+  DevBuf raw;
+  int rc = upload_points(ctx, points, n, stride_bytes, inf_offset, raw, S.bases_tmp.as<Affine>(), ctx->stream);
+  if (rc == GM_OK && raw.p) rc = srs_pack(ctx, raw.as<uint8_t>(), n, stride_bytes, inf_offset, S.bases_tmp.as<Affine>());
+  if (rc == GM_OK) rc = S.scalars.reserve(std::max<size_t>(n, 1) * 32);
+  if (rc == GM_OK && n) {
+    cudaError_t e = cudaMemcpyAsync(S.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { set_error("H2D scalars: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+  }
+  if (rc == GM_OK) rc = msm_common(ctx, S.bases_tmp.as<Affine>(), S.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
+  cudaStreamSynchronize(ctx->stream);
+  raw.release();
+  return rc;
+}
+
+int gm_g1_sum(gm_ctx* ctx, const uint64_t* jacobians, size_t k, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && out_jacobian && (jacobians || k == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  ResultSlot* slot;
+  GM_TRY(ensure_result(ctx, &slot));
+  GM_TRY(ctx->msm.bases_tmp.reserve(std::max<size_t>(k, 1) * sizeof(Jacobian)));
+  if (k) GM_CUDA(cudaMemcpyAsync(ctx->msm.bases_tmp.p, jacobians, k * sizeof(Jacobian), cudaMemcpyHostToDevice, ctx->stream));
+  GM_TRY(msm_acc_reset(ctx, &slot->acc));
+  if (k) GM_TRY(msm_acc_add_jacobians(ctx, ctx->msm.bases_tmp.as<Jacobian>(), k, &slot->acc));
+  GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
+  GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_jacobian, ctx->pinned, sizeof(Jacobian));
+  return GM_OK;
+}
+
+// ---- streamed MSM ------------------------------------------------------------------------
+int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, gm_msm_stream** out) {
+  GM_ARG(ctx && out, "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_msm_stream* s = new (std::nothrow) gm_msm_stream();
+  if (!s) return GM_ERR_OOM;
+  s->ctx = ctx;
+  s->srs = srs_or_null;
+  s->chunk_cap = chunk_cap;
+  cudaError_t e = cudaMalloc(&s->d_acc, sizeof(XYZZ));
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_acc, 0, sizeof(XYZZ), ctx->stream);
+  for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+    e = cudaEventCreateWithFlags(&s->copied[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->consumed[k], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    set_error("msm stream: %s", cudaGetErrorString(e));
+    gm_msm_stream_free(s);
+    return GM_ERR_CUDA;
+  }
+  *out = s;
+  return GM_OK;
+}
+
+int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes, long inf_offset, size_t base_offset,
+                       const uint64_t* scalars, size_t m, int scalars_are_bigint) {
+  GM_ARG(s && (scalars || m == 0), "NULL argument");
+  gm_ctx* ctx = s->ctx;
+  GM_TRY(set_device(ctx));
+  if (m == 0) return GM_OK;
+  const Affine* d_bases = nullptr;
+  const unsigned b = s->turn & 1u;
+  // the staging buffers of this slot may still be read by the chunk pushed two calls ago
+  if (s->used[b]) GM_CUDA(cudaEventSynchronize(s->consumed[b]));
+  GM_TRY(s->scal[b].reserve(m * 32));
+  GM_CUDA(cudaMemcpyAsync(s->scal[b].p, scalars, m * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+  bool need_pack = false;
+  if (points) {
+    GM_TRY(s->pts[b].reserve(m * sizeof(Affine)));
+    GM_TRY(upload_points(ctx, points, m, stride_bytes, inf_offset, s->pts_raw[b], s->pts[b].as<Affine>(), ctx->copy_stream));
+    need_pack = !(stride_bytes == 96 && inf_offset < 0);
+    d_bases = s->pts[b].as<Affine>();
+  } else {
+    GM_ARG(s->srs != nullptr, "stream has no SRS and no points were supplied");
+    GM_ARG(base_offset <= s->srs->n && m <= s->srs->n - base_offset, "base range outside the SRS");
+    d_bases = reinterpret_cast<const Affine*>(s->srs->d_points) + base_offset;
+  }
+  GM_CUDA(cudaEventRecord(s->copied[b], ctx->copy_stream));
+  // the caller may reuse its buffers as soon as we return: wait for the copies (the previous chunk's
+  // kernels keep running on ctx->stream meanwhile - this is the H2D / compute overlap)
+  GM_CUDA(cudaEventSynchronize(s->copied[b]));
+  GM_CUDA(cudaStreamWaitEvent(ctx->stream, s->copied[b], 0));
+  if (need_pack) GM_TRY(srs_pack(ctx, s->pts_raw[b].as<uint8_t>(), m, stride_bytes, inf_offset, s->pts[b].as<Affine>()));
+  GM_TRY(msm_accumulate(ctx, d_bases, s->scal[b].as<uint32_t>(), m, scalars_are_bigint != 0, s->d_acc));
+  GM_CUDA(cudaEventRecord(s->consumed[b], ctx->stream));
+  s->used[b] = true;
+  s->turn++;
+  return GM_OK;
+}
+
+int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]) {
+  GM_ARG(s && out_jacobian, "NULL argument");
+  gm_ctx* ctx = s->ctx;
+  GM_TRY(set_device(ctx));
+  ResultSlot* slot;
+  GM_TRY(ensure_result(ctx, &slot));
+  GM_TRY(msm_acc_normalize(ctx, s->d_acc, &slot->out));
+  GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_jacobian, ctx->pinned, sizeof(Jacobian));
+  return GM_OK;
+}
+
+int gm_msm_stream_free(gm_msm_stream* s) {
+  if (!s) return GM_OK;
+  if (s->ctx) {
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaStreamSynchronize(s->ctx->copy_stream);
+  }
+  if (s->d_acc) cudaFree(s->d_acc);
+  for (int k = 0; k < 2; k++) {
+    s->scal[k].release(); s->pts_raw[k].release(); s->pts[k].release();
+    if (s->copied[k]) cudaEventDestroy(s->copied[k]);
+    if (s->consumed[k]) cudaEventDestroy(s->consumed[k]);
+  }
+  delete s;
+  return GM_OK;
+}
+
+// ---- Fr folds ----------------------------------------------------------------------------
+int gm_fr_fold_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t r[4], void* out_dev) {
+  GM_ARG(ctx && r && ((f_dev && out_dev) || n == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  Fr rr;
+  fr_from_u64(rr, r);
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  GM_TRY(fr_fold_dev(ctx, reinterpret_cast<const Fr*>(f_dev), n, rr, reinterpret_cast<Fr*>(out_dev)));
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  return GM_OK;
+}
+
+int gm_fr_fold(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t r[4], uint64_t* out) {
+  GM_ARG(ctx && r && ((f && out) || n == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  if (n == 0) return GM_OK;
+  const size_t half = (n + 1) / 2;
+  DevBuf& in = ctx->msm.scalars;
+  DevBuf& res = ctx->msm.bases_tmp;
+  GM_TRY(in.reserve(n * 32));
+  GM_TRY(res.reserve(half * 32));
+  Fr rr;
+  fr_from_u64(rr, r);
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(in.p, f, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  GM_TRY(fr_fold_dev(ctx, in.as<Fr>(), n, rr, res.as<Fr>()));
+  GM_CUDA(cudaMemcpyAsync(out, res.p, half * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  return GM_OK;
+}
+
+size_t gm_fr_fold_chain_len(size_t n, size_t k) {
+  size_t tot = 0;
+  for (size_t j = 0; j < k; j++) { n = (n + 1) / 2; tot += n; }
+  return tot;
+}
+
+int gm_fr_fold_chain(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t* challenges, size_t k, uint64_t* out_levels) {
+  GM_ARG(ctx && ((f && out_levels) || n == 0 || k == 0) && (challenges || k == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  if (n == 0 || k == 0) return GM_OK;
+  const size_t tot = gm_fr_fold_chain_len(n, k);
+  DevBuf& in = ctx->msm.scalars;
+  DevBuf& res = ctx->msm.bases_tmp;
+  GM_TRY(in.reserve(n * 32));
+  GM_TRY(res.reserve(tot * 32));
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(in.p, f, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  const Fr* src = in.as<Fr>();
+  Fr* dst = res.as<Fr>();
+  size_t len = n;
+  for (size_t j = 0; j < k; j++) {
+    Fr rr;
+    fr_from_u64(rr, challenges + 4 * j);
+    GM_TRY(fr_fold_dev(ctx, src, len, rr, dst));
+    src = dst;
+    len = (len + 1) / 2;
+    dst += len;
+  }
+  GM_CUDA(cudaMemcpyAsync(out_levels, res.p, tot * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  return GM_OK;
+}
+
+// ---- sumcheck ----------------------------------------------------------------------------
+static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_t twist[4], int flavour, gm_sumcheck** out) {
+  GM_ARG(flavour == GM_SUMCHECK_GEMINI_TIME || flavour == GM_SUMCHECK_HERRING_F, "unknown flavour");
+  gm_sumcheck* p = new (std::nothrow) gm_sumcheck();
+  if (!p) return GM_ERR_OOM;
+  p->ctx = ctx;
+  p->nf = f_len;
+  p->ng = g_len;
+  p->flavour = flavour;
+  fr_from_u64(p->twist, twist);
+  // time_prover.rs:35-38 (max) vs herring/time_prover.rs:36-39 (min)
+  p->tot_rounds = flavour == GM_SUMCHECK_GEMINI_TIME ? ceil_log2(std::max(f_len, g_len)) : ceil_log2(std::min(f_len, g_len));
+  const size_t ctas = sc_max_ctas(f_len, g_len);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, std::max<size_t>(bytes, 32)); };
+  alloc((void**)&p->f[0], f_len * 32);
+  alloc((void**)&p->f[1], ((f_len + 1) / 2) * 32);
+  alloc((void**)&p->g[0], g_len * 32);
+  alloc((void**)&p->g[1], ((g_len + 1) / 2) * 32);
+  alloc((void**)&p->d_partials, ctas * 64);
+  alloc((void**)&p->d_ticket, 16);
+  alloc((void**)&p->d_out, 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ticket, 0, 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&p->h_out, 64, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    set_error("sumcheck alloc: %s", cudaGetErrorString(e));
+    gm_sumcheck_free(p);
+    return e == cudaErrorMemoryAllocation ? GM_ERR_OOM : GM_ERR_CUDA;
+  }
+  *out = p;
+  return GM_OK;
+}
+
+int gm_sumcheck_new(gm_ctx* ctx, const uint64_t* f, size_t f_len, const uint64_t* g, size_t g_len, const uint64_t twist[4],
+                    int flavour, gm_sumcheck** out) {
+  GM_ARG(ctx && out && twist && (f || f_len == 0) && (g || g_len == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_sumcheck* p = nullptr;
+  GM_TRY(sumcheck_alloc(ctx, f_len, g_len, twist, flavour, &p));
+  cudaError_t e = cudaSuccess;
+  if (f_len) e = cudaMemcpyAsync(p->f[0], f, f_len * 32, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && g_len) e = cudaMemcpyAsync(p->g[0], g, g_len * 32, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    set_error("sumcheck upload: %s", cudaGetErrorString(e));
+    gm_sumcheck_free(p);
+    return GM_ERR_CUDA;
+  }
+  *out = p;
+  return GM_OK;
+}
+
+int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void* g_dev, size_t g_len, const uint64_t twist[4],
+                        int flavour, gm_sumcheck** out) {
+  GM_ARG(ctx && out && twist && (f_dev || f_len == 0) && (g_dev || g_len == 0), "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_sumcheck* p = nullptr;
+  GM_TRY(sumcheck_alloc(ctx, f_len, g_len, twist, flavour, &p));
+  cudaError_t e = cudaSuccess;
+  if (f_len) e = cudaMemcpyAsync(p->f[0], f_dev, f_len * 32, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess && g_len) e = cudaMemcpyAsync(p->g[0], g_dev, g_len * 32, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    set_error("sumcheck copy: %s", cudaGetErrorString(e));
+    gm_sumcheck_free(p);
+    return GM_ERR_CUDA;
+  }
+  *out = p;
+  return GM_OK;
+}
+
+static bool sc_use_twist(const gm_sumcheck* p, const Fr& tw) {
+  return p->flavour == GM_SUMCHECK_GEMINI_TIME && tw != Fr::one();
+}
+
+int gm_sumcheck_fold(gm_sumcheck* p, const uint64_t r[4]) {
+  GM_ARG(p && r, "NULL argument");
+  gm_ctx* ctx = p->ctx;
+  GM_TRY(set_device(ctx));
+  Fr rg;
+  fr_from_u64(rg, r);
+  const Fr rf = rg * p->twist;  // time_prover.rs:77 / herring/time_prover.rs:85
+  const int nxt = p->cur ^ 1;
+  GM_TRY(fr_fold_dev(ctx, p->f[p->cur], p->nf, rf, p->f[nxt]));
+  GM_TRY(fr_fold_dev(ctx, p->g[p->cur], p->ng, rg, p->g[nxt]));
+  p->cur = nxt;
+  p->nf = (p->nf + 1) / 2;
+  p->ng = (p->ng + 1) / 2;
+  p->twist = p->twist.sqr();
+  return GM_OK;
+}
+
+int gm_sumcheck_next_message(gm_sumcheck* p, const uint64_t* challenge_or_null, uint64_t out_ab[8], int* out_has_msg) {
+  GM_ARG(p && out_ab && out_has_msg, "NULL argument");
+  gm_ctx* ctx = p->ctx;
+  GM_TRY(set_device(ctx));
+  if (p->round > p->tot_rounds) {  // time_prover.rs:84 assert
+    set_error("next_message: more rounds than needed");
+    return GM_ERR_STATE;
+  }
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  const bool last = p->round == p->tot_rounds;
+  if (challenge_or_null && last) {
+    GM_TRY(gm_sumcheck_fold(p, challenge_or_null));
+  }
+  if (last) {
+    *out_has_msg = 0;
+    GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    return GM_OK;
+  }
+  if (challenge_or_null) {
+    Fr rg;
+    fr_from_u64(rg, challenge_or_null);
+    const Fr rf = rg * p->twist;
+    const Fr new_twist = p->twist.sqr();
+    const int nxt = p->cur ^ 1;
+    GM_TRY(sc_fold_message_dev(ctx, p->f[p->cur], p->nf, p->g[p->cur], p->ng, rf, rg, p->f[nxt], p->g[nxt], new_twist,
+                               sc_use_twist(p, new_twist), p->d_partials, p->d_ticket, p->d_out));
+    p->cur = nxt;
+    p->nf = (p->nf + 1) / 2;
+    p->ng = (p->ng + 1) / 2;
+    p->twist = new_twist;
+  } else {
+    GM_TRY(sc_message_dev(ctx, p->f[p->cur], p->nf, p->g[p->cur], p->ng, p->twist, sc_use_twist(p, p->twist), p->d_partials,
+                          p->d_ticket, p->d_out));
+  }
+  GM_CUDA(cudaMemcpyAsync(p->h_out, p->d_out, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_ab, p->h_out, 64);
+  p->round++;
+  *out_has_msg = 1;
+  return GM_OK;
+}
+
+size_t gm_sumcheck_rounds(const gm_sumcheck* p) { return p ? p->tot_rounds : 0; }
+size_t gm_sumcheck_round(const gm_sumcheck* p) { return p ? p->round : 0; }
+int gm_sumcheck_set_rounds(gm_sumcheck* p, size_t round, size_t tot_rounds) {
+  GM_ARG(p, "NULL argument");
+  p->round = round;
+  p->tot_rounds = tot_rounds;
+  return GM_OK;
+}
+
+int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has) {
+  GM_ARG(p && out_fg && out_has, "NULL argument");
+  gm_ctx* ctx = p->ctx;
+  GM_TRY(set_device(ctx));
+  if (p->round != p->tot_rounds) { *out_has = 0; return GM_OK; }
+  if (p->nf == 0 || p->ng == 0) {
+    set_error("final_foldings on an empty vector");
+    return GM_ERR_STATE;
+  }
+  GM_CUDA(cudaMemcpyAsync(p->h_out, p->f[p->cur], 32, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(p->h_out + 1, p->g[p->cur], 32, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_fg, p->h_out, 64);
+  *out_has = 1;
+  return GM_OK;
+}
+
+int gm_sumcheck_read_state(gm_sumcheck* p, uint64_t* out_f, size_t* f_len, uint64_t* out_g, size_t* g_len, uint64_t out_twist[4]) {
+  GM_ARG(p, "NULL argument");
+  gm_ctx* ctx = p->ctx;
+  GM_TRY(set_device(ctx));
+  if (f_len) *f_len = p->nf;
+  if (g_len) *g_len = p->ng;
+  if (out_twist) memcpy(out_twist, p->twist.v, 32);
+  if (out_f && p->nf) GM_CUDA(cudaMemcpyAsync(out_f, p->f[p->cur], p->nf * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_g && p->ng) GM_CUDA(cudaMemcpyAsync(out_g, p->g[p->cur], p->ng * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GM_OK;
+}
+
+int gm_sumcheck_free(gm_sumcheck* p) {
+  if (!p) return GM_OK;
+  if (p->ctx) {
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+  }
+  for (int k = 0; k < 2; k++) { if (p->f[k]) cudaFree(p->f[k]); if (p->g[k]) cudaFree(p->g[k]); }
+  if (p->d_partials) cudaFree(p->d_partials);
+  if (p->d_ticket) cudaFree(p->d_ticket);
+  if (p->d_out) cudaFree(p->d_out);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  delete p;
+  return GM_OK;
+}
+
+}  // extern "C"

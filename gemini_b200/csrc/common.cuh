@@ -1,0 +1,112 @@
+// Shared host-side plumbing of libgemini_b200: context, error reporting, scratch arena.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gemini_b200.h"
+
+namespace gm {
+
+void set_error(const char* fmt, ...);
+
+#define GM_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::gm::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (_e == cudaErrorMemoryAllocation) ? GM_ERR_OOM : GM_ERR_CUDA;                  \
+    }                                                                                       \
+  } while (0)
+
+#define GM_TRY(expr)        \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != GM_OK) return _r; \
+  } while (0)
+
+#define GM_ARG(cond, msg)                   \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::gm::set_error("bad argument: %s", msg); \
+      return GM_ERR_ARG;                    \
+    }                                       \
+  } while (0)
+
+// Grow-only device buffer (cudaMalloc is slow and synchronising; scratch is reused across calls).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return GM_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+      if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return GM_ERR_OOM;
+      }
+    }
+    cap = want;
+    return GM_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct MsmScratch {
+  DevBuf scalars;    // staged scalars (host-call path)
+  DevBuf digits;     // W*n digit codes
+  DevBuf sorted;     // W*n point references grouped by bucket
+  DevBuf counts, starts, cursor, poff;  // per global bucket
+  DevBuf buckets;    // XYZZ per global bucket
+  DevBuf partials;   // XYZZ partial sums of split buckets
+  DevBuf work;       // work items
+  DevBuf split;      // split-bucket list
+  DevBuf small;      // counters, size histogram, chunk sums, window sums, result
+  DevBuf scan_tmp;
+  DevBuf bases_tmp;  // ad-hoc bases (hostbases / stream pushes with points)
+  void release() {
+    scalars.release(); digits.release(); sorted.release(); counts.release(); starts.release();
+    cursor.release(); poff.release(); buckets.release(); partials.release(); work.release();
+    split.release(); small.release(); scan_tmp.release(); bases_tmp.release();
+  }
+};
+
+}  // namespace gm
+
+struct gm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  float last_ms[4] = {0, 0, 0, 0};
+  uint64_t launches = 0;
+  int sm_count = 148;
+  gm::MsmScratch msm;
+  void* pinned = nullptr;  // small pinned staging block (results, challenges)
+  size_t pinned_bytes = 0;
+  void* d_result = nullptr;  // device result slot (accumulator + normalised output)
+  void* d_flush = nullptr;   // 256 MB scratch written by gm_l2_flush
+};
+
+struct gm_srs {
+  gm_ctx* ctx = nullptr;
+  void* d_points = nullptr;  // n * 96 B, Montgomery x|y, (0,0) = identity
+  size_t n = 0;
+  bool owned = true;
+};
+
+namespace gm {
+inline int set_device(const gm_ctx* ctx) {
+  GM_CUDA(cudaSetDevice(ctx->device));
+  return GM_OK;
+}
+}  // namespace gm

@@ -1,0 +1,257 @@
+// Montgomery prime-field arithmetic on 32-bit limbs (BLS12-381 Fq: 12 limbs,
+// Fr: 8 limbs).  Elements live in Montgomery form, fully reduced (< p), in the
+// same little-endian limb order arkworks' Fp<MontBackend, N> keeps in memory
+// (ark-ff 0.4.2, pinned by /root/reference/Cargo.lock:62-64), so host buffers
+// are consumed and produced without any conversion.
+//
+// mont_mul is an operand-scanning (CIOS) product whose partial sums are split
+// into an even- and an odd-column accumulator: every 64-bit partial product
+// a[j]*w then lands on an aligned (lo,hi) pair of one accumulator, which lets a
+// whole row run as one carry chain of mad.lo.cc/madc.hi.cc pairs (IMAD.WIDE.X
+// in SASS) with no carry fix-up instructions.
+#pragma once
+#include "limbs.cuh"
+
+namespace gm {
+
+// ---------------------------------------------------------------------------
+// Field parameters: compile-time limb tables (constexpr switch => immediates
+// after unrolling; no constant-memory traffic, identical on host and device).
+// ---------------------------------------------------------------------------
+struct FqParams {
+  static constexpr int N = 12;
+  static constexpr uint32_t INV = 0xfffcfffdu;  // -q^{-1} mod 2^32
+  GM_HD static constexpr uint32_t mod(int j) {
+    constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return t[j];
+  }
+  // R = 2^384 mod q (Montgomery one)
+  GM_HD static constexpr uint32_t one(int j) {
+    constexpr uint32_t t[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+    return t[j];
+  }
+  // R^2 mod q
+  GM_HD static constexpr uint32_t r2(int j) {
+    constexpr uint32_t t[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+    return t[j];
+  }
+};
+
+struct FrParams {
+  static constexpr int N = 8;
+  static constexpr uint32_t INV = 0xffffffffu;  // -r^{-1} mod 2^32
+  GM_HD static constexpr uint32_t mod(int j) {
+    constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                               0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return t[j];
+  }
+  GM_HD static constexpr uint32_t one(int j) {
+    constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                               0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+    return t[j];
+  }
+  GM_HD static constexpr uint32_t r2(int j) {
+    constexpr uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                               0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+    return t[j];
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Raw limb routines
+// ---------------------------------------------------------------------------
+namespace detail {
+
+// First row: (E, O) = a * w, E = even-column accumulator (E[k] at column k),
+// O = odd-column accumulator (O[k] at column k+1).
+template <int N>
+GM_HD void row_first(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t w) {
+#pragma unroll
+  for (int j = 0; j < N; j += 2) mul_wide(E[j], E[j + 1], a[j], w);
+#pragma unroll
+  for (int j = 1; j < N; j += 2) mul_wide(O[j - 1], O[j], a[j], w);
+}
+
+// Montgomery step: add m*p with m chosen so that column 0 (E[0]) becomes zero.
+template <class P>
+GM_HD void mont_reduce_step(uint32_t* E, uint32_t* O) {
+  constexpr int N = P::N;
+  const uint32_t m = E[0] * P::INV;
+  mad_wide_cc(O[0], O[1], m, P::mod(1), O[0], O[1]);
+#pragma unroll
+  for (int j = 3; j < N; j += 2) madc_wide_cc(O[j - 1], O[j], m, P::mod(j), O[j - 1], O[j]);
+  // (no carry out of the odd chain: the running value is < 2^(32(N+1)))
+  mad_wide_cc(E[0], E[1], m, P::mod(0), E[0], E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], m, P::mod(j), E[j], E[j + 1]);
+  O[N - 1] = addc(O[N - 1], 0);  // even chain's carry sits at column N
+}
+
+// Divide by 2^32 (drop the now-zero column 0) and add the next row a*w.
+// On entry E/O are the even/odd accumulators; on exit the roles are swapped
+// (the caller passes them swapped to the next step).
+template <int N>
+GM_HD void row_next(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t w) {
+  O[0] = add_cc(O[0], E[1]);  // stray limb of the old even accumulator
+#pragma unroll
+  for (int j = 1; j < N - 1; j += 2) madc_wide_cc(E[j - 1], E[j], a[j], w, E[j + 1], E[j + 2]);
+  madc_wide_top(E[N - 2], E[N - 1], a[N - 1], w);
+  mad_wide_cc(O[0], O[1], a[0], w, O[0], O[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) madc_wide_cc(O[j], O[j + 1], a[j], w, O[j], O[j + 1]);
+  E[N - 1] = addc(E[N - 1], 0);
+}
+
+// r = (a >= p) ? a - p : a
+template <class P>
+GM_HD void cond_sub_p(uint32_t* r, const uint32_t* a) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+  t[0] = sub_cc(a[0], P::mod(0));
+#pragma unroll
+  for (int j = 1; j < N; j++) t[j] = subc_cc(a[j], P::mod(j));
+  const uint32_t borrow = subc(0, 0);  // 0xffffffff if a < p
+#pragma unroll
+  for (int j = 0; j < N; j++) r[j] = borrow ? a[j] : t[j];
+}
+
+}  // namespace detail
+
+template <class P>
+GM_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  uint32_t x[N], y[N];
+  detail::row_first<N>(x, y, a, b[0]);
+  detail::mont_reduce_step<P>(x, y);
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    detail::row_next<N>(x, y, a, b[i]);  // roles swap: even = y, odd = x
+    detail::mont_reduce_step<P>(y, x);
+    if (i + 1 < N) {
+      detail::row_next<N>(y, x, a, b[i + 1]);  // roles swap back
+      detail::mont_reduce_step<P>(x, y);
+    }
+  }
+  // N is even: after the loop the even accumulator is y, the odd one is x.
+  // result = (even + odd * 2^32) / 2^32 -> limbs odd[k] + even[k+1]
+  uint32_t t[N];
+  t[0] = add_cc(x[0], y[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[k] = addc_cc(x[k], y[k + 1]);
+  t[N - 1] = addc(x[N - 1], 0);
+  detail::cond_sub_p<P>(r, t);
+}
+
+// Montgomery reduction of a single N-limb value: r = a * R^{-1} mod p
+// (used for into_bigint: Montgomery -> canonical).
+template <class P>
+GM_HD void mont_redc(uint32_t* r, const uint32_t* a) {
+  constexpr int N = P::N;
+  uint32_t one[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) one[j] = (j == 0) ? 1u : 0u;
+  mont_mul<P>(r, a, one);
+}
+
+template <class P>
+GM_HD void fp_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+  t[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) t[j] = addc_cc(a[j], b[j]);
+  t[N - 1] = addc(a[N - 1], b[N - 1]);  // 2p < 2^(32N): no carry out
+  detail::cond_sub_p<P>(r, t);
+}
+
+template <class P>
+GM_HD void fp_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  uint32_t t[N];
+  t[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int j = 1; j < N; j++) t[j] = subc_cc(a[j], b[j]);
+  const uint32_t borrow = subc(0, 0);  // all-ones if a < b
+  r[0] = add_cc(t[0], P::mod(0) & borrow);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) r[j] = addc_cc(t[j], P::mod(j) & borrow);
+  r[N - 1] = addc(t[N - 1], P::mod(N - 1) & borrow);
+}
+
+// ---------------------------------------------------------------------------
+// Value type
+// ---------------------------------------------------------------------------
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  GM_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int j = 0; j < N; j++) r.v[j] = 0;
+    return r;
+  }
+  GM_HD static Fp one() {
+    Fp r;
+#pragma unroll
+    for (int j = 0; j < N; j++) r.v[j] = P::one(j);
+    return r;
+  }
+  GM_HD bool is_zero() const {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) acc |= v[j];
+    return acc == 0;
+  }
+  GM_HD bool operator==(const Fp& o) const {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) acc |= v[j] ^ o.v[j];
+    return acc == 0;
+  }
+  GM_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+  GM_HD Fp operator+(const Fp& o) const { Fp r; fp_add<P>(r.v, v, o.v); return r; }
+  GM_HD Fp operator-(const Fp& o) const { Fp r; fp_sub<P>(r.v, v, o.v); return r; }
+  GM_HD Fp operator*(const Fp& o) const { Fp r; mont_mul<P>(r.v, v, o.v); return r; }
+  GM_HD Fp sqr() const { Fp r; mont_mul<P>(r.v, v, v); return r; }
+  GM_HD Fp dbl() const { Fp r; fp_add<P>(r.v, v, v); return r; }
+  GM_HD Fp neg() const { Fp z = zero(); Fp r; fp_sub<P>(r.v, z.v, v); return r; }
+  GM_HD Fp from_mont() const { Fp r; mont_redc<P>(r.v, v); return r; }
+  GM_HD Fp to_mont() const {
+    Fp k;
+#pragma unroll
+    for (int j = 0; j < N; j++) k.v[j] = P::r2(j);
+    return *this * k;
+  }
+};
+
+using Fq = Fp<FqParams>;
+using Fr = Fp<FrParams>;
+
+// a^(p-2) by square-and-multiply (field inversion; a != 0).  Loop is rolled on
+// purpose: it runs once per MSM (final normalisation), never in a hot loop.
+template <class P>
+GM_HD Fp<P> fp_inv(const Fp<P>& a) {
+  constexpr int N = P::N;
+  uint32_t e[N];
+  // e = p - 2 (p is odd and p mod 2^32 >= 2 for both fields? handled generally)
+  uint32_t borrow = 0;
+  for (int j = 0; j < N; j++) {
+    uint64_t t = (uint64_t)P::mod(j) - (j == 0 ? 2u : 0u) - borrow;
+    e[j] = (uint32_t)t;
+    borrow = (uint32_t)(t >> 63);
+  }
+  Fp<P> acc = Fp<P>::one();
+#pragma unroll 1
+  for (int bit = 32 * N - 1; bit >= 0; bit--) {
+    acc = acc.sqr();
+    if ((e[bit >> 5] >> (bit & 31)) & 1u) acc = acc * a;
+  }
+  return acc;
+}
+
+}  // namespace gm

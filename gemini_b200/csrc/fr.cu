@@ -1,0 +1,299 @@
+// Fold-in-half reductions over Fr (BLS12-381 scalar field) for sm_100a.
+//
+//   k_fr_fold           misc::fold_polynomial (/root/reference/src/misc.rs:52-56), herring split_fold
+//                       (/root/reference/src/herring/time_prover.rs:72-76)             [48 B / input element]
+//   k_sc_message        first round message of TimeProver::next_message
+//                       (/root/reference/src/subprotocols/sumcheck/time_prover.rs:98-118)
+//   k_sc_fold_message   fold of f and g (time_prover.rs:75-80) FUSED with the next round's message:
+//                       the folded vectors are produced, written once and consumed from registers
+//                       (the CPU reference makes two passes and allocates two fresh Vecs per round)
+//
+// Message, for pair i of the (folded) vectors with t_i = twist^(2i):
+//   gemini  : a += f[2i] g[2i] t_i ; b += (f[2i] g[2i+1] + g[2i] f[2i+1] twist) t_i
+//   herring : the same with twist = 1 (herring/time_prover.rs:91-123 applies the twist only in fold)
+// Missing elements (odd tails, unequal lengths) read as zero, exactly like the reference's
+// `unwrap_or(&zero)` / zip-to-shorter (a product with a zero partner vanishes).
+#include "common.cuh"
+#include "fp.cuh"
+#include "fr.cuh"
+
+namespace gm {
+
+static constexpr int SC_THREADS = 256;
+static constexpr int SC_K = 8;                       // pairs per thread
+static constexpr int SC_TILE = SC_THREADS * SC_K;    // pairs per CTA
+
+__device__ __forceinline__ Fr load_fr(const Fr* p) {
+  Fr r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4 lo = s[0], hi = s[1];
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+__device__ __forceinline__ Fr load_fr_or_zero(const Fr* base, size_t idx, size_t n) {
+  return idx < n ? load_fr(base + idx) : Fr::zero();
+}
+__device__ __forceinline__ void store_fr(Fr* p, const Fr& v) {
+  uint4* d = reinterpret_cast<uint4*>(p);
+  d[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  d[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fr_fold(const Fr* __restrict__ f, size_t n, Fr r, Fr* __restrict__ out) {
+  const size_t half = (n + 1) / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    Fr e = load_fr(f + 2 * i);
+    if (2 * i + 1 < n) {
+      Fr o = load_fr(f + 2 * i + 1);
+      e = e + r * o;
+    }
+    store_fr(out + i, e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PowTable {
+  Fr p[40];  // p[k] = (twist^2)^(2^k)
+};
+
+__device__ __forceinline__ Fr pow_from_table(const PowTable& tab, uint64_t e) {
+  Fr r = Fr::one();
+  for (int k = 0; k < 40 && (e >> k); k++)
+    if ((e >> k) & 1ull) r = r * tab.p[k];
+  return r;
+}
+
+__device__ __forceinline__ Fr warp_sum_fr(Fr v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Fr other;
+#pragma unroll
+    for (int j = 0; j < 8; j++) other.v[j] = __shfl_down_sync(0xffffffffu, v.v[j], o);
+    v = v + other;
+  }
+  return v;
+}
+
+// CTA sum of (a, b); then the last CTA to arrive sums all CTA partials into out[0..1].
+__device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, unsigned int* ticket, Fr* out) {
+  __shared__ Fr sh[2 * (SC_THREADS / 32)];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  a = warp_sum_fr(a);
+  b = warp_sum_fr(b);
+  if (lane == 0) { sh[2 * wid] = a; sh[2 * wid + 1] = b; }
+  __syncthreads();
+  if (wid == 0) {
+    Fr x = lane < SC_THREADS / 32 ? sh[2 * lane] : Fr::zero();
+    Fr y = lane < SC_THREADS / 32 ? sh[2 * lane + 1] : Fr::zero();
+    x = warp_sum_fr(x);
+    y = warp_sum_fr(y);
+    if (lane == 0) {
+      store_fr(partials + 2 * blockIdx.x, x);
+      store_fr(partials + 2 * blockIdx.x + 1, y);
+      __threadfence();
+      unsigned int tk = atomicAdd(ticket, 1u);
+      is_last = (tk == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  Fr x = Fr::zero(), y = Fr::zero();
+  for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
+    x = x + load_fr(partials + 2 * k);
+    y = y + load_fr(partials + 2 * k + 1);
+  }
+  x = warp_sum_fr(x);
+  y = warp_sum_fr(y);
+  __syncthreads();
+  if (lane == 0) { sh[2 * wid] = x; sh[2 * wid + 1] = y; }
+  __syncthreads();
+  if (wid == 0) {
+    x = lane < SC_THREADS / 32 ? sh[2 * lane] : Fr::zero();
+    y = lane < SC_THREADS / 32 ? sh[2 * lane + 1] : Fr::zero();
+    x = warp_sum_fr(x);
+    y = warp_sum_fr(y);
+    if (lane == 0) {
+      store_fr(out, x);
+      store_fr(out + 1, y);
+      *ticket = 0;  // re-arm for the next round
+    }
+  }
+}
+
+template <bool TW>
+__device__ __forceinline__ void pair_contrib(Fr& a, Fr& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
+                                             const Fr& twist, const Fr& t) {
+  if (TW) {
+    a = a + (fe * ge) * t;
+    b = b + (fe * go + (ge * fo) * twist) * t;
+  } else {
+    a = a + fe * ge;
+    b = b + (fe * go + ge * fo);
+  }
+}
+
+template <bool TW>
+__global__ void __launch_bounds__(SC_THREADS)
+k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr twist, PowTable tab,
+             Fr* partials, unsigned int* ticket, Fr* out) {
+  const size_t npairs = min((nf + 1) / 2, (ng + 1) / 2);
+  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  Fr a = Fr::zero(), b = Fr::zero();
+  Fr t = Fr::one(), step = Fr::one();
+  if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }  // (twist^2)^SC_THREADS
+#pragma unroll 1
+  for (int k = 0; k < SC_K; k++) {
+    const size_t i = i0 + (size_t)k * SC_THREADS;
+    if (i >= npairs) break;
+    Fr fe = load_fr_or_zero(f, 2 * i, nf), fo = load_fr_or_zero(f, 2 * i + 1, nf);
+    Fr ge = load_fr_or_zero(g, 2 * i, ng), go = load_fr_or_zero(g, 2 * i + 1, ng);
+    pair_contrib<TW>(a, b, fe, fo, ge, go, twist, t);
+    if (TW) t = t * step;
+  }
+  sc_reduce_and_publish(a, b, partials, ticket, out);
+}
+
+// fold by (rf, rg) and message of the folded vectors with the squared twist `twist` (already squared
+// by the host) in one pass.  nf/ng are the lengths BEFORE the fold.
+template <bool TW>
+__global__ void __launch_bounds__(SC_THREADS)
+k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr rf, Fr rg,
+                  Fr* __restrict__ f_out, Fr* __restrict__ g_out, Fr twist, PowTable tab,
+                  Fr* partials, unsigned int* ticket, Fr* out) {
+  const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
+  const size_t npairs = max((nf2 + 1) / 2, (ng2 + 1) / 2);  // every element must be folded
+  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  Fr a = Fr::zero(), b = Fr::zero();
+  Fr t = Fr::one(), step = Fr::one();
+  if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }
+#pragma unroll 1
+  for (int k = 0; k < SC_K; k++) {
+    const size_t i = i0 + (size_t)k * SC_THREADS;
+    if (i >= npairs) break;
+    Fr fe = load_fr_or_zero(f, 4 * i, nf);
+    if (4 * i + 1 < nf) fe = fe + rf * load_fr(f + 4 * i + 1);
+    Fr fo = load_fr_or_zero(f, 4 * i + 2, nf);
+    if (4 * i + 3 < nf) fo = fo + rf * load_fr(f + 4 * i + 3);
+    Fr ge = load_fr_or_zero(g, 4 * i, ng);
+    if (4 * i + 1 < ng) ge = ge + rg * load_fr(g + 4 * i + 1);
+    Fr go = load_fr_or_zero(g, 4 * i + 2, ng);
+    if (4 * i + 3 < ng) go = go + rg * load_fr(g + 4 * i + 3);
+    if (2 * i < nf2) store_fr(f_out + 2 * i, fe);
+    if (2 * i + 1 < nf2) store_fr(f_out + 2 * i + 1, fo);
+    if (2 * i < ng2) store_fr(g_out + 2 * i, ge);
+    if (2 * i + 1 < ng2) store_fr(g_out + 2 * i + 1, go);
+    pair_contrib<TW>(a, b, fe, fo, ge, go, twist, t);
+    if (TW) t = t * step;
+  }
+  sc_reduce_and_publish(a, b, partials, ticket, out);
+}
+
+// splitmix64 counter stream -> Fr elements (the 255-bit value, minus r if needed, is used directly as
+// the Montgomery representative).  tests/util.py holds the numpy restatement.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_fr_random(Fr* __restrict__ out, size_t n, uint64_t seed) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint64_t w = splitmix64(seed + 4 * i + j);
+      v.v[2 * j] = (uint32_t)w;
+      v.v[2 * j + 1] = (uint32_t)(w >> 32);
+    }
+    v.v[7] &= 0x7FFFFFFFu;
+    detail::cond_sub_p<FrParams>(v.v, v.v);
+    store_fr(out + i, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define LAUNCH(ctx, kernel, grid, block, shmem, ...)                \
+  do {                                                              \
+    kernel<<<grid, block, shmem, (ctx)->stream>>>(__VA_ARGS__);     \
+    (ctx)->launches++;                                              \
+  } while (0)
+
+static inline unsigned fold_grid(const gm_ctx* ctx, size_t outputs) {
+  size_t blocks = (outputs + 255) / 256;
+  size_t cap = (size_t)ctx->sm_count * 16;
+  return (unsigned)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+int fr_fold_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& r, Fr* d_out) {
+  if (n == 0) return GM_OK;
+  LAUNCH(ctx, k_fr_fold, fold_grid(ctx, (n + 1) / 2), 256, 0, d_f, n, r, d_out);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_random_dev(gm_ctx* ctx, Fr* d_out, size_t n, uint64_t seed) {
+  if (n == 0) return GM_OK;
+  LAUNCH(ctx, k_fr_random, fold_grid(ctx, n), 256, 0, d_out, n, seed);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+static PowTable make_pow_table(const Fr& twist, size_t npairs) {
+  PowTable tab;
+  Fr x = twist.sqr();
+  int need = 9;  // p[8] is always read as the per-thread step
+  while (need < 40 && (npairs >> need)) need++;
+  for (int k = 0; k < 40; k++) {
+    if (k < need) { tab.p[k] = x; x = x.sqr(); }
+    else tab.p[k] = Fr::one();
+  }
+  return tab;
+}
+
+size_t sc_max_ctas(size_t nf, size_t ng) {
+  size_t npairs = std::max((nf + 1) / 2, (ng + 1) / 2);
+  return std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+}
+
+int sc_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
+                   Fr* d_partials, unsigned int* d_ticket, Fr* d_out) {
+  const size_t npairs = std::min((nf + 1) / 2, (ng + 1) / 2);
+  const unsigned grid = (unsigned)std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+  if (use_twist) {
+    PowTable tab = make_pow_table(twist, npairs);
+    LAUNCH(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, d_partials, d_ticket, d_out);
+  } else {
+    PowTable tab;  // unused
+    LAUNCH(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, d_partials, d_ticket, d_out);
+  }
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
+                        Fr* d_f_out, Fr* d_g_out, const Fr& new_twist, bool use_twist, Fr* d_partials,
+                        unsigned int* d_ticket, Fr* d_out) {
+  const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
+  const size_t npairs = std::max((nf2 + 1) / 2, (ng2 + 1) / 2);
+  const unsigned grid = (unsigned)std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+  if (use_twist) {
+    PowTable tab = make_pow_table(new_twist, npairs);
+    LAUNCH(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab,
+           d_partials, d_ticket, d_out);
+  } else {
+    PowTable tab;
+    LAUNCH(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab,
+           d_partials, d_ticket, d_out);
+  }
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+}  // namespace gm

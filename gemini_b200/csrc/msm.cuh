@@ -1,0 +1,27 @@
+// Internal interface of the MSM pipeline (msm.cu) used by the C ABI layer (api.cu).
+#pragma once
+#include "common.cuh"
+#include "g1.cuh"
+
+namespace gm {
+
+struct MsmPlan {
+  int c;             // window bits
+  int W;             // number of windows = ceil(256 / c)
+  uint32_t nb;       // buckets per window = 2^(c-1) (signed digits)
+  int L;             // buckets per running-sum slice
+  uint32_t nchunks;  // nb / L
+};
+MsmPlan msm_plan(size_t n);
+
+// *d_acc (XYZZ, device) += sum_i scalars[i] * bases[i]; asynchronous on ctx->stream
+int msm_accumulate(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc);
+int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
+int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);
+int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out);
+
+int srs_pack(gm_ctx* ctx, const uint8_t* d_raw, size_t n, size_t stride, long inf_offset, Affine* d_out);
+int srs_fill(gm_ctx* ctx, const Affine& p, size_t n, Affine* d_out);
+int srs_generate(gm_ctx* ctx, size_t n, uint64_t first, Affine* d_out);
+
+}  // namespace gm

@@ -1,0 +1,198 @@
+"""KZG committer keys over the device MSM.
+
+  * :class:`CommitterKey`       - /root/reference/src/kzg/time.rs:24-160 (in-memory, little-endian coefficients)
+  * :class:`CommitterKeyStream` - /root/reference/src/kzg/space.rs:59-297 (big-endian streams, chunked MSM)
+
+The MSMs (the hot path) run on the GPU against the device-resident SRS.  The O(n) scalar preparation
+around them (Horner quotients, division by the vanishing polynomial, linear combinations) is host-side
+bookkeeping in this round - SURVEY.md 8(f) rank 1 lists it as the next tier to move onto the device.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import field
+from .context import Context, Srs, as_fr_array
+from .msm import ChunkedPippenger, HashMapPippenger, VariableBaseMSM, _DeviceStream, msm_chunks
+
+R = field.R
+
+
+def vanishing_polynomial(points: Sequence[int]) -> List[int]:
+    """kzg/mod.rs:262-268 (little-endian coefficients)."""
+    poly = [1]
+    for p in points:
+        nxt = [0] * (len(poly) + 1)
+        for i, c in enumerate(poly):
+            nxt[i] = (nxt[i] - p * c) % R
+            nxt[i + 1] = (nxt[i + 1] + c) % R
+        poly = nxt
+    return poly
+
+
+def _poly_div(f: Sequence[int], z: Sequence[int]) -> List[int]:
+    """DensePolynomial::div by a monic divisor, quotient only (time.rs:142-143)."""
+    f = [x % R for x in f]
+    dz = len(z) - 1
+    if len(f) <= dz:
+        return []
+    q = [0] * (len(f) - dz)
+    for i in range(len(f) - 1, dz - 1, -1):
+        c = f[i]
+        q[i - dz] = c
+        if c:
+            for j, zc in enumerate(z):
+                f[i - dz + j] = (f[i - dz + j] - c * zc) % R
+    return q
+
+
+def _linear_combination(polys: Sequence[Sequence[int]], coeffs: Sequence[int]) -> List[int]:
+    """misc::linear_combination (src/misc.rs:37-48)."""
+    n = max((len(p) for p in polys), default=0)
+    out = [0] * n
+    for p, c in zip(polys, coeffs):
+        for i, v in enumerate(p):
+            out[i] = (out[i] + c * v) % R
+    return out
+
+
+def _powers(x: int, n: int) -> List[int]:
+    out, cur = [], 1
+    for _ in range(n):
+        out.append(cur)
+        cur = cur * x % R
+    return out
+
+
+class CommitterKey:
+    """``CommitterKey<E>``: ``powers_of_g`` resident on the device."""
+
+    def __init__(self, ctx: Context, powers_of_g):
+        self.ctx = ctx
+        self.srs = powers_of_g if isinstance(powers_of_g, Srs) else ctx.srs_load(powers_of_g)
+        self._msm = VariableBaseMSM(ctx)
+
+    def max_degree(self) -> int:
+        return len(self.srs) - 1
+
+    def commit(self, polynomial) -> field.Point:
+        """time.rs:81-83: one MSM against the SRS prefix (silently truncating to the shorter)."""
+        return self._msm.msm_unchecked(self.srs, polynomial)
+
+    def commit_raw(self, polynomial) -> np.ndarray:
+        return self.ctx.msm(self.srs, polynomial)
+
+    def batch_commit(self, polynomials) -> List[field.Point]:
+        """time.rs:98-107."""
+        return [self.commit(p) for p in polynomials]
+
+    def open(self, polynomial: Sequence[int], evaluation_point: int) -> Tuple[int, field.Point]:
+        """time.rs:112-131: synthetic division (Horner) then an MSM over the quotient."""
+        quotient_rev = []
+        prev = 0
+        for c in reversed(list(polynomial)):
+            coeff = (c + prev * evaluation_point) % R
+            quotient_rev.append(coeff)
+            prev = coeff
+        if not quotient_rev:
+            return 0, None
+        quotient = quotient_rev[::-1]
+        return quotient[0], self._msm.msm_unchecked(self.srs, quotient[1:])
+
+    def open_multi_points(self, polynomial: Sequence[int], eval_points: Sequence[int]) -> field.Point:
+        """time.rs:134-145."""
+        return self.commit(_poly_div(polynomial, vanishing_polynomial(eval_points)))
+
+    def batch_open_multi_points(self, polynomials, eval_points: Sequence[int], eval_chal: int) -> field.Point:
+        """time.rs:149-159."""
+        etas = _powers(eval_chal, len(polynomials))
+        return self.open_multi_points(_linear_combination(polynomials, etas), eval_points)
+
+
+def _folded_len(n: int, k: int) -> int:
+    return (n + (1 << k) - 1) >> k
+
+
+class CommitterKeyStream:
+    """``CommitterKeyStream``: the SRS in BIG-endian stream order (``Reverse(powers_of_g)``, space.rs:288-297)."""
+
+    def __init__(self, ctx: Context, powers_of_g_be):
+        self.ctx = ctx
+        if isinstance(powers_of_g_be, Srs):
+            self.srs_be = powers_of_g_be
+        else:
+            self.srs_be = ctx.srs_load(powers_of_g_be)
+
+    @classmethod
+    def from_committer_key(cls, ck: CommitterKey) -> "CommitterKeyStream":
+        le = ck.srs.read()
+        return cls(ck.ctx, np.ascontiguousarray(le[::-1]))
+
+    def __len__(self) -> int:
+        return len(self.srs_be)
+
+    def commit(self, polynomial_be, step: int = 1 << 20) -> field.Point:
+        """space.rs:169-177 -> msm_chunks (space.rs:22-55)."""
+        return msm_chunks(self.ctx, self.srs_be, polynomial_be, step)
+
+    def open(self, polynomial_be: Sequence[int], alpha: int, max_msm_buffer: int) -> Tuple[int, field.Point]:
+        """space.rs:95-125: quotient coefficients stream into the chunked MSM."""
+        poly = [x % R for x in polynomial_be]
+        n, off = len(poly), len(self) - len(poly)
+        st = _DeviceStream(self.ctx, self.srs_be, max(max_msm_buffer, 1))
+        cap = max(max_msm_buffer, 1)
+        prev, buf, start = 0, [], 0
+        for i, scalar in enumerate(poly):
+            buf.append(prev)
+            prev = (prev * alpha + scalar) % R
+            if len(buf) == cap:
+                st.push_range(off + start, buf)
+                start, buf = i + 1, []
+        if buf:
+            st.push_range(off + start, buf)
+        return prev, st.finalize()
+
+    def open_multi_points(self, polynomial_be: Sequence[int], points: Sequence[int], max_msm_buffer: int):
+        """space.rs:128-166: returns (remainder, proof)."""
+        zeros = vanishing_polynomial(points)
+        deg = len(zeros) - 1
+        poly = [x % R for x in polynomial_be]
+        off = len(self) - len(poly) + deg
+        it = iter(poly)
+        state = deque(next(it) for _ in range(len(points)))
+        cap = max(max_msm_buffer, 1)
+        st = _DeviceStream(self.ctx, self.srs_be, cap)
+        buf, start, i = [], 0, 0
+        for coeff in it:
+            qc = state.popleft()
+            state.append(coeff)
+            for k in range(len(points)):
+                state[k] = (state[k] - zeros[deg - k - 1] * qc) % R
+            buf.append(qc)
+            i += 1
+            if len(buf) == cap:
+                st.push_range(off + start, buf)
+                start, buf = i, []
+        if buf:
+            st.push_range(off + start, buf)
+        return list(state), st.finalize()
+
+    def commit_folding(self, polynomials_be, challenges: Sequence[int], max_msm_buffer: int) -> List[field.Point]:
+        """space.rs:192-223.  The reference walks the FoldedPolynomialTree once and feeds one
+        ChunkedPippenger per level; here every level is produced by the device fold chain and committed
+        against the SRS range that lines its low-order end up with g^(tau^0)."""
+        f_le = as_fr_array(polynomials_be)[::-1].copy()
+        k = len(challenges)
+        if k == 0:
+            return []
+        levels = self.ctx.fr_fold_chain(f_le, challenges)
+        out = []
+        for lvl in levels:
+            m = lvl.shape[0]
+            st = _DeviceStream(self.ctx, self.srs_be, max(m, 1))
+            st.push_range(len(self) - m, np.ascontiguousarray(lvl[::-1]))
+            out.append(st.finalize())
+        return out

@@ -1,0 +1,182 @@
+"""ark_ec::VariableBaseMSM, ChunkedPippenger, HashMapPippenger and msm_chunks on the device.
+
+Reference interfaces (paths relative to /root/reference):
+  * ``VariableBaseMSM::{msm_unchecked, msm, msm_bigint}`` - ark-ec 0.4.2 (Cargo.lock:44-46), called at
+    src/kzg/time.rs:82,129 and src/kzg/space.rs:52; written spec src/kzg/msm/variable_base.rs:95-177
+  * ``ChunkedPippenger`` / ``HashMapPippenger`` - spec src/kzg/msm/stream_pippenger.rs:143-271
+  * ``msm_chunks`` - src/kzg/space.rs:22-55
+
+Scalars are Python ints (canonical) or (n,4) uint64 Montgomery limb arrays; bases are a device-resident
+:class:`Srs`, a sequence of oracle-style points ((x, y) | None) or an (n,12) uint64 limb array.
+Results are affine points ((x, y) | None) - the canonical form of the parity rule.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import field
+from ._lib import check, lib
+from .context import Context, Srs, _ptr, as_fr_array
+
+
+def _len_bases(bases) -> int:
+    return len(bases) if not isinstance(bases, np.ndarray) else bases.reshape(-1, 12).shape[0]
+
+
+class VariableBaseMSM:
+    """Mirror of the ``VariableBaseMSM`` trait for BLS12-381 G1."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def msm_unchecked(self, bases, scalars) -> field.Point:
+        """Silently truncates to the shorter input (relied on by CommitterKey::commit, time.rs:82)."""
+        return field.jacobian_to_affine(self.msm_unchecked_raw(bases, scalars))
+
+    def msm_unchecked_raw(self, bases, scalars, bigint: bool = False) -> np.ndarray:
+        if isinstance(bases, Srs):
+            return self.ctx.msm(bases, scalars, bigint=bigint)
+        return self.ctx.msm_hostbases(bases, scalars, bigint=bigint)
+
+    def msm(self, bases, scalars):
+        """``Result<G1, usize>``: ("ok", point) or ("err", min_len) on a length mismatch."""
+        sarr = as_fr_array(scalars)
+        nb = _len_bases(bases)
+        if nb != sarr.shape[0]:
+            if isinstance(bases, Srs):
+                tag, val = self.ctx.msm_checked(bases, nb, sarr)
+                assert tag == "err"
+                return (tag, val)
+            return ("err", min(nb, sarr.shape[0]))
+        return ("ok", self.msm_unchecked(bases, sarr))
+
+    def msm_bigint(self, bases, bigints) -> field.Point:
+        return field.jacobian_to_affine(self.msm_unchecked_raw(bases, as_fr_array(bigints, montgomery=False), bigint=True))
+
+
+class _DeviceStream:
+    """gm_msm_stream handle: device-resident accumulator fed chunk by chunk."""
+
+    def __init__(self, ctx: Context, srs: Optional[Srs], chunk_cap: int):
+        self.ctx = ctx
+        self.srs = srs
+        h = C.c_void_p()
+        check(lib.gm_msm_stream_new(ctx._h, srs._h if srs is not None else None, chunk_cap, C.byref(h)))
+        self._h = h
+
+    def push_range(self, base_offset: int, scalars, bigint: bool = False) -> None:
+        if hasattr(scalars, "data_ptr"):
+            m = scalars.numel() * scalars.element_size() // 32
+            check(lib.gm_msm_stream_push(self._h, None, 0, -1, base_offset, _ptr(scalars), m, int(bigint)))
+            return
+        arr = as_fr_array(scalars, montgomery=not bigint)
+        check(lib.gm_msm_stream_push(self._h, None, 0, -1, base_offset, _ptr(arr), arr.shape[0], int(bigint)))
+
+    def push_points(self, points, scalars, bigint: bool = False) -> None:
+        parr = points if isinstance(points, np.ndarray) else field.g1_to_limbs(points)
+        parr = np.ascontiguousarray(parr.reshape(-1, 12))
+        sarr = as_fr_array(scalars, montgomery=not bigint)
+        m = min(parr.shape[0], sarr.shape[0])
+        check(lib.gm_msm_stream_push(self._h, _ptr(parr), 96, -1, 0, _ptr(sarr), m, int(bigint)))
+
+    def finalize_raw(self) -> np.ndarray:
+        out = np.empty(18, dtype=np.uint64)
+        check(lib.gm_msm_stream_finalize(self._h, _ptr(out)))
+        return out
+
+    def finalize(self) -> field.Point:
+        return field.jacobian_to_affine(self.finalize_raw())
+
+    def free(self) -> None:
+        if self._h:
+            lib.gm_msm_stream_free(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ChunkedPippenger:
+    """stream_pippenger.rs:209-271: buffer (base, scalar) pairs, run one MSM per full buffer.
+
+    A ``buf_size`` of 0 flushes only at ``finalize`` (snark/tests.rs:18 passes 20 / n_levels == 0)."""
+
+    def __init__(self, ctx: Context, buf_size: int):
+        self.ctx = ctx
+        self.buf_size = buf_size
+        self._stream = _DeviceStream(ctx, None, max(buf_size, 1))
+        self._bases: list = []
+        self._scalars: list = []
+
+    @classmethod
+    def with_size(cls, ctx: Context, buf_size: int) -> "ChunkedPippenger":
+        return cls(ctx, buf_size)
+
+    def _flush(self) -> None:
+        if self._scalars:
+            self._stream.push_points(self._bases, self._scalars)
+            self._bases, self._scalars = [], []
+
+    def add(self, base: field.Point, scalar: int) -> None:
+        self._scalars.append(scalar)
+        self._bases.append(base)
+        if len(self._scalars) == self.buf_size:
+            self._flush()
+
+    def finalize(self) -> field.Point:
+        self._flush()
+        return self._stream.finalize()
+
+
+class HashMapPippenger:
+    """stream_pippenger.rs:143-206: scalars of identical bases are merged (added in Fr) before the MSM."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.ctx = ctx
+        self.capacity = max(capacity, 1)
+        self._stream = _DeviceStream(ctx, None, self.capacity)
+        self._buf: dict = {}
+
+    def _flush(self) -> None:
+        if self._buf:
+            bases = list(self._buf.keys())
+            self._stream.push_points(bases, [self._buf[b] for b in bases])
+            self._buf = {}
+
+    def add(self, base: field.Point, scalar: int) -> None:
+        self._buf[base] = (self._buf.get(base, 0) + scalar) % field.R
+        if len(self._buf) == self.capacity:
+            self._flush()
+
+    def finalize(self) -> field.Point:
+        self._flush()
+        return self._stream.finalize()
+
+
+def msm_chunks(ctx: Context, bases_stream, scalars_stream, step: int = 1 << 20) -> field.Point:
+    """src/kzg/space.rs:22-55.  Both streams are BIG-endian (highest degree first); the leading
+    ``len(bases) - len(scalars)`` bases are skipped; one pipelined device chunk per ``step`` scalars.
+
+    ``bases_stream`` may be an :class:`Srs` holding the bases in stream order."""
+    nb = _len_bases(bases_stream)
+    sarr = as_fr_array(scalars_stream)
+    ns = sarr.shape[0]
+    assert ns <= nb, "scalars stream longer than the bases stream"  # space.rs:30 assert
+    off = nb - ns
+    if isinstance(bases_stream, Srs):
+        st = _DeviceStream(ctx, bases_stream, step)
+        for s in range(0, ns, step):
+            st.push_range(off + s, sarr[s:s + step])
+    else:
+        parr = bases_stream if isinstance(bases_stream, np.ndarray) else field.g1_to_limbs(bases_stream)
+        parr = parr.reshape(-1, 12)
+        st = _DeviceStream(ctx, None, step)
+        for s in range(0, ns, step):
+            st.push_points(parr[off + s: off + s + step], sarr[s:s + step])
+    return st.finalize()

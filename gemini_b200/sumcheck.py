@@ -1,0 +1,243 @@
+"""Sumcheck provers on the device: trait ``Prover`` (/root/reference/src/subprotocols/sumcheck/prover.rs:30-45).
+
+  * :class:`TimeProver`        - sumcheck/time_prover.rs:42-137
+  * :class:`HerringTimeProver` - herring/time_prover.rs:44-137 over ``FModule`` (herring/module.rs:127-146)
+  * :class:`SpaceProver`       - sumcheck/space_prover.rs:38-266.  B200-first: a 2^28-element Fr stream is
+    8 GiB and fits in HBM many times over, so the "space" prover keeps the folded vectors resident and
+    folds once per round instead of re-streaming and re-folding the whole input every round; it keeps
+    the reference's observable behaviour (big-endian inputs, rounds from the MIN length, stream
+    alignment, final foldings taken from the head of the stream).
+  * :class:`ElasticProver`     - sumcheck/elastic_prover.rs:29-79
+  * :class:`Sumcheck`          - the Fiat-Shamir driver, sumcheck/proof.rs:36-66
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import field
+from ._lib import check, lib
+from .context import Context, _ptr, as_fr_array
+
+GEMINI_TIME, HERRING_F = 0, 1
+
+
+def ark_log2(x: int) -> int:
+    return 0 if x <= 1 else (x - 1).bit_length()
+
+
+def fold_polynomial(ctx: Context, f, r: int) -> List[int]:
+    """misc::fold_polynomial (src/misc.rs:52-56) / herring split_fold."""
+    return field.fr_from_limbs(ctx.fr_fold(f, r))
+
+
+class _DeviceProver:
+    def __init__(self, ctx: Context, f, g, twist: int, flavour: int):
+        self.ctx = ctx
+        if hasattr(f, "data_ptr") and f.is_cuda:
+            nf = f.numel() * f.element_size() // 32
+            ng = g.numel() * g.element_size() // 32
+            tw = field.fr_to_limbs([twist])
+            h = C.c_void_p()
+            check(lib.gm_sumcheck_new_dev(ctx._h, _ptr(f), nf, _ptr(g), ng, _ptr(tw), flavour, C.byref(h)))
+        else:
+            fa = f if hasattr(f, "data_ptr") else as_fr_array(f)
+            ga = g if hasattr(g, "data_ptr") else as_fr_array(g)
+            nf = fa.shape[0] if isinstance(fa, np.ndarray) else fa.numel() * fa.element_size() // 32
+            ng = ga.shape[0] if isinstance(ga, np.ndarray) else ga.numel() * ga.element_size() // 32
+            tw = field.fr_to_limbs([twist])
+            h = C.c_void_p()
+            check(lib.gm_sumcheck_new(ctx._h, _ptr(fa), nf, _ptr(ga), ng, _ptr(tw), flavour, C.byref(h)))
+        self._h = h
+
+    # -- trait Prover ------------------------------------------------------------------------
+    def next_message_raw(self, verifier_message) -> Optional[np.ndarray]:
+        out = np.empty(8, dtype=np.uint64)
+        has = C.c_int(0)
+        ch = None if verifier_message is None else as_fr_array(
+            [verifier_message] if isinstance(verifier_message, int) else verifier_message)
+        check(lib.gm_sumcheck_next_message(self._h, _ptr(ch), _ptr(out), C.byref(has)))
+        return out if has.value else None
+
+    def next_message(self, verifier_message: Optional[int]) -> Optional[Tuple[int, int]]:
+        raw = self.next_message_raw(verifier_message)
+        if raw is None:
+            return None
+        a, b = field.fr_from_limbs(raw)
+        return (a, b)
+
+    def fold(self, r: int) -> None:
+        check(lib.gm_sumcheck_fold(self._h, _ptr(field.fr_to_limbs([r]))))
+
+    def rounds(self) -> int:
+        return int(lib.gm_sumcheck_rounds(self._h))
+
+    def round(self) -> int:
+        return int(lib.gm_sumcheck_round(self._h))
+
+    @property
+    def tot_rounds(self) -> int:
+        return self.rounds()
+
+    def final_foldings(self) -> Optional[Tuple[int, int]]:
+        out = np.empty(8, dtype=np.uint64)
+        has = C.c_int(0)
+        check(lib.gm_sumcheck_final_foldings(self._h, _ptr(out), C.byref(has)))
+        if not has.value:
+            return None
+        a, b = field.fr_from_limbs(out)
+        return (a, b)
+
+    # -- inspection --------------------------------------------------------------------------
+    def lengths(self) -> Tuple[int, int]:
+        nf, ng = C.c_size_t(0), C.c_size_t(0)
+        check(lib.gm_sumcheck_read_state(self._h, None, C.byref(nf), None, C.byref(ng), None))
+        return int(nf.value), int(ng.value)
+
+    def state(self):
+        """(f, g, twist) of the current round as Python ints (tests, elastic hand-off)."""
+        nf, ng = self.lengths()
+        f = np.empty((nf, 4), dtype=np.uint64)
+        g = np.empty((ng, 4), dtype=np.uint64)
+        tw = np.empty(4, dtype=np.uint64)
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.gm_sumcheck_read_state(self._h, _ptr(f), C.byref(a), _ptr(g), C.byref(b), _ptr(tw)))
+        return field.fr_from_limbs(f), field.fr_from_limbs(g), field.fr_from_limbs(tw)[0]
+
+    def free(self) -> None:
+        if self._h:
+            lib.gm_sumcheck_free(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class TimeProver(_DeviceProver):
+    """sumcheck/time_prover.rs: rounds = ceil(log2(max(|f|,|g|))), twist in fold AND message."""
+
+    def __init__(self, ctx: Context, f, g, twist: int = 1):
+        super().__init__(ctx, f, g, twist, GEMINI_TIME)
+
+
+class HerringTimeProver(_DeviceProver):
+    """herring/time_prover.rs with FModule: rounds from the MIN length, twist only in ``fold``."""
+
+    def __init__(self, ctx: Context, f, g, twist: int = 1):
+        super().__init__(ctx, f, g, twist, HERRING_F)
+
+
+class SpaceProver(_DeviceProver):
+    """sumcheck/space_prover.rs: inputs are BIG-endian streams (highest-degree coefficient first)."""
+
+    def __init__(self, ctx: Context, f_be, g_be, twist: int = 1):
+        fa = as_fr_array(f_be)[::-1].copy()
+        ga = as_fr_array(g_be)[::-1].copy()
+        super().__init__(ctx, fa, ga, twist, GEMINI_TIME)
+        # required_rounds uses the MIN length (space_prover.rs:76-79)
+        check(lib.gm_sumcheck_set_rounds(self._h, 0, ark_log2(min(fa.shape[0], ga.shape[0]))))
+
+    def _check_alignment(self, fold_first: bool) -> None:
+        """The reference aligns the two folded streams (space_prover.rs:142-174) and asserts equal pair
+        counts (:173); inputs on which it panics are rejected here instead of answered differently."""
+        nf, ng = self.lengths()
+        if fold_first:
+            nf, ng = (nf + 1) // 2, (ng + 1) // 2
+        if nf == ng:
+            return
+        if nf > ng:
+            nf -= nf - ng + (ng % 2)
+        else:
+            ng -= ng - nf + (nf % 2)
+        assert nf >= 1 and ng >= 1, "stream exhausted during alignment (reference panics: unwrap on None)"
+        f_pairs = (nf - 2 + nf % 2) // 2
+        g_pairs = (ng - 2 + ng % 2) // 2
+        assert f_pairs == g_pairs, "assert_eq!(f_pairs, g_pairs) fails in the reference"
+
+    def next_message_raw(self, verifier_message):
+        if self.round() < self.rounds():
+            self._check_alignment(verifier_message is not None)
+        return super().next_message_raw(verifier_message)
+
+    def final_foldings(self):
+        if self.round() != self.rounds():
+            return None
+        f, g, _ = self.state()
+        if not f or not g:
+            return None
+        return (f[-1], g[-1])  # head of the big-endian folded streams (space_prover.rs:260-266)
+
+
+class ElasticProver:
+    """sumcheck/elastic_prover.rs:29-79.  ``next_message`` always delegates to the wrapped prover (so,
+    as in the reference, the Space->Time switch only happens through an explicit ``fold`` call)."""
+
+    def __init__(self, ctx: Context, f_be, g_be, twist: int = 1, threshold: int = 22):
+        self.p = SpaceProver(ctx, f_be, g_be, twist)
+        self.is_space = True
+        self.threshold = threshold  # SPACE_TIME_THRESHOLD, src/lib.rs:76
+
+    def fold(self, r: int) -> None:
+        if self.is_space and self.p.rounds() - self.p.round() < self.threshold:
+            # From<&SpaceProver> for TimeProver (space_prover.rs:269-307): the folded vectors are already
+            # resident in little-endian order; only the Time semantics of final_foldings change.
+            self.p.__class__ = TimeProver
+            self.is_space = False
+        self.p.fold(r)
+
+    def next_message(self, verifier_message):
+        return self.p.next_message(verifier_message)
+
+    def rounds(self) -> int:
+        return self.p.rounds()
+
+    def round(self) -> int:
+        return self.p.round()
+
+    @property
+    def tot_rounds(self) -> int:
+        return self.p.rounds()
+
+    def final_foldings(self):
+        return self.p.final_foldings()
+
+
+class Sumcheck:
+    """proof.rs:13-66.  The transcript is abstracted as ``challenge_fn(message) -> challenge``."""
+
+    def __init__(self, messages, challenges, rounds, final_foldings):
+        self.messages = messages
+        self.challenges = challenges
+        self.rounds = rounds
+        self.final_foldings = final_foldings
+
+    @classmethod
+    def prove(cls, prover, challenge_fn: Callable[[Tuple[int, int]], int]) -> "Sumcheck":
+        messages, challenges = [], []
+        vm = None
+        while True:
+            msg = prover.next_message(vm)
+            if msg is None:
+                break
+            ch = challenge_fn(msg) % field.R
+            vm = ch
+            messages.append(msg)
+            challenges.append(ch)
+        return cls(messages, challenges, prover.rounds(), [prover.final_foldings()])
+
+    @classmethod
+    def new_time(cls, ctx: Context, challenge_fn, f, g, twist: int) -> "Sumcheck":
+        return cls.prove(TimeProver(ctx, f, g, twist), challenge_fn)
+
+    @classmethod
+    def new_space(cls, ctx: Context, challenge_fn, f_be, g_be, twist: int) -> "Sumcheck":
+        return cls.prove(SpaceProver(ctx, f_be, g_be, twist), challenge_fn)
+
+    @classmethod
+    def new_elastic(cls, ctx: Context, challenge_fn, f_be, g_be, twist: int) -> "Sumcheck":
+        return cls.prove(ElasticProver(ctx, f_be, g_be, twist), challenge_fn)

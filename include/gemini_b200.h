@@ -1,0 +1,157 @@
+/* gemini_b200 - C ABI of the B200-native Gemini prover hot path.
+ *
+ * This header is the drop-in boundary.  The reference (arkworks-rs/gemini @ 844a85e5)
+ * has no FFI of its own: its seams are Rust traits and inherent methods.  Each entry
+ * point below names the reference interface it replaces (paths relative to
+ * /root/reference); INTEGRATION.md shows the Rust `extern "C"` block and the wrapper
+ * types that bind them to ark_ec::VariableBaseMSM / sumcheck::Prover.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a GM_ERR_* code; nothing unwinds;
+ *    gm_last_error() returns a thread-local description of the last failure.
+ *  - field elements are little-endian u64 limbs in MONTGOMERY form exactly as
+ *    arkworks' Fp<MontBackend,N> stores them: Fr = 4 limbs (32 B), Fq = 6 limbs (48 B).
+ *  - an affine G1 point is x | y (96 B).  The identity is flagged either by a byte at
+ *    `inf_offset` inside each record (arkworks' repr: stride 104, flag at 96) or by
+ *    x = y = 0 when inf_offset < 0.
+ *  - a projective G1 result is Jacobian X | Y | Z (18 limbs, 144 B) = arkworks'
+ *    short_weierstrass::Projective.  Results are returned NORMALISED (Z = 1, identity
+ *    = (1,1,0)), so equal group elements are equal byte strings.
+ *  - host pointers unless the name ends in _dev (device pointers of the ctx's GPU).
+ *  - handles are opaque; distinct handles may be used concurrently from different
+ *    host threads (sumcheck provers are driven from rayon workers in
+ *    src/subprotocols/sumcheck/proof.rs:85); one handle is never shared mutably.
+ *  - there is no CPU fallback: without a CUDA device gm_init fails with GM_ERR_CUDA.
+ */
+#ifndef GEMINI_B200_H
+#define GEMINI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK 0
+#define GM_ERR_CUDA 1      /* CUDA runtime failure (see gm_last_error) */
+#define GM_ERR_ARG 2       /* invalid argument */
+#define GM_ERR_LENGTH 3    /* gm_msm_g1_checked: bases/scalars length mismatch (== Err(min_len)) */
+#define GM_ERR_STATE 4     /* call not valid in the handle's state (e.g. next_message past the last round) */
+#define GM_ERR_OOM 5
+
+typedef struct gm_ctx gm_ctx;
+typedef struct gm_srs gm_srs;
+typedef struct gm_msm_stream gm_msm_stream;
+typedef struct gm_sumcheck gm_sumcheck;
+
+/* ---- context ---------------------------------------------------------------------- */
+int gm_init(int device_id, gm_ctx** out_ctx);
+int gm_shutdown(gm_ctx* ctx);
+const char* gm_last_error(void);
+int gm_abi_version(void);
+/* number of kernels this library has launched on this ctx since gm_init (bench gpu_launches) */
+uint64_t gm_launch_count(const gm_ctx* ctx);
+/* device elapsed ms of the last gm_msm_* / gm_sumcheck_* call, by CUDA events on the ctx stream;
+ * phase 0 = whole call; for MSM calls 1 = digits + counting sort + work list, 2 = k_accumulate (the
+ * dominant kernel), 3 = split combine + bucket reduction + finish */
+float gm_last_device_ms(const gm_ctx* ctx, int phase);
+int gm_device_synchronize(gm_ctx* ctx);
+/* CUDA-event stopwatch on the ctx stream (the stream every kernel of this library is launched on)
+ * and an L2 flush (writes a 256 MB scratch buffer) - measurement helpers for bench.py */
+int gm_timer_start(gm_ctx* ctx);
+int gm_timer_stop(gm_ctx* ctx, float* out_ms);
+int gm_l2_flush(gm_ctx* ctx);
+
+/* ---- SRS (CommitterKey::powers_of_g, src/kzg/time.rs:24-27, resident on the device) ---- */
+int gm_srs_load_g1(gm_ctx* ctx, const void* points, size_t n, size_t stride_bytes, long inf_offset,
+                   gm_srs** out_srs);
+/* synthetic bases P_i = [first_multiple + i] * G generated on the device (bench / tests) */
+int gm_srs_generate_g1(gm_ctx* ctx, size_t n, uint64_t first_multiple, gm_srs** out_srs);
+/* n copies of one point: DummyStreamer(G1::generator(), n), examples/snark.rs:62-65 */
+int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** out_srs);
+size_t gm_srs_len(const gm_srs* srs);
+int gm_srs_read(gm_ctx* ctx, const gm_srs* srs, size_t offset, size_t n, uint64_t* out_xy /* n*12 */);
+int gm_srs_free(gm_srs* srs);
+
+/* ---- MSM: ark_ec::VariableBaseMSM (called at src/kzg/time.rs:82,129; src/kzg/space.rs:52) ---- */
+/* msm_unchecked / msm_bigint: sum_{i<n} scalars[i] * srs[base_offset + i].
+ * n is clamped to the bases available (min(len) truncation of msm_unchecked).
+ * scalars_are_bigint = 0: Montgomery Fr (msm_unchecked); 1: canonical BigInt<4> (msm_bigint). */
+int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+              int scalars_are_bigint, uint64_t out_jacobian[18]);
+int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
+                  int scalars_are_bigint, uint64_t out_jacobian[18]);
+/* VariableBaseMSM::msm: returns GM_ERR_LENGTH and *out_min_len = min(lens) on a length mismatch */
+int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t bases_len,
+                      const uint64_t* scalars, size_t scalars_len, uint64_t out_jacobian[18],
+                      size_t* out_min_len);
+/* ad-hoc bases supplied with the call (herring/module.rs:100, kzg/mod.rs:163) */
+int gm_msm_g1_hostbases(gm_ctx* ctx, const void* points, size_t stride_bytes, long inf_offset,
+                        const uint64_t* scalars, size_t n, int scalars_are_bigint, uint64_t out_jacobian[18]);
+
+/* ---- streamed MSM: msm_chunks (src/kzg/space.rs:22-55) and ChunkedPippenger
+ *      (src/kzg/msm/stream_pippenger.rs:209-271).  The accumulator stays on the device;
+ *      each push is one pipelined chunk; finalize performs the single 144-byte D2H. ---- */
+int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, gm_msm_stream** out);
+/* points == NULL: bases are srs[base_offset .. base_offset+m) ; else m ad-hoc points */
+int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes, long inf_offset,
+                       size_t base_offset, const uint64_t* scalars, size_t m, int scalars_are_bigint);
+int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]);
+int gm_msm_stream_free(gm_msm_stream* s);
+
+/* sum of k Jacobian points (combine of per-GPU partial accumulators after the all-gather) */
+int gm_g1_sum(gm_ctx* ctx, const uint64_t* jacobians /* k*18 */, size_t k, uint64_t out_jacobian[18]);
+
+/* ---- Fr folds: misc::fold_polynomial (src/misc.rs:52-56), herring split_fold
+ *      (src/herring/time_prover.rs:72-76), tensorcheck::foldings_polynomial
+ *      (src/subprotocols/tensorcheck/mod.rs:124-133) ---- */
+/* out[i] = f[2i] + r * f[2i+1], i < ceil(n/2); a missing odd element is zero */
+int gm_fr_fold(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t r[4], uint64_t* out);
+int gm_fr_fold_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t r[4], void* out_dev);
+/* k successive folds by challenges[0..k); level j (1-based) has ceil(n / 2^j) elements and is
+ * written at out + level_offset(j) elements, levels concatenated in order 1..k */
+int gm_fr_fold_chain(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t* challenges, size_t k,
+                     uint64_t* out_levels);
+/* total number of Fr elements gm_fr_fold_chain writes */
+size_t gm_fr_fold_chain_len(size_t n, size_t k);
+
+/* ---- sumcheck provers: trait Prover (src/subprotocols/sumcheck/prover.rs:30-45) ---- */
+#define GM_SUMCHECK_GEMINI_TIME 0 /* TimeProver, sumcheck/time_prover.rs:42-137: rounds from max len, twisted message */
+#define GM_SUMCHECK_HERRING_F 1   /* herring TimeProver<FModule>, herring/time_prover.rs:44-137: rounds from min len */
+int gm_sumcheck_new(gm_ctx* ctx, const uint64_t* f, size_t f_len, const uint64_t* g, size_t g_len,
+                    const uint64_t twist[4], int flavour, gm_sumcheck** out);
+int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void* g_dev, size_t g_len,
+                        const uint64_t twist[4], int flavour, gm_sumcheck** out);
+/* next_message(Option<F>): challenge may be NULL (first call).  *out_has_msg = 0 <=> None. */
+int gm_sumcheck_next_message(gm_sumcheck* p, const uint64_t* challenge_or_null, uint64_t out_ab[8],
+                             int* out_has_msg);
+int gm_sumcheck_fold(gm_sumcheck* p, const uint64_t r[4]);
+size_t gm_sumcheck_rounds(const gm_sumcheck* p);
+size_t gm_sumcheck_round(const gm_sumcheck* p);
+/* override the round counters (From<&SpaceProver> for TimeProver, space_prover.rs:269-307) */
+int gm_sumcheck_set_rounds(gm_sumcheck* p, size_t round, size_t tot_rounds);
+int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has);
+/* copy out the current (folded) vectors - used by tests and by the elastic hand-off */
+int gm_sumcheck_read_state(gm_sumcheck* p, uint64_t* out_f, size_t* f_len, uint64_t* out_g, size_t* g_len,
+                           uint64_t out_twist[4]);
+int gm_sumcheck_free(gm_sumcheck* p);
+
+/* ---- raw device buffers for callers that keep vectors resident (bench, pipelines) ---- */
+int gm_dev_alloc(gm_ctx* ctx, size_t bytes, void** out_dev);
+int gm_dev_free(gm_ctx* ctx, void* dev);
+int gm_dev_upload(gm_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int gm_dev_download(gm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* fill a device buffer with n pseudo-random canonical-range Fr elements in Montgomery form
+ * (splitmix64 counter stream; bench / full-size property tests) */
+int gm_fr_random_dev(gm_ctx* ctx, void* out_dev, size_t n, uint64_t seed);
+
+/* ---- self-test kernels (parity tests of the device field / curve arithmetic) ---- */
+/* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 sqr;  field: 0 = Fq (12 u32), 1 = Fr (8 u32) */
+int gm_selftest_field(gm_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, size_t n);
+/* op: 0 xyzz += affine, 1 xyzz += -affine, 2 xyzz += xyzz, 3 xyzz = 2*xyzz; out = normalised Jacobian (36 u32) */
+int gm_selftest_curve(gm_ctx* ctx, int op, const uint32_t* acc_xyzz, const uint32_t* other, uint32_t* out_jac, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMINI_B200_H */

@@ -1,0 +1,813 @@
+"""Pure-Python big-integer ground truth for the Gemini prover hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is imported, linked or
+executed by the product (``gemini_b200/``); only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may use it, and there only as the checker / timed baseline.
+
+Every function restates a routine of the reference (arkworks-rs/gemini @
+844a85e5, paths relative to /root/reference) with Python integers:
+
+* field / curve arithmetic: BLS12-381 as pinned by ``Cargo.lock:44-46,62-64``
+  (ark-ec / ark-ff 0.4.2, NOT vendored in the reference tree).  The published
+  curve is restated here: y^2 = x^3 + 4 over Fq, prime-order subgroup r.
+* MSM: ``src/kzg/msm/variable_base.rs:16-177`` (orphan copy of arkworks'
+  signed-digit windowed Pippenger), chunking ``src/kzg/space.rs:22-55`` and
+  ``src/kzg/msm/stream_pippenger.rs:143-271``.
+* folds / sumcheck: ``src/misc.rs:52-56``, ``src/subprotocols/sumcheck/
+  {time_prover.rs:75-137, space_prover.rs:117-307, streams.rs:69-229,
+  elastic_prover.rs:44-57, subclaim.rs:77-97}``, herring
+  ``src/herring/time_prover.rs:72-137`` and ``src/misc.rs:235-266``.
+* KZG callers: ``src/kzg/time.rs:81-159`` and ``src/kzg/space.rs:95-285``.
+
+Parity status: the Fr paths are pinned by the reference's own known-answer
+tests (see tests/test_oracle_kats.py).  For the MSM *value* the reference
+holds no golden vector - "parity unpinned" at the
+ark-ec boundary; the oracle of record is the naive sum of scalar multiples
+below, whose group law is self-checked (generator on curve, [r]G = O).
+
+Representation: field elements are plain ``int`` in canonical form; a G1 point
+is ``None`` (identity) or an ``(x, y)`` tuple of canonical ints.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+# --------------------------------------------------------------------------
+# BLS12-381 parameters (ark-bls12-381 0.4.0 / ark-test-curves 0.4.2)
+# --------------------------------------------------------------------------
+Q = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+B_COEFF = 4
+GX = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
+GY = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
+G1_GEN = (GX, GY)
+
+FQ_LIMBS64 = 6
+FR_LIMBS64 = 4
+FQ_RBITS = 384
+FR_RBITS = 256
+FQ_MONT_R = (1 << FQ_RBITS) % Q
+FR_MONT_R = (1 << FR_RBITS) % R
+FQ_MONT_R2 = (FQ_MONT_R * FQ_MONT_R) % Q
+FR_MONT_R2 = (FR_MONT_R * FR_MONT_R) % R
+FQ_INV64 = (-pow(Q, -1, 1 << 64)) % (1 << 64)
+FR_INV64 = (-pow(R, -1, 1 << 64)) % (1 << 64)
+FR_MODULUS_BITS = 255
+
+Point = Optional[Tuple[int, int]]
+
+
+# --------------------------------------------------------------------------
+# Montgomery <-> canonical, limb packing (the in-memory form arkworks holds)
+# --------------------------------------------------------------------------
+def fr_to_mont(x: int) -> int:
+    return (x << FR_RBITS) % R
+
+
+def fr_from_mont(x: int) -> int:
+    return (x * pow(1 << FR_RBITS, -1, R)) % R
+
+
+def fq_to_mont(x: int) -> int:
+    return (x << FQ_RBITS) % Q
+
+
+def fq_from_mont(x: int) -> int:
+    return (x * pow(1 << FQ_RBITS, -1, Q)) % Q
+
+
+def int_to_limbs(x: int, n: int) -> List[int]:
+    return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
+
+
+def limbs_to_int(limbs: Sequence[int]) -> int:
+    v = 0
+    for i, l in enumerate(limbs):
+        v |= int(l) << (64 * i)
+    return v
+
+
+# --------------------------------------------------------------------------
+# G1 group law (affine, canonical ints).  Complete: handles identity, P+P, P-P.
+# --------------------------------------------------------------------------
+def g1_is_on_curve(p: Point) -> bool:
+    if p is None:
+        return True
+    x, y = p
+    return (y * y - (x * x * x + B_COEFF)) % Q == 0
+
+
+def g1_neg(p: Point) -> Point:
+    if p is None:
+        return None
+    return (p[0], (-p[1]) % Q)
+
+
+def g1_double(p: Point) -> Point:
+    if p is None:
+        return None
+    x, y = p
+    if y == 0:
+        return None
+    lam = (3 * x * x) * pow(2 * y, -1, Q) % Q
+    x3 = (lam * lam - 2 * x) % Q
+    y3 = (lam * (x - x3) - y) % Q
+    return (x3, y3)
+
+
+def g1_add(p: Point, q: Point) -> Point:
+    if p is None:
+        return q
+    if q is None:
+        return p
+    x1, y1 = p
+    x2, y2 = q
+    if x1 == x2:
+        if (y1 + y2) % Q == 0:
+            return None
+        return g1_double(p)
+    lam = (y2 - y1) * pow(x2 - x1, -1, Q) % Q
+    x3 = (lam * lam - x1 - x2) % Q
+    y3 = (lam * (x1 - x3) - y1) % Q
+    return (x3, y3)
+
+
+# Jacobian arithmetic for speed in the larger oracle cases (result normalised
+# by the caller, so representation never leaks).
+def _jac_double(p):
+    x, y, z = p
+    if z == 0:
+        return p
+    a = x * x % Q
+    b = y * y % Q
+    c = b * b % Q
+    d = 2 * ((x + b) * (x + b) - a - c) % Q
+    e = 3 * a % Q
+    f = e * e % Q
+    x3 = (f - 2 * d) % Q
+    y3 = (e * (d - x3) - 8 * c) % Q
+    z3 = 2 * y * z % Q
+    return (x3, y3, z3)
+
+
+def _jac_add(p, q):
+    x1, y1, z1 = p
+    x2, y2, z2 = q
+    if z1 == 0:
+        return q
+    if z2 == 0:
+        return p
+    z1z1 = z1 * z1 % Q
+    z2z2 = z2 * z2 % Q
+    u1 = x1 * z2z2 % Q
+    u2 = x2 * z1z1 % Q
+    s1 = y1 * z2 * z2z2 % Q
+    s2 = y2 * z1 * z1z1 % Q
+    if u1 == u2:
+        if s1 == s2:
+            return _jac_double(p)
+        return (1, 1, 0)
+    h = (u2 - u1) % Q
+    i = (2 * h) * (2 * h) % Q
+    j = h * i % Q
+    r = 2 * (s2 - s1) % Q
+    v = u1 * i % Q
+    x3 = (r * r - j - 2 * v) % Q
+    y3 = (r * (v - x3) - 2 * s1 * j) % Q
+    z3 = ((z1 + z2) * (z1 + z2) - z1z1 - z2z2) * h % Q
+    return (x3, y3, z3)
+
+
+def _to_jac(p: Point):
+    return (1, 1, 0) if p is None else (p[0], p[1], 1)
+
+
+def _from_jac(p) -> Point:
+    x, y, z = p
+    if z == 0:
+        return None
+    zi = pow(z, -1, Q)
+    zi2 = zi * zi % Q
+    return (x * zi2 % Q, y * zi2 * zi % Q)
+
+
+def jac_to_affine(x: int, y: int, z: int) -> Point:
+    """Canonicalise a Jacobian triple (canonical ints) - the parity rule of SURVEY 8(d)."""
+    return _from_jac((x % Q, y % Q, z % Q))
+
+
+def g1_mul(p: Point, k: int) -> Point:
+    """Double-and-add k*P (``mul_bigint`` in the reference's naive test oracle,
+    src/kzg/msm/variable_base.rs:183-194)."""
+    if p is None or k == 0:
+        return None
+    acc = (1, 1, 0)
+    base = _to_jac(p)
+    for bit in bin(k)[2:]:
+        acc = _jac_double(acc)
+        if bit == "1":
+            acc = _jac_add(acc, base)
+    return _from_jac(acc)
+
+
+def naive_msm(bases: Sequence[Point], scalars: Sequence[int]) -> Point:
+    """sum_i s_i * P_i - the oracle of record for MSM (truncates to the shorter
+    input exactly like msm_unchecked, src/kzg/time.rs:82)."""
+    acc = (1, 1, 0)
+    for p, s in zip(bases, scalars):
+        if p is None or s % R == 0:
+            continue
+        acc = _jac_add(acc, _to_jac(g1_mul(p, s % R)))
+    return _from_jac(acc)
+
+
+# --------------------------------------------------------------------------
+# arkworks Pippenger restated (src/kzg/msm/variable_base.rs)
+# --------------------------------------------------------------------------
+def ark_log2(x: int) -> int:
+    """ark_std::log2 = ceil(log2 x), 0 for x in {0, 1} (time_prover.rs:154-158)."""
+    if x <= 1:
+        return 0
+    return (x - 1).bit_length()
+
+
+def ln_without_floats(a: int) -> int:
+    """variable_base.rs:16-19."""
+    return ark_log2(a) * 69 // 100
+
+
+def msm_window_size(size: int) -> int:
+    """variable_base.rs:105-109."""
+    return 3 if size < 32 else ln_without_floats(size) + 2
+
+
+def make_digits(a: int, w: int, num_bits: int) -> List[int]:
+    """Signed radix-2^w digits, variable_base.rs:21-61 (bit-level restatement)."""
+    radix = 1 << w
+    mask = radix - 1
+    if num_bits == 0:
+        num_bits = a.bit_length()
+    count = (num_bits + w - 1) // w
+    digits = [0] * count
+    carry = 0
+    for i in range(count):
+        coef = carry + ((a >> (i * w)) & mask)
+        carry = (coef + radix // 2) >> w
+        digits[i] = coef - (carry << w)
+    digits[count - 1] += carry << w
+    return digits
+
+
+def pippenger_msm(bases: Sequence[Point], scalars: Sequence[int]) -> Point:
+    """VariableBaseMSM::multi_scalar_mul, variable_base.rs:95-177 (= ark-ec
+    msm_bigint): scalars are canonical bigints."""
+    size = min(len(bases), len(scalars))
+    if size == 0:
+        return None
+    c = msm_window_size(size)
+    ndig = (FR_MODULUS_BITS + c - 1) // c
+    digs = [make_digits(s, c, FR_MODULUS_BITS) for s in scalars[:size]]
+    window_sums = []
+    for i in range(ndig):
+        buckets = [(1, 1, 0)] * (1 << c)
+        for d, b in zip(digs, bases):
+            s = d[i]
+            if b is None or s == 0:
+                continue
+            if s > 0:
+                buckets[s - 1] = _jac_add(buckets[s - 1], _to_jac(b))
+            else:
+                buckets[-s - 1] = _jac_add(buckets[-s - 1], _to_jac(g1_neg(b)))
+        running = (1, 1, 0)
+        res = (1, 1, 0)
+        for b in reversed(buckets):
+            running = _jac_add(running, b)
+            res = _jac_add(res, running)
+        window_sums.append(res)
+    total = window_sums[-1]
+    for ws in reversed(window_sums[:-1]):
+        for _ in range(c):
+            total = _jac_double(total)
+        total = _jac_add(total, ws)
+    return _from_jac(total)
+
+
+def msm_unchecked(bases: Sequence[Point], scalars: Sequence[int]) -> Point:
+    """VariableBaseMSM::msm_unchecked: silently truncates to the shorter input."""
+    return pippenger_msm(bases, [s % R for s in scalars])
+
+
+def msm_checked(bases: Sequence[Point], scalars: Sequence[int]):
+    """VariableBaseMSM::msm: Err(min_len) on length mismatch."""
+    if len(bases) != len(scalars):
+        return ("err", min(len(bases), len(scalars)))
+    return ("ok", msm_unchecked(bases, scalars))
+
+
+class ChunkedPippenger:
+    """stream_pippenger.rs:209-271."""
+
+    def __init__(self, buf_size: int):
+        self.buf_size = buf_size
+        self.scalars: List[int] = []
+        self.bases: List[Point] = []
+        self.result: Point = None
+
+    def add(self, base: Point, scalar: int) -> None:
+        self.scalars.append(scalar)
+        self.bases.append(base)
+        if len(self.scalars) == self.buf_size:
+            self.result = g1_add(self.result, pippenger_msm(self.bases, self.scalars))
+            self.scalars, self.bases = [], []
+
+    def finalize(self) -> Point:
+        if self.scalars:
+            self.result = g1_add(self.result, pippenger_msm(self.bases, self.scalars))
+        return self.result
+
+
+class HashMapPippenger:
+    """stream_pippenger.rs:143-206: merge scalars of identical bases, flush at capacity."""
+
+    def __init__(self, capacity: int):
+        self.capacity = max(capacity, 1)
+        self.buf: dict = {}
+        self.result: Point = None
+
+    def _flush(self) -> None:
+        bases = list(self.buf.keys())
+        scalars = [self.buf[b] for b in bases]
+        self.result = g1_add(self.result, pippenger_msm(bases, scalars))
+        self.buf = {}
+
+    def add(self, base: Point, scalar: int) -> None:
+        self.buf[base] = (self.buf.get(base, 0) + scalar) % R
+        if len(self.buf) == self.capacity:
+            self._flush()
+
+    def finalize(self) -> Point:
+        if self.buf:
+            self._flush()
+        return self.result
+
+
+def msm_chunks(bases_stream: Sequence[Point], scalars_stream: Sequence[int], step: int = 1 << 20) -> Point:
+    """src/kzg/space.rs:22-55: big-endian streams, leading surplus bases skipped."""
+    assert len(scalars_stream) <= len(bases_stream)
+    off = len(bases_stream) - len(scalars_stream)
+    result: Point = None
+    n = len(scalars_stream)
+    for s in range(0, n, step):
+        b = bases_stream[off + s: off + s + step]
+        sc = scalars_stream[s: s + step]
+        result = g1_add(result, msm_unchecked(b, sc))
+    return result
+
+
+# --------------------------------------------------------------------------
+# Fr vector helpers (src/misc.rs)
+# --------------------------------------------------------------------------
+def fold_polynomial(f: Sequence[int], r: int) -> List[int]:
+    """misc.rs:52-56."""
+    out = []
+    for i in range(0, len(f), 2):
+        odd = f[i + 1] if i + 1 < len(f) else 0
+        out.append((f[i] + r * odd) % R)
+    return out
+
+
+split_fold = fold_polynomial  # herring/time_prover.rs:72-76 over Fr
+
+
+def foldings_polynomial(poly: Sequence[int], challenges: Sequence[int]) -> List[List[int]]:
+    """tensorcheck/mod.rs:124-133 (last challenge stripped)."""
+    out = []
+    cur = list(poly)
+    for ch in challenges[:-1] if challenges else []:
+        cur = fold_polynomial(cur, ch)
+        out.append(list(cur))
+    return out
+
+
+def powers(x: int, n: int) -> List[int]:
+    out = [1] * n
+    for i in range(1, n):
+        out[i] = out[i - 1] * x % R
+    return out
+
+
+def evaluate_le(coeffs: Sequence[int], x: int) -> int:
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % R
+    return acc
+
+
+def evaluate_be(coeffs: Sequence[int], x: int) -> int:
+    acc = 0
+    for c in coeffs:
+        acc = (acc * x + c) % R
+    return acc
+
+
+def ip(f: Sequence[int], g: Sequence[int]) -> int:
+    """misc.rs:235-266 (ip_unsafe): zips to the shorter iterator."""
+    return sum(a * b for a, b in zip(f, g)) % R
+
+
+def hadamard(f: Sequence[int], g: Sequence[int]) -> List[int]:
+    return [a * b % R for a, b in zip(f, g)]
+
+
+def vanishing_polynomial(points: Sequence[int]) -> List[int]:
+    """kzg/mod.rs:262-268, little-endian coefficients."""
+    poly = [1]
+    for p in points:
+        nxt = [0] * (len(poly) + 1)
+        for i, c in enumerate(poly):
+            nxt[i] = (nxt[i] - p * c) % R
+            nxt[i + 1] = (nxt[i + 1] + c) % R
+        poly = nxt
+    return poly
+
+
+def poly_div(f: Sequence[int], z: Sequence[int]) -> List[int]:
+    """DensePolynomial::div (quotient only), little-endian; z monic."""
+    f = list(f)
+    dz = len(z) - 1
+    if len(f) <= dz:
+        return []
+    q = [0] * (len(f) - dz)
+    for i in range(len(f) - 1, dz - 1, -1):
+        c = f[i]
+        q[i - dz] = c
+        if c:
+            for j, zc in enumerate(z):
+                f[i - dz + j] = (f[i - dz + j] - c * zc) % R
+    return q
+
+
+# --------------------------------------------------------------------------
+# Sumcheck provers
+# --------------------------------------------------------------------------
+class TimeProver:
+    """sumcheck/time_prover.rs:42-137 (rounds from the MAX length, twist in fold and message)."""
+
+    def __init__(self, f: Sequence[int], g: Sequence[int], twist: int):
+        self.f = [x % R for x in f]
+        self.g = [x % R for x in g]
+        self.twist = twist % R
+        self.round = 0
+        self.tot_rounds = ark_log2(max(len(self.f), len(self.g)))
+
+    def fold(self, r: int) -> None:
+        self.f = fold_polynomial(self.f, r * self.twist % R)
+        self.g = fold_polynomial(self.g, r)
+        self.twist = self.twist * self.twist % R
+
+    def next_message(self, verifier_message: Optional[int]):
+        assert self.round <= self.tot_rounds, "More rounds than needed."
+        if verifier_message is not None:
+            self.fold(verifier_message)
+        if self.round == self.tot_rounds:
+            return None
+        a = b = 0
+        twist2 = self.twist * self.twist % R
+        runner = 1
+        npairs = min((len(self.f) + 1) // 2, (len(self.g) + 1) // 2)
+        for i in range(npairs):
+            fe = self.f[2 * i]
+            ge = self.g[2 * i]
+            fo = self.f[2 * i + 1] if 2 * i + 1 < len(self.f) else 0
+            go = self.g[2 * i + 1] if 2 * i + 1 < len(self.g) else 0
+            a = (a + fe * ge * runner) % R
+            b = (b + (fe * go + ge * fo * self.twist) * runner) % R
+            runner = runner * twist2 % R
+        self.round += 1
+        return (a, b)
+
+    def final_foldings(self):
+        if self.round != self.tot_rounds:
+            return None
+        return (self.f[0], self.g[0])
+
+
+class HerringTimeProver:
+    """herring/time_prover.rs:44-137 with FModule (module.rs:127-146): rounds from the
+    MIN length; the twist only enters ``fold``; message = three strided inner products."""
+
+    def __init__(self, f: Sequence[int], g: Sequence[int], twist: int):
+        self.f = [x % R for x in f]
+        self.g = [x % R for x in g]
+        self.twist = twist % R
+        self.round = 0
+        self.tot_rounds = ark_log2(min(len(self.f), len(self.g)))
+
+    def fold(self, r: int) -> None:
+        self.f = split_fold(self.f, r * self.twist % R)
+        self.g = split_fold(self.g, r)
+        self.twist = self.twist * self.twist % R
+
+    def next_message(self, verifier_message: Optional[int]):
+        assert self.round <= self.tot_rounds
+        if verifier_message is not None:
+            self.fold(verifier_message)
+        if self.round == self.tot_rounds:
+            return None
+        a = ip(self.f[0::2], self.g[0::2])
+        b = (ip(self.f[0::2], self.g[1::2]) + ip(self.f[1::2], self.g[0::2])) % R
+        self.round += 1
+        return (a, b)
+
+    def final_foldings(self):
+        if self.round != self.tot_rounds:
+            return None
+        return (self.f[0], self.g[0])
+
+
+def init_stack(n: int, challenges_len: int) -> List[Tuple[int, int]]:
+    """sumcheck/streams.rs:69-85."""
+    stack = []
+    chunk = 1 << challenges_len
+    if n % chunk != 0:
+        delta = chunk - n % chunk
+        for i in reversed(range(challenges_len)):
+            if delta >= 1 << i:
+                stack.append((i, 0))
+                delta -= 1 << i
+    return stack
+
+
+def folded_polynomial_tree(coeffs_be: Sequence[int], challenges: Sequence[int]) -> Iterator[Tuple[int, int]]:
+    """FoldedPolynomialTreeIter, streams.rs:112-138: big-endian input, yields (level, coeff)
+    for level >= 1 in the order the stack machine emits them."""
+    stack = init_stack(len(coeffs_be), len(challenges))
+    it = iter(coeffs_be)
+    depth = len(challenges)
+    while True:
+        if len(stack) > 1 and stack[-1][0] == stack[-2][0]:
+            _, lhs = stack[-1]
+            level, rhs = stack[-2]
+            del stack[-2:]
+            item = (level + 1, (rhs * challenges[level] + lhs) % R)
+        else:
+            try:
+                item = (0, next(it) % R)
+            except StopIteration:
+                return
+        if item[0] != depth:
+            stack.append(item)
+        if item[0] != 0:
+            yield item
+
+
+def folded_polynomial_stream(coeffs_be: Sequence[int], challenges: Sequence[int]) -> Iterator[int]:
+    """FoldedPolynomialStreamIter, streams.rs:198-229: big-endian fold by all challenges."""
+    target = len(challenges)
+    stack = init_stack(len(coeffs_be), target)
+    it = iter(coeffs_be)
+    while True:
+        try:
+            n = len(stack)
+            if n > 1 and stack[-1][0] == stack[-2][0]:
+                _, lhs = stack[-1]
+                level, rhs = stack[-2]
+                del stack[-2:]
+                level, element = level + 1, (rhs * challenges[level] + lhs) % R
+            elif target > 0 and (n == 0 or stack[-1][0] != 0):
+                rhs = next(it)
+                lhs = next(it)
+                level, element = 1, (challenges[0] * rhs + lhs) % R
+            else:
+                level, element = 0, next(it) % R
+        except StopIteration:
+            return
+        if level != target:
+            stack.append((level, element))
+        else:
+            yield element
+
+
+def folded_stream_len(n: int, nchallenges: int) -> int:
+    return (n + (1 << nchallenges) - 1) >> nchallenges
+
+
+class SpaceProver:
+    """sumcheck/space_prover.rs:38-266: big-endian re-streamable inputs, rounds from MIN length."""
+
+    def __init__(self, f_be: Sequence[int], g_be: Sequence[int], twist: int):
+        self.f = [x % R for x in f_be]
+        self.g = [x % R for x in g_be]
+        self.twist = twist % R
+        self.challenges: List[int] = []
+        self.twisted_challenges: List[int] = []
+        self.round = 0
+        self.tot_rounds = ark_log2(min(len(self.f), len(self.g)))
+
+    def fold(self, r: int) -> None:
+        self.challenges.append(r % R)
+        self.twisted_challenges.append(r * self.twist % R)
+        self.twist = self.twist * self.twist % R
+
+    def next_message(self, verifier_message: Optional[int]):
+        assert self.round <= self.tot_rounds
+        if verifier_message is not None:
+            self.fold(verifier_message)
+        if self.round == self.tot_rounds:
+            return None
+        f_n = folded_stream_len(len(self.f), len(self.twisted_challenges))
+        g_n = folded_stream_len(len(self.g), len(self.challenges))
+        f_it = folded_polynomial_stream(self.f, self.twisted_challenges)
+        g_it = folded_polynomial_stream(self.g, self.challenges)
+        if f_n > g_n:
+            delta = f_n - g_n + (g_n % 2)
+            for _ in range(delta):
+                next(f_it)
+            f_n -= delta
+        elif f_n < g_n:
+            delta = g_n - f_n + (f_n % 2)
+            for _ in range(delta):
+                next(g_it)
+            g_n -= delta
+        if f_n & 1:
+            f_odd, f_even = 0, next(f_it)
+        else:
+            f_odd, f_even = next(f_it), next(f_it)
+        if g_n & 1:
+            g_odd, g_even = 0, next(g_it)
+        else:
+            g_odd, g_even = next(g_it), next(g_it)
+        f_pairs = (f_n - 2 + f_n % 2) // 2
+        g_pairs = (g_n - 2 + g_n % 2) // 2
+        assert f_pairs == g_pairs
+        twist2inv = pow(self.twist * self.twist % R, -1, R) if self.twist else 0
+        runner = pow(self.twist, f_pairs * 2, R)
+        a = f_even * g_even * runner % R
+        b = (f_even * g_odd + f_odd * g_even * self.twist) * runner % R
+        runner = runner * twist2inv % R
+        for _ in range(f_pairs):
+            f_odd = next(f_it)
+            g_odd = next(g_it)
+            f_even = next(f_it)
+            g_even = next(g_it)
+            a = (a + f_even * g_even * runner) % R
+            b = (b + (f_even * g_odd + f_odd * g_even * self.twist) * runner) % R
+            runner = runner * twist2inv % R
+        self.round += 1
+        return (a, b)
+
+    def final_foldings(self):
+        lhs = next(folded_polynomial_stream(self.f, self.twisted_challenges), None)
+        rhs = next(folded_polynomial_stream(self.g, self.challenges), None)
+        if lhs is None or rhs is None or self.round != self.tot_rounds:
+            return None
+        return (lhs, rhs)
+
+    def to_time_prover(self) -> TimeProver:
+        """From<&SpaceProver> for TimeProver, space_prover.rs:269-307."""
+        f = list(folded_polynomial_stream(self.f, self.twisted_challenges))[::-1]
+        g = list(folded_polynomial_stream(self.g, self.challenges))[::-1]
+        tp = TimeProver(f, g, self.twist)
+        tp.round = self.round
+        tp.tot_rounds = self.tot_rounds
+        return tp
+
+
+class ElasticProver:
+    """sumcheck/elastic_prover.rs:29-79 (threshold = SPACE_TIME_THRESHOLD, lib.rs:76)."""
+
+    def __init__(self, f_be, g_be, twist, threshold: int = 22):
+        self.p = SpaceProver(f_be, g_be, twist)
+        self.is_space = True
+        self.threshold = threshold
+
+    def fold(self, r: int) -> None:
+        if self.is_space and self.p.tot_rounds - self.p.round < self.threshold:
+            tp = self.p.to_time_prover()
+            tp.fold(r)
+            self.p = tp
+            self.is_space = False
+        else:
+            self.p.fold(r)
+
+    def next_message(self, verifier_message: Optional[int]):
+        if not self.is_space:
+            return self.p.next_message(verifier_message)
+        # SpaceProver::next_message calls its own fold; the enum's fold (with the
+        # hand-off) is only reached through Prover::fold - restated faithfully.
+        return self.p.next_message(verifier_message)
+
+    @property
+    def tot_rounds(self):
+        return self.p.tot_rounds
+
+    def final_foldings(self):
+        return self.p.final_foldings()
+
+
+def sumcheck_prove(prover, challenge_fn: Callable[[Tuple[int, int]], int]):
+    """Sumcheck::prove, proof.rs:36-66, with the Fiat-Shamir transcript abstracted
+    as ``challenge_fn(message) -> challenge`` (Merlin stays on the host)."""
+    messages, challenges = [], []
+    vm = None
+    while True:
+        msg = prover.next_message(vm)
+        if msg is None:
+            break
+        ch = challenge_fn(msg) % R
+        vm = ch
+        messages.append(msg)
+        challenges.append(ch)
+    return messages, challenges, prover.final_foldings()
+
+
+def subclaim_reduce(messages, challenges, asserted_sum: int) -> int:
+    """Verifier recurrence, subclaim.rs:77-97."""
+    claim = asserted_sum % R
+    for (a, b), r in zip(messages, challenges):
+        c = (claim - a) % R
+        claim = (a + r * b + c * r * r) % R
+    return claim
+
+
+# --------------------------------------------------------------------------
+# KZG callers (time: kzg/time.rs, space: kzg/space.rs)
+# --------------------------------------------------------------------------
+def kzg_commit(powers_of_g: Sequence[Point], poly: Sequence[int]) -> Point:
+    """CommitterKey::commit, time.rs:81-83."""
+    return msm_unchecked(powers_of_g, poly)
+
+
+def kzg_open(powers_of_g: Sequence[Point], poly: Sequence[int], x: int):
+    """CommitterKey::open, time.rs:112-131."""
+    quotient = []
+    prev = 0
+    for c in reversed(poly):
+        coeff = (c + prev * x) % R
+        quotient.insert(0, coeff)
+        prev = coeff
+    if not quotient:
+        return 0, None
+    return quotient[0], msm_unchecked(powers_of_g, quotient[1:])
+
+
+def kzg_open_multi_points(powers_of_g, poly, points) -> Point:
+    """time.rs:134-145."""
+    return kzg_commit(powers_of_g, poly_div(poly, vanishing_polynomial(points)))
+
+
+def kzg_stream_commit(powers_of_g_be: Sequence[Point], poly_be: Sequence[int]) -> Point:
+    """CommitterKeyStream::commit, space.rs:169-177."""
+    assert len(powers_of_g_be) >= len(poly_be)
+    return msm_chunks(powers_of_g_be, poly_be)
+
+
+def kzg_stream_open(powers_of_g_be, poly_be, alpha: int, max_msm_buffer: int):
+    """space.rs:95-125."""
+    quotient = ChunkedPippenger(max_msm_buffer)
+    bases = iter(powers_of_g_be[len(powers_of_g_be) - len(poly_be):])
+    prev = 0
+    for scalar, base in zip(poly_be, bases):
+        quotient.add(base, prev)
+        prev = (prev * alpha + scalar) % R
+    return prev, quotient.finalize()
+
+
+def kzg_stream_open_multi_points(powers_of_g_be, poly_be, points, max_msm_buffer: int):
+    """space.rs:128-166; returns (remainder big-endian, proof)."""
+    zeros = vanishing_polynomial(points)
+    deg = len(zeros) - 1
+    quotient = ChunkedPippenger(max_msm_buffer)
+    bases = iter(powers_of_g_be[len(powers_of_g_be) - len(poly_be) + deg:])
+    it = iter(poly_be)
+    state = deque(next(it) % R for _ in range(len(points)))
+    for coeff in it:
+        qc = state.popleft()
+        state.append(coeff % R)
+        for i in range(len(points)):
+            state[i] = (state[i] - zeros[deg - i - 1] * qc) % R
+        quotient.add(next(bases), qc)
+    return list(state), quotient.finalize()
+
+
+def kzg_commit_folding(powers_of_g_be, coeffs_be, challenges, max_msm_buffer: int) -> List[Point]:
+    """space.rs:192-223: one ChunkedPippenger per fold level, one pass over the tree."""
+    n = len(challenges)
+    pips, bases = [], []
+    for i in range(1, n + 1):
+        pips.append(ChunkedPippenger(max_msm_buffer // n))
+        delta = len(powers_of_g_be) - folded_stream_len(len(coeffs_be), i)
+        bases.append(iter(powers_of_g_be[delta:]))
+    for level, coeff in folded_polynomial_tree(coeffs_be, challenges):
+        pips[level - 1].add(next(bases[level - 1]), coeff)
+    return [p.finalize() for p in pips]
+
+
+def evaluate_folding(coeffs_be, challenges, x: int) -> List[int]:
+    """tensorcheck/mod.rs:73-88."""
+    result = [0] * len(challenges)
+    for level, c in folded_polynomial_tree(coeffs_be, challenges):
+        result[level - 1] = (result[level - 1] * x + c) % R
+    return result

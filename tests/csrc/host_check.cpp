@@ -1,0 +1,66 @@
+// CPU-side harness that compiles the *device* limb schedules (fp.cuh / g1.cuh)
+// with the host emulation of the PTX carry flag, so tests/test_host_field.py can
+// compare them with Python big integers without a GPU.  Test scaffolding only.
+#include "../../gemini_b200/csrc/fp.cuh"
+#include "../../gemini_b200/csrc/g1.cuh"
+#include <string.h>
+using namespace gm;
+
+template <class F> static void bin(void (*op)(F&, const F&, const F&), const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
+  for (int i = 0; i < n; i++) {
+    F x, y, z;
+    memcpy(x.v, a + i * F::N, 4 * F::N); memcpy(y.v, b + i * F::N, 4 * F::N);
+    op(z, x, y);
+    memcpy(r + i * F::N, z.v, 4 * F::N);
+  }
+}
+template <class F> static void f_mul(F& z, const F& x, const F& y) { z = x * y; }
+template <class F> static void f_add(F& z, const F& x, const F& y) { z = x + y; }
+template <class F> static void f_sub(F& z, const F& x, const F& y) { z = x - y; }
+template <class F> static void f_inv(F& z, const F& x, const F&) { z = fp_inv(x); }
+template <class F> static void f_redc(F& z, const F& x, const F&) { z = x.from_mont(); }
+template <class F> static void f_tom(F& z, const F& x, const F&) { z = x.to_mont(); }
+template <class F> static void f_sqr(F& z, const F& x, const F&) { z = x.sqr(); }
+
+extern "C" {
+void hc_fq(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
+  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>};
+  bin<Fq>(ops[op], a, b, r, n);
+}
+void hc_fr(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
+  void (*ops[])(Fr&, const Fr&, const Fr&) = {f_mul<Fr>, f_add<Fr>, f_sub<Fr>, f_inv<Fr>, f_redc<Fr>, f_tom<Fr>, f_sqr<Fr>};
+  bin<Fr>(ops[op], a, b, r, n);
+}
+// XYZZ accumulator (48 u32) (+)= affine point (24 u32, (0,0) = identity), optionally negated
+void hc_xyzz_madd(uint32_t* acc, const uint32_t* aff, int neg, int n) {
+  for (int i = 0; i < n; i++) {
+    XYZZ A; memcpy(&A, acc + 48 * i, 192);
+    Affine P; memcpy(&P, aff + 24 * i, 96);
+    if (neg) P.y = P.y.neg();
+    xyzz_madd(A, P);
+    memcpy(acc + 48 * i, &A, 192);
+  }
+}
+void hc_xyzz_add(uint32_t* acc, const uint32_t* other, int n) {
+  for (int i = 0; i < n; i++) {
+    XYZZ A, B; memcpy(&A, acc + 48 * i, 192); memcpy(&B, other + 48 * i, 192);
+    xyzz_add(A, B);
+    memcpy(acc + 48 * i, &A, 192);
+  }
+}
+void hc_xyzz_dbl(uint32_t* acc, int n) {
+  for (int i = 0; i < n; i++) {
+    XYZZ A; memcpy(&A, acc + 48 * i, 192);
+    xyzz_dbl(A);
+    memcpy(acc + 48 * i, &A, 192);
+  }
+}
+// XYZZ -> normalised Jacobian (x, y, 1) in Montgomery form, (0,1,0)-style identity => all zero z
+void hc_xyzz_to_jacobian(const uint32_t* acc, uint32_t* out, int n) {
+  for (int i = 0; i < n; i++) {
+    XYZZ A; memcpy(&A, acc + 48 * i, 192);
+    Jacobian J = xyzz_to_jacobian_normalized(A);
+    memcpy(out + 36 * i, &J, 144);
+  }
+}
+}

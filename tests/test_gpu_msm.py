@@ -1,0 +1,127 @@
+"""MSM parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Mirrors the reference's differential pattern (src/kzg/msm/variable_base.rs:179-215: Pippenger vs
+naive sum of scalar multiples) and the degenerate inputs its default workloads produce.
+"""
+import numpy as np
+import pytest
+
+import gemini_b200 as gm
+import pyref as o
+from gemini_b200 import field
+from util import R, fr_random_limbs, limbs_to_ints, rand_points, rand_scalars
+
+pytestmark = pytest.mark.gpu
+
+
+def run(ctx, bases, scalars):
+    return gm.VariableBaseMSM(ctx).msm_unchecked(bases, scalars)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 7, 31, 32, 33, 100, 257, 1000])
+def test_msm_small_vs_naive(ctx, n):
+    bases, scalars = rand_points(n, 1), rand_scalars(n, n + 1)
+    assert run(ctx, bases, scalars) == o.naive_msm(bases, scalars)
+
+
+@pytest.mark.parametrize("n", [1 << 12, 5000])
+def test_msm_config1_vs_pippenger_oracle(ctx, n):
+    """BASELINE config 1 (msm_bench 2^12) - bases resident on the device."""
+    bases, scalars = rand_points(n, 2), rand_scalars(n, 3)
+    srs = ctx.srs_load(bases)
+    got = field.jacobian_to_affine(ctx.msm(srs, scalars))
+    assert got == o.msm_unchecked(bases, scalars)
+    # raw output is normalised: Z == 1 in Montgomery form
+    raw = ctx.msm(srs, scalars)
+    assert list(raw[12:]) == field._limbs((1 << 384) % field.Q, 6)
+
+
+def test_msm_edge_scalars(ctx):
+    bases = rand_points(12, 4)
+    scalars = [0, 1, R - 1, 1 << 254, R - 2, 2, (R - 1) // 2, (R + 1) // 2, 0, 1 << 128, (1 << 255) % R, 12345]
+    assert run(ctx, bases, scalars) == o.naive_msm(bases, scalars)
+    assert run(ctx, bases, [0] * 12) is None
+
+
+def test_msm_identity_and_duplicate_bases(ctx):
+    """index_by injects identity points (kzg/time.rs:87); duplicates force P+P in a bucket."""
+    pts = rand_points(40, 5)
+    bases = pts[:10] + [None, None] + pts[10:20] + [pts[3], pts[3], o.g1_neg(pts[4])] + pts[20:]
+    scalars = rand_scalars(len(bases), 6)
+    scalars[22] = scalars[3]        # same base, same scalar -> doubling inside a bucket
+    scalars[24] = scalars[4]        # P + (-P) inside a bucket
+    assert run(ctx, bases, scalars) == o.naive_msm(bases, scalars)
+    # arkworks 104-byte records with the infinity flag
+    ark = field.g1_to_ark104(bases)
+    got = field.jacobian_to_affine(ctx.msm_hostbases(ark, scalars))
+    assert got == o.naive_msm(bases, scalars)
+    srs = ctx.srs_load(ark)
+    assert field.jacobian_to_affine(ctx.msm(srs, scalars)) == o.naive_msm(bases, scalars)
+
+
+def test_msm_all_equal_scalars_splits_buckets(ctx):
+    """dummy_r1cs (src/circuit.rs:349-365) makes every scalar identical: one bucket per window holds all
+    points and is cut into many work items + a CTA combine."""
+    n = 3000
+    bases = rand_points(n, 7)
+    s = rand_scalars(1, 8)[0]
+    want = o.g1_mul(o.naive_msm(bases, [1] * n), s)
+    assert run(ctx, bases, [s] * n) == want
+
+
+def test_msm_all_identical_bases(ctx):
+    """elastic example SRS: DummyStreamer(G1::generator(), n) (examples/snark.rs:62-65)."""
+    n = 2000
+    scalars = rand_scalars(n, 9)
+    srs = ctx.srs_fill(o.G1_GEN, n)
+    want = o.g1_mul(o.G1_GEN, sum(scalars) % R)
+    assert field.jacobian_to_affine(ctx.msm(srs, scalars)) == want
+    assert field.jacobian_to_affine(ctx.msm(srs, [5] * n)) == o.g1_mul(o.G1_GEN, 5 * n)
+
+
+def test_msm_truncation_and_checked(ctx):
+    bases, scalars = rand_points(50, 10), rand_scalars(64, 11)
+    srs = ctx.srs_load(bases)
+    v = gm.VariableBaseMSM(ctx)
+    # msm_unchecked truncates to the shorter input (commit relies on it, kzg/time.rs:82)
+    assert v.msm_unchecked(srs, scalars) == o.naive_msm(bases, scalars[:50])
+    assert v.msm_unchecked(srs, scalars[:20]) == o.naive_msm(bases[:20], scalars[:20])
+    assert v.msm(srs, scalars) == o.msm_checked(bases, scalars) == ("err", 50)
+    assert v.msm(bases, scalars[:50]) == ("ok", o.naive_msm(bases, scalars[:50]))
+    assert v.msm_bigint(srs, scalars[:50]) == o.naive_msm(bases, scalars[:50])
+    assert field.jacobian_to_affine(ctx.msm(srs, scalars[:10], base_offset=30)) == o.naive_msm(bases[30:40], scalars[:10])
+
+
+def test_srs_generate_and_g1_sum(ctx):
+    srs = ctx.srs_generate(100, first_multiple=0)
+    pts = srs.points()
+    assert pts[0] is None and pts[1] == o.G1_GEN
+    assert pts[37] == o.g1_mul(o.G1_GEN, 37) and pts[99] == o.g1_mul(o.G1_GEN, 99)
+    srs2 = ctx.srs_generate(33, first_multiple=(1 << 40) + 5)
+    assert srs2.points()[32] == o.g1_mul(o.G1_GEN, (1 << 40) + 37)
+    parts = [o.g1_mul(o.G1_GEN, k) for k in (3, 5, 9)] + [None]
+    jac = np.stack([field.affine_to_jacobian_limbs(p) for p in parts])
+    assert field.jacobian_to_affine(ctx.g1_sum(jac)) == o.g1_mul(o.G1_GEN, 17)
+
+
+@pytest.mark.parametrize("logn", [16, 20])
+def test_msm_closed_form_large(ctx, logn):
+    """Size-independent property at BASELINE config 2 size: bases P_i = [i+1]G generated on the device,
+    so sum_i s_i P_i = [sum_i s_i (i+1) mod r] G, which the oracle evaluates with one scalar mul."""
+    n = 1 << logn
+    srs = ctx.srs_generate(n, first_multiple=1)
+    limbs = fr_random_limbs(n, seed=logn)
+    rinv = pow(1 << 256, -1, R)
+    tot = sum(v * (i + 1) for i, v in enumerate(limbs_to_ints(limbs))) % R * rinv % R
+    assert field.jacobian_to_affine(ctx.msm(srs, limbs)) == o.g1_mul(o.G1_GEN, tot)
+    # the device generator agrees with its numpy restatement (same scalars, resident in HBM)
+    d = ctx.dev_alloc(n * 32)
+    ctx.fr_random_dev(d, n, logn)
+    assert np.array_equal(ctx.dev_download(d, n * 32).reshape(n, 4), limbs)
+    assert field.jacobian_to_affine(ctx.msm_dev(srs, d, n)) == o.g1_mul(o.G1_GEN, tot)
+    ctx.dev_free(d)
+    # linearity: msm(2s) == 2 msm(s) through the bigint entry point
+    small = limbs_to_ints(limbs[:4096])
+    a = field.jacobian_to_affine(ctx.msm(srs, [2 * (v * rinv % R) % R for v in small], bigint=True))
+    b = field.jacobian_to_affine(ctx.msm(srs, limbs[:4096]))
+    assert a == o.g1_double(b)

@@ -1,0 +1,135 @@
+"""Pins the big-integer oracle (oracle/pyref.py) to every known-answer value and differential
+property the reference's own tests hold for this path."""
+import random
+
+import pytest
+
+import pyref as o
+
+R = o.R
+
+
+def rs(n, seed):
+    rng = random.Random(seed)
+    return [rng.randrange(R) for _ in range(n)]
+
+
+def test_curve_self_check():
+    assert o.g1_is_on_curve(o.G1_GEN)
+    assert o.g1_mul(o.G1_GEN, R) is None          # [r]G = O
+    assert o.g1_add(o.G1_GEN, o.g1_neg(o.G1_GEN)) is None
+    assert o.g1_mul(o.G1_GEN, 5) == o.g1_add(o.g1_double(o.g1_double(o.G1_GEN)), o.G1_GEN)
+    assert o.FQ_INV64 == 0x89F3FFFCFFFCFFFD and o.FR_INV64 == 0xFFFFFFFEFFFFFFFF  # SURVEY 8c constants
+    assert o.FR_MONT_R == 0x1824B159ACC5056F998C4FEFECBC4FF55884B7FA0003480200000001FFFFFFFE
+
+
+def test_window_sizes_match_survey():
+    # n=2^12->10 (26 win), 2^16->13 (20), 2^20->15 (17), 2^24->18 (15), 2^28->21 (13)
+    for logn, c, w in [(12, 10, 26), (16, 13, 20), (20, 15, 17), (24, 18, 15), (28, 21, 13)]:
+        assert o.msm_window_size(1 << logn) == c
+        assert (255 + c - 1) // c == w
+    assert o.msm_window_size(31) == 3
+    assert o.ark_log2(17) == 5  # time_prover.rs:154-158
+
+
+def test_radix_digits_recompose():
+    """variable_base.rs:63-93 test_radix."""
+    for w in (3, 10, 15, 21):
+        for a in rs(20, w) + [0, 1, R - 1]:
+            d = o.make_digits(a, w, 0 if a else 255)
+            assert sum(x << (i * w) for i, x in enumerate(d)) == a
+            d = o.make_digits(a, w, 255)
+            assert sum(x << (i * w) for i, x in enumerate(d)) == a
+            assert all(-(1 << (w - 1)) <= x for x in d[:-1]) and all(x < (1 << (w - 1)) for x in d[:-1])
+
+
+def test_pippenger_vs_naive():
+    """variable_base.rs:179-215."""
+    rng = random.Random(1)
+    bases = [o.g1_mul(o.G1_GEN, rng.randrange(1, R)) for _ in range(40)]
+    for n in (1, 7, 31, 40):
+        sc = rs(n, n)
+        assert o.pippenger_msm(bases[:n], sc) == o.naive_msm(bases[:n], sc)
+    # chunked / hash-map variants (stream_pippenger.rs:356-425)
+    sc = rs(40, 99)
+    cp = o.ChunkedPippenger(7)
+    hp = o.HashMapPippenger(5)
+    for b, s in zip(bases, sc):
+        cp.add(b, s)
+        hp.add(b, s)
+    assert cp.finalize() == hp.finalize() == o.naive_msm(bases, sc)
+
+
+def test_fold_stream_kats():
+    """sumcheck/streams.rs:232-288."""
+    assert list(o.folded_polynomial_stream([1, 2, 1, 1], [1, 2])) == [8]
+    out = list(o.folded_polynomial_stream([1] * 12, [1, 1, 1, 1]))
+    assert out[-1] == 12
+    tree = list(o.folded_polynomial_tree([1, 1, 2], [1, 1])) if False else None
+    assert list(o.folded_polynomial_tree([1, 2, 1, 1], [1, 2])) == [(1, 3), (1, 2), (2, 8)]
+    # tensorcheck/mod.rs:388-398
+    assert o.foldings_polynomial([100, 101, 102, 103], [1, 1]) == [[201, 205]]
+
+
+@pytest.mark.parametrize("n,levels", [(16, 1), (16, 3), (19, 1), (19, 2), (19, 3)])
+def test_fold_polynomial_vs_stream(n, levels):
+    """sumcheck/tests.rs:140-200 (sizes 16 and 19, 1-3 levels, zero padding of non powers of two)."""
+    f, ch = rs(n, n), rs(levels, 7)
+    cur = f
+    for c in ch:
+        cur = o.fold_polynomial(cur, c)
+    assert list(o.folded_polynomial_stream(f[::-1], ch))[::-1] == cur
+
+
+def test_open_multi_points_kat():
+    """kzg/space.rs:321-387: remainder(53) = 1807299544171."""
+    rng = random.Random(3)
+    srs = [o.g1_mul(o.G1_GEN, rng.randrange(1, R)) for _ in range(10)]
+    rem, _ = o.kzg_stream_open_multi_points(srs[::-1], [80, 80, 88, 3, 73, 7, 24], [53 * 53, 53, R - 53], 4)
+    assert o.evaluate_be(rem, 53) == 1807299544171
+
+
+@pytest.mark.parametrize("nf,ng", [(30, 30), (93, 16), (16, 16), (29, 29)])
+def test_time_vs_space_vs_elastic(nf, ng):
+    """sumcheck/tests.rs:41-138."""
+    f, g, tw = rs(nf, 1), rs(ng, 2), rs(1, 3)[0]
+    ch = rs(12, 4)
+    runs = []
+    for mk in (lambda: o.TimeProver(f, g, tw), lambda: o.SpaceProver(f[::-1], g[::-1], tw), lambda: o.ElasticProver(f[::-1], g[::-1], tw)):
+        it = iter(ch)
+        runs.append(o.sumcheck_prove(mk(), lambda m: next(it)))
+    nmin = min(len(r[0]) for r in runs)
+    if nf == ng:
+        assert runs[0][0] == runs[1][0] == runs[2][0]
+        if nf & (nf - 1) == 0:
+            assert runs[0][2] == runs[1][2]
+    else:
+        assert runs[1][0] == runs[2][0]
+        assert runs[0][0][:3] == runs[1][0][:3]  # first three rounds, tests.rs:113-138
+    assert nmin >= 3
+
+
+def test_sumcheck_completeness():
+    """sumcheck/tests.rs:202-224: n = 2^10+1, random twist; messages satisfy subclaim.rs:77-97."""
+    n = (1 << 10) + 1
+    f, g, tw = rs(n, 5), rs(n, 6), rs(1, 7)[0]
+    it = iter(rs(16, 8))
+    msgs, ch, final = o.sumcheck_prove(o.TimeProver(f, g, tw), lambda m: next(it))
+    asserted = sum(a * b * pow(tw, i, R) for i, (a, b) in enumerate(zip(f, g))) % R
+    assert o.subclaim_reduce(msgs, ch, asserted) == final[0] * final[1] % R
+
+
+def test_kzg_time_equals_space():
+    """kzg/tests.rs:15-59."""
+    rng = random.Random(9)
+    d = 15
+    srs = [o.g1_mul(o.G1_GEN, rng.randrange(1, R)) for _ in range(d + 4)]
+    poly = rs(d + 1, 10)
+    assert o.kzg_commit(srs, poly) == o.kzg_stream_commit(srs[::-1], poly[::-1])
+    alpha = rs(1, 11)[0]
+    ev_t, pf_t = o.kzg_open(srs, poly, alpha)
+    ev_s, pf_s = o.kzg_stream_open(srs[::-1], poly[::-1], alpha, 4)
+    assert (ev_t, pf_t) == (ev_s, pf_s) and ev_t == o.evaluate_le(poly, alpha)
+    ch = rs(3, 12)
+    folds = o.foldings_polynomial(poly, ch + [0])
+    assert o.kzg_commit_folding(srs[::-1], poly[::-1], ch, 20) == [o.kzg_commit(srs, f) for f in folds]
