@@ -278,6 +278,48 @@ int go_msm_g1(const uint64_t* bases, const uint64_t* scalars, size_t n, int scal
   return c;
 }
 
+/* Synthetic bases of the benchmark: P_i = [first + i] G, affine Montgomery x|y, (0,0) = identity.
+ * CPU twin of k_generate_points (gemini_b200/csrc/msm.cu) so that the reference arm of bench.py can
+ * build the same workload without a GPU. */
+void go_generate_bases(size_t n, uint64_t first, uint64_t* out_xy) {
+  static const uint64_t gx[6] = {0x5cb38790fd530c16ULL, 0x7817fc679976fff5ULL, 0x154f95c7143ba1c1ULL, 0xf0ae6acdf3d0e747ULL, 0xedce6ecc21dbf440ULL, 0x120177419e0bfb75ULL};
+  static const uint64_t gy[6] = {0xbaac93d50ce72271ULL, 0x8c22631a7918fd8eULL, 0xdd595f13570725ceULL, 0x51ac582950405194ULL, 0x0e1c8c3fad0059c0ULL, 0x0bbc3efc5008a26aULL};
+  jac_t p;
+  jac_set_identity(&p);
+  for (int bit = 63; bit >= 0; bit--) {
+    jac_double(&p);
+    if ((first >> bit) & 1) jac_add_affine(&p, gx, gy, 0);
+  }
+  const size_t B = 1024; /* batch for Montgomery's inversion trick */
+  jac_t* run = (jac_t*)malloc(B * sizeof(jac_t));
+  uint64_t(*pref)[6] = (uint64_t(*)[6])malloc(B * 48);
+  for (size_t i0 = 0; i0 < n; i0 += B) {
+    const size_t m = n - i0 < B ? n - i0 : B;
+    uint64_t acc[6];
+    memcpy(acc, fq_one, 48);
+    for (size_t k = 0; k < m; k++) {
+      run[k] = p;
+      memcpy(pref[k], acc, 48);
+      if (!fq_is_zero(p.z)) fq_mul(acc, acc, p.z);
+      jac_add_affine(&p, gx, gy, 0);
+    }
+    uint64_t inv[6];
+    fq_inv(inv, acc);
+    for (size_t k = m; k-- > 0;) {
+      uint64_t* o = out_xy + 12 * (i0 + k);
+      if (fq_is_zero(run[k].z)) { memset(o, 0, 96); continue; }
+      uint64_t zi[6], zi2[6];
+      fq_mul(zi, inv, pref[k]);
+      fq_mul(inv, inv, run[k].z);
+      fq_mul(zi2, zi, zi);
+      fq_mul(o, run[k].x, zi2);
+      fq_mul(zi2, zi2, zi);
+      fq_mul(o + 6, run[k].y, zi2);
+    }
+  }
+  free(run); free(pref);
+}
+
 /* ---------------------------------------------------------------- Fr folds / sumcheck */
 void go_fr_fold(const uint64_t* f, size_t n, const uint64_t r[4], uint64_t* out) { /* misc.rs:52-56 */
   for (size_t i = 0; i < (n + 1) / 2; i++) {
