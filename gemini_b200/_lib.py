@@ -46,6 +46,8 @@ SIGNATURES = {
     "gm_srs_load_g1": (_i, [_vp, _vp, _sz, _sz, _l, _pp]),
     "gm_srs_generate_g1": (_i, [_vp, _sz, _u64, _pp]),
     "gm_srs_fill_g1": (_i, [_vp, _vp, _sz, _pp]),
+    "gm_srs_precompute": (_i, [_vp, _vp, _sz]),
+    "gm_srs_precompute_info": (_i, [_vp, _pi, _pi]),
     "gm_srs_len": (_sz, [_vp]),
     "gm_srs_read": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "gm_srs_free": (_i, [_vp]),

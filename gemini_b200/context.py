@@ -44,6 +44,16 @@ class Srs:
     def __len__(self) -> int:
         return int(lib.gm_srs_len(self._h))
 
+    def precompute(self, expected_msm_len: int = 0) -> "Srs":
+        """One-time table of 2^(c*w) multiples (gm_srs_precompute); MSMs over this SRS get faster."""
+        check(lib.gm_srs_precompute(self.ctx._h, self._h, expected_msm_len))
+        return self
+
+    def precompute_info(self):
+        c, w = C.c_int(0), C.c_int(0)
+        check(lib.gm_srs_precompute_info(self._h, C.byref(c), C.byref(w)))
+        return int(c.value), int(w.value)
+
     def read(self, offset: int = 0, n: Optional[int] = None) -> np.ndarray:
         n = len(self) - offset if n is None else n
         out = np.empty((n, 12), dtype=np.uint64)

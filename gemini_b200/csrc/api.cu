@@ -258,6 +258,39 @@ int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** 
   return GM_OK;
 }
 
+int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len) {
+  GM_ARG(ctx && srs, "NULL argument");
+  GM_TRY(set_device(ctx));
+  if (srs->n == 0) return GM_OK;
+  if (srs->d_table) { cudaFree(srs->d_table); srs->d_table = nullptr; srs->pre_c = srs->pre_W = 0; }
+  const MsmPlan P = msm_plan_merged(expected_msm_len ? expected_msm_len : srs->n, 0);
+  GM_ARG((double)P.W * (double)srs->n < 2147483648.0, "SRS too large for a precomputed table (W * n must stay below 2^31)");
+  void* table = nullptr;
+  cudaError_t e = cudaMalloc(&table, (size_t)P.W * srs->n * sizeof(Affine));
+  if (e != cudaSuccess) {
+    set_error("precompute: cudaMalloc of %zu bytes failed: %s", (size_t)P.W * srs->n * sizeof(Affine), cudaGetErrorString(e));
+    return GM_ERR_OOM;
+  }
+  int rc = msm_precompute(ctx, reinterpret_cast<const Affine*>(srs->d_points), srs->n, P.c, P.W, reinterpret_cast<Affine*>(table));
+  e = cudaStreamSynchronize(ctx->stream);
+  if (rc != GM_OK || e != cudaSuccess) {
+    if (rc == GM_OK) { set_error("precompute: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+    cudaFree(table);
+    return rc;
+  }
+  srs->d_table = table;
+  srs->pre_c = P.c;
+  srs->pre_W = P.W;
+  return GM_OK;
+}
+
+int gm_srs_precompute_info(const gm_srs* srs, int* out_window_bits, int* out_levels) {
+  GM_ARG(srs, "NULL argument");
+  if (out_window_bits) *out_window_bits = srs->pre_c;
+  if (out_levels) *out_levels = srs->pre_W;
+  return GM_OK;
+}
+
 size_t gm_srs_len(const gm_srs* srs) { return srs ? srs->n : 0; }
 
 int gm_srs_read(gm_ctx* ctx, const gm_srs* srs, size_t offset, size_t n, uint64_t* out_xy) {
@@ -277,6 +310,7 @@ int gm_srs_free(gm_srs* srs) {
     cudaStreamSynchronize(srs->ctx->stream);
   }
   if (srs->owned && srs->d_points) cudaFree(srs->d_points);
+  if (srs->d_table) cudaFree(srs->d_table);
   delete srs;
   return GM_OK;
 }
@@ -295,11 +329,27 @@ static void record_phases(gm_ctx* ctx) {
   cudaEventElapsedTime(&ctx->last_ms[3], ctx->ev[4], ctx->ev[5]);
 }
 
-static int msm_common(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scalars, size_t n, bool bigint, uint64_t out[18]) {
+static MsmBases bases_of_srs(const gm_srs* srs) {
+  MsmBases b;
+  b.points = reinterpret_cast<const Affine*>(srs->d_points);
+  b.table = reinterpret_cast<const Affine*>(srs->d_table);
+  b.n = srs->n;
+  b.c = srs->pre_c;
+  b.W = srs->pre_W;
+  return b;
+}
+static MsmBases bases_of_points(const Affine* pts, size_t n) {
+  MsmBases b;
+  b.points = pts;
+  b.n = n;
+  return b;
+}
+
+static int msm_common(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, uint64_t out[18]) {
   ResultSlot* slot;
   GM_TRY(ensure_result(ctx, &slot));
   GM_TRY(msm_acc_reset(ctx, &slot->acc));
-  GM_TRY(msm_accumulate(ctx, d_bases, d_scalars, n, bigint, &slot->acc));
+  GM_TRY(msm_accumulate(ctx, bases, base_offset, d_scalars, n, bigint, &slot->acc));
   GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
   GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
   GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -316,8 +366,8 @@ int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void
   GM_TRY(set_device(ctx));
   n = std::min(n, srs->n - base_offset);  // msm_unchecked truncates to the shorter input
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  return msm_common(ctx, reinterpret_cast<const Affine*>(srs->d_points) + base_offset,
-                    reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0, out_jacobian);
+  return msm_common(ctx, bases_of_srs(srs), base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0,
+                    out_jacobian);
 }
 
 int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
@@ -329,8 +379,7 @@ int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
   if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return msm_common(ctx, reinterpret_cast<const Affine*>(srs->d_points) + base_offset, ctx->msm.scalars.as<uint32_t>(), n,
-                    scalars_are_bigint != 0, out_jacobian);
+  return msm_common(ctx, bases_of_srs(srs), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
 }
 
 int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t bases_len, const uint64_t* scalars,
@@ -360,7 +409,7 @@ int gm_msm_g1_hostbases(gm_ctx* ctx, const void* points, size_t stride_bytes, lo
     cudaError_t e = cudaMemcpyAsync(S.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { set_error("H2D scalars: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
   }
-  if (rc == GM_OK) rc = msm_common(ctx, S.bases_tmp.as<Affine>(), S.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
+  if (rc == GM_OK) rc = msm_common(ctx, bases_of_points(S.bases_tmp.as<Affine>(), n), 0, S.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
   cudaStreamSynchronize(ctx->stream);
   raw.release();
   return rc;
@@ -412,7 +461,8 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   gm_ctx* ctx = s->ctx;
   GM_TRY(set_device(ctx));
   if (m == 0) return GM_OK;
-  const Affine* d_bases = nullptr;
+  MsmBases bases;
+  size_t boff = 0;
   const unsigned b = s->turn & 1u;
   // the staging buffers of this slot may still be read by the chunk pushed two calls ago
   if (s->used[b]) GM_CUDA(cudaEventSynchronize(s->consumed[b]));
@@ -423,11 +473,12 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
     GM_TRY(s->pts[b].reserve(m * sizeof(Affine)));
     GM_TRY(upload_points(ctx, points, m, stride_bytes, inf_offset, s->pts_raw[b], s->pts[b].as<Affine>(), ctx->copy_stream));
     need_pack = !(stride_bytes == 96 && inf_offset < 0);
-    d_bases = s->pts[b].as<Affine>();
+    bases = bases_of_points(s->pts[b].as<Affine>(), m);
   } else {
     GM_ARG(s->srs != nullptr, "stream has no SRS and no points were supplied");
     GM_ARG(base_offset <= s->srs->n && m <= s->srs->n - base_offset, "base range outside the SRS");
-    d_bases = reinterpret_cast<const Affine*>(s->srs->d_points) + base_offset;
+    bases = bases_of_srs(s->srs);
+    boff = base_offset;
   }
   GM_CUDA(cudaEventRecord(s->copied[b], ctx->copy_stream));
   // the caller may reuse its buffers as soon as we return: wait for the copies (the previous chunk's
@@ -435,7 +486,7 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   GM_CUDA(cudaEventSynchronize(s->copied[b]));
   GM_CUDA(cudaStreamWaitEvent(ctx->stream, s->copied[b], 0));
   if (need_pack) GM_TRY(srs_pack(ctx, s->pts_raw[b].as<uint8_t>(), m, stride_bytes, inf_offset, s->pts[b].as<Affine>()));
-  GM_TRY(msm_accumulate(ctx, d_bases, s->scal[b].as<uint32_t>(), m, scalars_are_bigint != 0, s->d_acc));
+  GM_TRY(msm_accumulate(ctx, bases, boff, s->scal[b].as<uint32_t>(), m, scalars_are_bigint != 0, s->d_acc));
   GM_CUDA(cudaEventRecord(s->consumed[b], ctx->stream));
   s->used[b] = true;
   s->turn++;

@@ -102,6 +102,9 @@ struct gm_srs {
   void* d_points = nullptr;  // n * 96 B, Montgomery x|y, (0,0) = identity
   size_t n = 0;
   bool owned = true;
+  // optional precomputed multiples: table[w][i] = 2^(c*w) * P_i, W levels of n points (gm_srs_precompute)
+  void* d_table = nullptr;
+  int pre_c = 0, pre_W = 0;
 };
 
 namespace gm {

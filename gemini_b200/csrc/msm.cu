@@ -82,7 +82,7 @@ struct Meta {
 // -------------------------------------------------------------------------------------------
 // 1. digits + histogram
 // -------------------------------------------------------------------------------------------
-__global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, int is_bigint, int c, int W,
+__global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, int is_bigint, int c, int W, int merged,
                               uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -128,7 +128,8 @@ __global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, 
       else code = coef - 1;
     }
     digits[(size_t)w * n + i] = code;
-    if (code != SKIP) atomicAdd(&counts[(size_t)w * nb + (code & 0x7FFFFFFFu)], 1u);
+    // merged: every window shares one bucket set (the bases are pre-multiplied by 2^(c*w))
+    if (code != SKIP) atomicAdd(&counts[(merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu)], 1u);
   }
 }
 
@@ -201,15 +202,16 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ co
 // -------------------------------------------------------------------------------------------
 // 3. counting-sort scatter
 // -------------------------------------------------------------------------------------------
-__global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W, uint32_t nb,
-                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+__global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W, uint32_t nb, int merged, uint32_t ref_offset,
+                          uint32_t ref_stride, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = blockIdx.y;
   if (i >= n) return;
   const uint32_t code = digits[(size_t)w * n + i];
   if (code == SKIP) return;
-  const uint32_t pos = atomicAdd(&cursor[(size_t)w * nb + (code & 0x7FFFFFFFu)], 1u);
-  sorted[pos] = i | (code & 0x80000000u);
+  const uint32_t pos = atomicAdd(&cursor[(merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu)], 1u);
+  // reference into the base table: level w of the precomputed table when merged
+  sorted[pos] = (i + ref_offset + (uint32_t)w * ref_stride) | (code & 0x80000000u);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -471,7 +473,7 @@ __global__ void k_fill_points(Affine p, size_t n, Affine* __restrict__ out) {
 // return to affine coordinates.
 static constexpr int GEN_RUN = 16;
 __device__ __forceinline__ Affine generator_affine() {
-  // BLS12-381 G1 generator, Montgomery form (oracle/pyref.py GX, GY)
+  // BLS12-381 G1 generator, Montgomery form (standard generator)
   const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
                            0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
   const uint32_t gy[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
@@ -519,9 +521,52 @@ k_generate_points(size_t n, uint64_t first, Affine* __restrict__ out) {
   }
 }
 
+// table[w][i] = 2^(c*w) * P_i for w < W (level 0 = the points themselves).  One thread per point:
+// c doublings per level in XYZZ, then one shared inversion (Montgomery's trick) back to affine.
+static constexpr int PRE_MAX_W = 26;
+__global__ void __launch_bounds__(64)
+k_precompute(const Affine* __restrict__ pts, size_t n, int c, int W, Affine* __restrict__ table) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine p = load_ro(pts + i);
+  store_rw(table + i, p);
+  if (p.is_identity()) {
+    for (int w = 1; w < W; w++) store_rw(table + (size_t)w * n + i, p);
+    return;
+  }
+  Fq xs[PRE_MAX_W], ys[PRE_MAX_W], zzs[PRE_MAX_W], zzzs[PRE_MAX_W], pref[PRE_MAX_W];
+  XYZZ q = xyzz_from_affine(p);
+  Fq run = Fq::one();
+  for (int w = 1; w < W; w++) {
+    for (int d = 0; d < c; d++) xyzz_dbl(q);
+    xs[w] = q.x; ys[w] = q.y; zzs[w] = q.zz; zzzs[w] = q.zzz;
+    pref[w] = run;
+    run = run * q.zzz;
+  }
+  Fq inv = fp_inv(run);
+  for (int w = W - 1; w >= 1; w--) {
+    Fq izzz = inv * pref[w];
+    inv = inv * zzzs[w];
+    Fq iz = zzs[w] * izzz;
+    Affine a;
+    a.x = xs[w] * iz.sqr();
+    a.y = ys[w] * izzz;
+    store_rw(table + (size_t)w * n + i, a);
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
+static void plan_chunks(MsmPlan& P) {
+  // slices of L buckets for the running-sum reduction: enough threads to fill the chip
+  const uint64_t total = (uint64_t)(P.merged ? 1 : P.W) * P.nb;
+  uint32_t L = 64;
+  while (L > 4 && total / L < 49152) L >>= 1;
+  P.L = (int)std::min<uint32_t>(L, P.nb);
+  P.nchunks = P.nb / P.L;
+}
+
 MsmPlan msm_plan(size_t n) {
   MsmPlan best{};
   double best_cost = 1e300;
@@ -539,8 +584,30 @@ MsmPlan msm_plan(size_t n) {
       best.c = c; best.W = W; best.nb = 1u << (c - 1);
     }
   }
-  best.L = (int)std::min<uint32_t>(64u, best.nb);
-  best.nchunks = best.nb / best.L;
+  best.merged = false;
+  plan_chunks(best);
+  return best;
+}
+
+// window size for a precomputed table: all windows share ONE bucket set, so the running-sum cost
+// is paid once and larger windows (fewer gathered points per scalar) win
+MsmPlan msm_plan_merged(size_t n, int c_forced) {
+  MsmPlan best{};
+  double best_cost = 1e300;
+  const char* env = getenv("GM_MSM_C_PRE");
+  int forced = c_forced ? c_forced : (env ? atoi(env) : 0);
+  for (int c = 10; c <= 23; c++) {
+    if (forced && c != forced) continue;
+    int W = (256 + c - 1) / c;
+    double nb = (double)(1u << (c - 1));
+    double cost = (double)n * W * 10.0 + nb * 28.0;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best.c = c; best.W = W; best.nb = 1u << (c - 1);
+    }
+  }
+  best.merged = true;
+  plan_chunks(best);
   return best;
 }
 
@@ -550,11 +617,16 @@ MsmPlan msm_plan(size_t n) {
     (ctx)->launches++;                                                     \
   } while (0)
 
-static int msm_chunk(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
+static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
   if (n == 0) return GM_OK;
   MsmScratch& S = ctx->msm;
-  const MsmPlan P = msm_plan(n);
-  const size_t M = (size_t)P.W * P.nb;
+  const bool merged = B.table != nullptr;
+  const MsmPlan P = merged ? msm_plan_merged(n, B.c) : msm_plan(n);
+  const int Weff = merged ? 1 : P.W;            // bucket sets
+  const size_t M = (size_t)Weff * P.nb;
+  const Affine* d_bases = merged ? B.table : B.points + base_offset;
+  const uint32_t ref_offset = merged ? (uint32_t)base_offset : 0u;
+  const uint32_t ref_stride = merged ? (uint32_t)B.n : 0u;
   const size_t refs = (size_t)P.W * n;
   const size_t max_split = refs / SPLIT + 1;
   const size_t max_partials = 2 * max_split + 1;
@@ -576,10 +648,10 @@ static int msm_chunk(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scala
   // small: Meta | chunk_s | chunk_w | block_part | win_sum
   const size_t off_meta = 0;
   const size_t off_cs = 4096;
-  const size_t off_cw = off_cs + (size_t)P.W * P.nchunks * sizeof(XYZZ);
-  const size_t off_bp = off_cw + (size_t)P.W * P.nchunks * sizeof(XYZZ);
-  const size_t off_ws = off_bp + (size_t)P.W * parts_per_win * sizeof(XYZZ);
-  const size_t small_bytes = off_ws + (size_t)P.W * sizeof(XYZZ);
+  const size_t off_cw = off_cs + (size_t)Weff * P.nchunks * sizeof(XYZZ);
+  const size_t off_bp = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
+  const size_t off_ws = off_bp + (size_t)Weff * parts_per_win * sizeof(XYZZ);
+  const size_t small_bytes = off_ws + (size_t)Weff * sizeof(XYZZ);
   static_assert(sizeof(Meta) <= 4096, "Meta fits its slot");
   GM_TRY(S.small.reserve(small_bytes));
   uint8_t* sm = S.small.as<uint8_t>();
@@ -595,11 +667,11 @@ static int msm_chunk(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scala
 
   const uint32_t n32 = (uint32_t)n;
   GM_CUDA(cudaEventRecord(ctx->ev[2], st));
-  LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, bigint ? 1 : 0, P.c, P.W, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
+  LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
   LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), (uint32_t)M);
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
   LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), (uint32_t)M);
-  LAUNCH(ctx, k_scatter, dim3((n32 + 255) / 256, P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
+  LAUNCH(ctx, k_scatter, dim3((n32 + 255) / 256, P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, merged ? 1 : 0, ref_offset, ref_stride, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
   LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
   LAUNCH(ctx, k_size_scan, 1, 32, 0, meta);
   LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, S.work.as<uint2>(), meta);
@@ -610,30 +682,30 @@ static int msm_chunk(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scala
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
          S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, S.partials.as<XYZZ>(), S.buckets.as<XYZZ>());
-  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, P.W), 128, 0, S.buckets.as<XYZZ>(), S.counts.as<uint32_t>(), P.nb, P.L, P.nchunks, P.W, chunk_s, chunk_w);
-  LAUNCH(ctx, k_chunk_weight, dim3(parts_per_win, P.W), RED_THREADS, red_sh, chunk_s, chunk_w, P.L, P.nchunks, block_part);
-  LAUNCH(ctx, k_window_finish, P.W, RED_THREADS, red_sh, block_part, parts_per_win, P.c, win_sum);
-  LAUNCH(ctx, k_final, 1, 32, 0, win_sum, P.W, d_acc);
+  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, S.buckets.as<XYZZ>(), S.counts.as<uint32_t>(), P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
+  LAUNCH(ctx, k_chunk_weight, dim3(parts_per_win, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.L, P.nchunks, block_part);
+  LAUNCH(ctx, k_window_finish, Weff, RED_THREADS, red_sh, block_part, parts_per_win, P.c, win_sum);
+  LAUNCH(ctx, k_final, 1, 32, 0, win_sum, Weff, d_acc);
   GM_CUDA(cudaEventRecord(ctx->ev[5], st));
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
 
-int msm_accumulate(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    const int red_sh = RED_THREADS * sizeof(XYZZ);
-    cudaFuncSetAttribute(k_split_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, red_sh);
-    cudaFuncSetAttribute(k_chunk_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, red_sh);
-    cudaFuncSetAttribute(k_window_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, red_sh);
-    attr_done = true;
-  }
-  // W * n references are addressed with 32 bits: run very large inputs as several passes
+int msm_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
+  // W * n references are addressed with 32 bits (31 + sign for table references): run very large inputs as several passes
   const size_t max_pass = (size_t)1 << 27;
   for (size_t off = 0; off < n; off += max_pass) {
     const size_t m = std::min(max_pass, n - off);
-    GM_TRY(msm_chunk(ctx, d_bases + off, d_scalars + off * 8, m, bigint, d_acc));
+    GM_TRY(msm_chunk(ctx, B, base_offset + off, d_scalars + off * 8, m, bigint, d_acc));
   }
+  return GM_OK;
+}
+
+int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, Affine* d_table) {
+  if (n == 0) return GM_OK;
+  if (W > PRE_MAX_W) { set_error("precompute: too many windows (%d)", W); return GM_ERR_ARG; }
+  LAUNCH(ctx, k_precompute, (unsigned)((n + 63) / 64), 64, 0, d_points, n, c, W, d_table);
+  GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
 

@@ -11,11 +11,22 @@ struct MsmPlan {
   uint32_t nb;       // buckets per window = 2^(c-1) (signed digits)
   int L;             // buckets per running-sum slice
   uint32_t nchunks;  // nb / L
+  bool merged;       // all windows share one bucket set (precomputed 2^(c*w) multiples of the bases)
 };
 MsmPlan msm_plan(size_t n);
+MsmPlan msm_plan_merged(size_t n, int c_forced);
+
+// Where the bases of an MSM live: plain points, or a precomputed table[w][i] = 2^(c*w) P_i of n points
+struct MsmBases {
+  const Affine* points = nullptr;
+  const Affine* table = nullptr;
+  size_t n = 0;  // points per table level
+  int c = 0, W = 0;
+};
 
 // *d_acc (XYZZ, device) += sum_i scalars[i] * bases[i]; asynchronous on ctx->stream
-int msm_accumulate(gm_ctx* ctx, const Affine* d_bases, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc);
+int msm_accumulate(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc);
+int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, Affine* d_table);
 int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);
 int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out);

@@ -125,3 +125,50 @@ def test_msm_closed_form_large(ctx, logn):
     a = field.jacobian_to_affine(ctx.msm(srs, [2 * (v * rinv % R) % R for v in small], bigint=True))
     b = field.jacobian_to_affine(ctx.msm(srs, limbs[:4096]))
     assert a == o.g1_double(b)
+
+
+# ---- precomputed 2^(c*w) tables (gm_srs_precompute): same results through the merged-window path ----
+def test_precompute_matches_plain_path(ctx):
+    pts = rand_points(300, 50)
+    bases = pts[:100] + [None] + pts[100:200] + [pts[7], pts[7], o.g1_neg(pts[8])] + pts[200:]
+    scalars = rand_scalars(len(bases), 51)
+    scalars[201] = scalars[7]
+    scalars[203] = scalars[8]
+    scalars[5:9] = [0, 1, R - 1, 1 << 254]
+    want = o.naive_msm(bases, scalars)
+    srs = ctx.srs_load(bases)
+    assert field.jacobian_to_affine(ctx.msm(srs, scalars)) == want
+    srs.precompute()
+    c, levels = srs.precompute_info()
+    assert levels == (256 + c - 1) // c and c >= 10
+    raw = ctx.msm(srs, scalars)
+    assert field.jacobian_to_affine(raw) == want
+    assert np.array_equal(raw, ctx.msm(ctx.srs_load(bases), scalars))  # byte-identical normalised output
+    # prefix, offset and bigint entry points against the table
+    assert field.jacobian_to_affine(ctx.msm(srs, scalars[:50])) == o.naive_msm(bases[:50], scalars[:50])
+    assert field.jacobian_to_affine(ctx.msm(srs, scalars[:40], base_offset=150)) == o.naive_msm(bases[150:190], scalars[:40])
+    assert gm.VariableBaseMSM(ctx).msm_bigint(srs, scalars) == want
+    # all-equal scalars: the single hot bucket per window is split into work items
+    s = rand_scalars(1, 52)[0]
+    assert field.jacobian_to_affine(ctx.msm(srs, [s] * len(bases))) == o.g1_mul(o.naive_msm(bases, [1] * len(bases)), s)
+    # table levels really are 2^(c*w) multiples
+    srs_small = ctx.srs_load(pts[:3]).precompute(expected_msm_len=1 << 20)
+    c2, lv2 = srs_small.precompute_info()
+    assert (c2, lv2) == (20, 13)
+
+
+@pytest.mark.parametrize("logn", [14, 20])
+def test_precompute_closed_form_large(ctx, logn):
+    n = 1 << logn
+    srs = ctx.srs_generate(n, first_multiple=1).precompute()
+    limbs = fr_random_limbs(n, seed=100 + logn)
+    rinv = pow(1 << 256, -1, R)
+    tot = sum(v * (i + 1) for i, v in enumerate(limbs_to_ints(limbs))) % R * rinv % R
+    assert field.jacobian_to_affine(ctx.msm(srs, limbs)) == o.g1_mul(o.G1_GEN, tot)
+    # streamed chunks against the same table (msm_chunks, chunk 2^12) give the same point
+    st = gm.msm._DeviceStream(ctx, srs, 1 << 12)
+    for s0 in range(0, min(n, 1 << 15), 1 << 12):
+        st.push_range(s0, limbs[s0:s0 + (1 << 12)])
+    m = min(n, 1 << 15)
+    tot_m = sum(v * (i + 1) for i, v in enumerate(limbs_to_ints(limbs[:m]))) % R * rinv % R
+    assert st.finalize() == o.g1_mul(o.G1_GEN, tot_m)

@@ -1,0 +1,116 @@
+"""The DEVICE limb schedules (gemini_b200/csrc/fp.cuh, g1.cuh) compiled for the host with an emulated
+PTX carry flag (tests/csrc/host_check.cpp) and compared with Python big integers.  This is how the
+Montgomery even/odd carry-chain product and the XYZZ formulas are validated before any GPU time."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import pyref as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hc():
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    so = os.path.join(ROOT, "build", "libhostcheck.so")
+    src = os.path.join(ROOT, "tests", "csrc", "host_check.cpp")
+    subprocess.run(["g++", "-O2", "-x", "c++", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+def pack(vals, n32):
+    a = np.zeros((len(vals), n32), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        for j in range(n32):
+            a[i, j] = (v >> (32 * j)) & 0xFFFFFFFF
+    return a
+
+
+def unpack(a):
+    return [sum(int(a[i, j]) << (32 * j) for j in range(a.shape[1])) for i in range(a.shape[0])]
+
+
+def P(x):
+    return C.c_void_p(x.ctypes.data)
+
+
+@pytest.mark.parametrize("name,p,n", [("hc_fq", o.Q, 12), ("hc_fr", o.R, 8)])
+def test_field_limb_schedules(hc, name, p, n):
+    fn = getattr(hc, name)
+    rng = random.Random(1)
+    Rm = (1 << (32 * n)) % p
+    Ri = pow(Rm, -1, p)
+    edge = [0, 1, p - 1, p - 2, Rm, (p - 1) // 2, (1 << (32 * n - 3)) % p]
+    A = edge + [rng.randrange(p) for _ in range(800)]
+    B = [rng.randrange(p) for _ in range(len(A) - len(edge))] + edge
+    a, b = pack(A, n), pack(B, n)
+    r = np.zeros_like(a)
+    exp = {0: lambda x, y: x * y * Ri % p, 1: lambda x, y: (x + y) % p, 2: lambda x, y: (x - y) % p,
+           4: lambda x, y: x * Ri % p, 5: lambda x, y: x * Rm % p, 6: lambda x, y: x * x * Ri % p}
+    for op, f in exp.items():
+        fn(op, P(a), P(b), P(r), len(A))
+        assert unpack(r) == [f(x, y) for x, y in zip(A, B)], (name, op)
+    A2 = [x for x in A if x][:30]
+    a2 = pack(A2, n)
+    r2 = np.zeros_like(a2)
+    fn(3, P(a2), P(a2), P(r2), len(A2))
+    assert unpack(r2) == [pow(x * Ri % p, -1, p) * Rm % p for x in A2]
+
+
+def fq_l(x):
+    x = x * o.FQ_MONT_R % o.Q
+    return [(x >> (32 * j)) & 0xFFFFFFFF for j in range(12)]
+
+
+def l_fq(l):
+    return sum(int(v) << (32 * j) for j, v in enumerate(l)) * pow(o.FQ_MONT_R, -1, o.Q) % o.Q
+
+
+def xyzz(p, z=1):
+    if p is None:
+        return [0] * 48
+    zz = z * z % o.Q
+    zzz = zz * z % o.Q
+    return fq_l(p[0] * zz % o.Q) + fq_l(p[1] * zzz % o.Q) + fq_l(zz) + fq_l(zzz)
+
+
+def from_jac(row):
+    x, y, z = l_fq(row[:12]), l_fq(row[12:24]), l_fq(row[24:])
+    if z == 0:
+        assert (x, y) == (1, 1)
+        return None
+    assert z == 1
+    return (x, y)
+
+
+def test_xyzz_formulas_complete(hc):
+    rng = random.Random(2)
+    pts = [o.g1_mul(o.G1_GEN, rng.randrange(1, o.R)) for _ in range(10)]
+    cases = [(a, b) for a in pts[:5] for b in pts[5:]]
+    cases += [(None, pts[0]), (pts[0], None), (None, None), (pts[1], pts[1]), (pts[2], o.g1_neg(pts[2]))]
+    n = len(cases)
+    aff = np.array([[0] * 24 if b is None else fq_l(b[0]) + fq_l(b[1]) for _, b in cases], dtype=np.uint32)
+    for neg in (0, 1):
+        acc = np.array([xyzz(a, rng.randrange(1, o.Q)) for a, _ in cases], dtype=np.uint32)
+        hc.hc_xyzz_madd(P(acc), P(aff), neg, n)
+        out = np.zeros((n, 36), dtype=np.uint32)
+        hc.hc_xyzz_to_jacobian(P(acc), P(out), n)
+        for i, (a, b) in enumerate(cases):
+            assert from_jac(out[i]) == o.g1_add(a, o.g1_neg(b) if neg else b), (neg, i)
+    acc = np.array([xyzz(a, rng.randrange(1, o.Q)) for a, _ in cases], dtype=np.uint32)
+    oth = np.array([xyzz(b, rng.randrange(1, o.Q)) for _, b in cases], dtype=np.uint32)
+    hc.hc_xyzz_add(P(acc), P(oth), n)
+    out = np.zeros((n, 36), dtype=np.uint32)
+    hc.hc_xyzz_to_jacobian(P(acc), P(out), n)
+    for i, (a, b) in enumerate(cases):
+        assert from_jac(out[i]) == o.g1_add(a, b), i
+    acc = np.array([xyzz(a, rng.randrange(1, o.Q)) for a, _ in cases], dtype=np.uint32)
+    hc.hc_xyzz_dbl(P(acc), n)
+    hc.hc_xyzz_to_jacobian(P(acc), P(out), n)
+    for i, (a, _) in enumerate(cases):
+        assert from_jac(out[i]) == o.g1_double(a), i

@@ -1,0 +1,104 @@
+"""Host-side logic that needs no GPU: marshalling, KZG scalar preparation, sharding, gloo exchange."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+import pyref as o
+from gemini_b200 import dist as gdist
+from gemini_b200 import field, kzg
+from util import R, fr_random_limbs, limbs_to_ints, rand_points, rand_scalars
+
+
+def test_fr_marshalling_roundtrip():
+    vals = rand_scalars(50, 1) + [0, 1, R - 1]
+    arr = field.fr_to_limbs(vals)
+    assert arr.shape == (53, 4) and arr.dtype == np.uint64
+    assert field.fr_from_limbs(arr) == vals
+    assert [o.limbs_to_int(r) for r in arr] == [o.fr_to_mont(v) for v in vals]
+    assert field.fr_from_limbs(field.fr_to_limbs(vals, montgomery=False), montgomery=False) == vals
+
+
+def test_g1_marshalling_roundtrip():
+    pts = rand_points(8, 2) + [None]
+    arr = field.g1_to_limbs(pts)
+    assert field.g1_from_limbs(arr) == pts
+    ark = field.g1_to_ark104(pts)
+    assert ark.shape == (9, 104) and ark[8, 96] == 1 and not ark[:8, 96].any()
+    for p in pts:
+        assert field.jacobian_to_affine(field.affine_to_jacobian_limbs(p)) == p
+    # non-normalised Jacobian input
+    x, y = pts[0]
+    z = 12345
+    jac = np.array(field._limbs((x * z * z << 384) % field.Q, 6) + field._limbs((y * z ** 3 << 384) % field.Q, 6) +
+                   field._limbs((z << 384) % field.Q, 6), dtype=np.uint64)
+    assert field.jacobian_to_affine(jac) == pts[0]
+
+
+def test_splitmix_twin_is_canonical():
+    limbs = fr_random_limbs(5000, 3)
+    vals = limbs_to_ints(limbs)
+    assert all(0 <= v < R for v in vals) and len(set(vals)) == 5000
+
+
+def test_kzg_scalar_preparation_matches_oracle():
+    pts = rand_scalars(3, 4)
+    assert kzg.vanishing_polynomial(pts) == o.vanishing_polynomial(pts)
+    f = rand_scalars(20, 5)
+    z = o.vanishing_polynomial(pts)
+    assert kzg._poly_div(f, z) == o.poly_div(f, z)
+    assert kzg._poly_div(f[:3], z) == []
+    polys = [rand_scalars(5, 6), rand_scalars(9, 7)]
+    eta = 77
+    assert kzg._linear_combination(polys, [1, eta]) == [(polys[0][i] if i < 5 else 0) % R + eta * polys[1][i] % R - (R if ((polys[0][i] if i < 5 else 0) + eta * polys[1][i] % R) >= R else 0) for i in range(9)]
+
+
+def test_shard_ranges_cover():
+    for n in (0, 1, 7, 1 << 20, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            rs = [gdist.shard_range(n, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            assert max(e - s for s, e in rs) - min(e - s for s, e in rs) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 41
+        bases, scalars = rand_points(n, 8), rand_scalars(n, 9)
+        s, e = gdist.shard_range(n, rank, world)
+        # stand-in for the device: the oracle computes this rank's partial and the combine
+        partial = field.affine_to_jacobian_limbs(o.naive_msm(bases[s:e], scalars[s:e]))
+
+        def combine(allp):
+            acc = None
+            for row in allp:
+                acc = o.g1_add(acc, field.jacobian_to_affine(row))
+            return field.affine_to_jacobian_limbs(acc)
+
+        total = gdist.allreduce_g1(partial, combine)
+        q.put((rank, field.jacobian_to_affine(total) == o.naive_msm(bases, scalars)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_g1_gloo_world2():
+    """The N>1 exchange (all-gather of 144-byte partial sums + adds on every rank) over gloo, world_size 2."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + random.randrange(2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
