@@ -18,8 +18,9 @@
 //                       128-bit loads), complete formulas (identity, P+P, P-P)
 //   6 k_split_combine   one CTA per split bucket: tree-sum of its partial sums
 //   7 k_bucket_chunks   running-sum reduction (variable_base.rs:150-166) over slices of L buckets
-//   8 k_chunk_weight    X_t = W_t + (t*L)*S_t, CTA tree-sum
-//   9 k_window_finish   per-window total times 2^(c*w) (variable_base.rs:168-175)
+//   8 k_rowcol          the chunk sums S_t carry weights t*L: row / column sums of the t = hi*L2 + lo matrix
+//   9 k_weighted, k_window_total   one short scalar multiplication per row and per column, CTA tree-sums,
+//                       per-window total times 2^(c*w) (variable_base.rs:168-175)
 //  10 k_final           sum of windows, += device-resident accumulator, optional normalisation
 //
 // The window size c is chosen by a cost model for the GPU (not arkworks' ln(n)+2): the result is a
@@ -367,45 +368,112 @@ k_bucket_chunks(const XYZZ* __restrict__ buckets, const uint32_t* __restrict__ c
   store_rw(chunk_w + (size_t)w * nchunks + t, sum);
 }
 
-// 8. X_t = W_t + (t*L) * S_t, then CTA tree-sum -> one partial per CTA
+// 8. The chunk sums S_t (t < T) still carry the weights t*L.  View t = hi*L2 + lo as an H2 x L2 matrix:
+//      sum_t t*S_t = sum_lo lo * C_lo + L2 * sum_hi hi * R_hi,   C_lo / R_hi = plain column / row sums,
+//    so the weighting needs one short double-and-add per ROW and per COLUMN (H2 + L2 of them) instead
+//    of one per chunk.  CTA roles by blockIdx.x: [0,H2) rows of S, [H2,2*H2) rows of W (plain sums of
+//    the locally weighted chunk sums), [2*H2, 2*H2+L2) columns of S.
 __global__ void __launch_bounds__(RED_THREADS)
-k_chunk_weight(const XYZZ* __restrict__ chunk_s, const XYZZ* __restrict__ chunk_w, int L, uint32_t nchunks,
-               XYZZ* __restrict__ block_part) {
+k_rowcol(const XYZZ* __restrict__ chunk_s, const XYZZ* __restrict__ chunk_w, uint32_t T, uint32_t H2, uint32_t L2,
+         XYZZ* __restrict__ row_sum, XYZZ* __restrict__ wrow_sum, XYZZ* __restrict__ col_sum) {
   extern __shared__ uint4 sh_raw[];
   XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = blockIdx.y;
-  XYZZ x = XYZZ::identity();
-  if (t < nchunks) {
-    const XYZZ s = load_rw(chunk_s + (size_t)w * nchunks + t);
-    const uint32_t k = t * (uint32_t)L;
-    if (k && !s.is_identity()) {
-      for (int bit = 31 - __clz(k); bit >= 0; bit--) {
-        xyzz_dbl(x);
-        if ((k >> bit) & 1u) xyzz_add(x, s);
-      }
-    }
-    XYZZ wsum = load_rw(chunk_w + (size_t)w * nchunks + t);
-    xyzz_add(x, wsum);
-  }
-  XYZZ tot = block_sum_xyzz(x, sh);
-  if (threadIdx.x == 0) store_rw(block_part + (size_t)w * gridDim.x + blockIdx.x, tot);
-}
-
-// 9. per-window total, weighted by 2^(c*w)
-__global__ void __launch_bounds__(RED_THREADS)
-k_window_finish(const XYZZ* __restrict__ block_part, uint32_t nparts, int c, XYZZ* __restrict__ win_sum) {
-  extern __shared__ uint4 sh_raw[];
-  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
-  const int w = blockIdx.x;
+  const uint32_t bx = blockIdx.x;
+  const XYZZ* src = (bx >= H2 && bx < 2 * H2) ? chunk_w : chunk_s;
+  src += (size_t)w * T;
   XYZZ acc = XYZZ::identity();
-  for (uint32_t k = threadIdx.x; k < nparts; k += blockDim.x) {
-    XYZZ b = load_rw(block_part + (size_t)w * nparts + k);
-    xyzz_add(acc, b);
+  if (bx < 2 * H2) {
+    const uint32_t row = bx < H2 ? bx : bx - H2;
+    for (uint32_t lo = threadIdx.x; lo < L2; lo += blockDim.x) {
+      XYZZ v = load_rw(src + (size_t)row * L2 + lo);
+      xyzz_add(acc, v);
+    }
+  } else {
+    const uint32_t col = bx - 2 * H2;
+    for (uint32_t hi = threadIdx.x; hi < H2; hi += blockDim.x) {
+      XYZZ v = load_rw(src + (size_t)hi * L2 + col);
+      xyzz_add(acc, v);
+    }
   }
   XYZZ tot = block_sum_xyzz(acc, sh);
   if (threadIdx.x == 0) {
-    for (int d = 0; d < c * w; d++) xyzz_dbl(tot);
+    if (bx < H2) store_rw(row_sum + (size_t)w * H2 + bx, tot);
+    else if (bx < 2 * H2) store_rw(wrow_sum + (size_t)w * H2 + (bx - H2), tot);
+    else store_rw(col_sum + (size_t)w * L2 + (bx - 2 * H2), tot);
+  }
+}
+
+__device__ __forceinline__ XYZZ small_scalar_mul(const XYZZ& p, uint32_t k) {
+  XYZZ x = XYZZ::identity();
+  if (k == 0 || p.is_identity()) return x;
+  for (int bit = 31 - __clz(k); bit >= 0; bit--) {
+    xyzz_dbl(x);
+    if ((k >> bit) & 1u) xyzz_add(x, p);
+  }
+  return x;
+}
+
+// 9a. one thread per column / row: lo * C_lo  or  2^log2(L2) * hi * R_hi; CTA tree-sum -> partials.
+//     CTAs [0, ctas_c) handle columns, the rest rows.
+__global__ void __launch_bounds__(RED_THREADS)
+k_weighted(const XYZZ* __restrict__ row_sum, const XYZZ* __restrict__ col_sum, uint32_t H2, uint32_t L2, int log_l2,
+           uint32_t ctas_c, XYZZ* __restrict__ part) {
+  extern __shared__ uint4 sh_raw[];
+  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
+  const int w = blockIdx.y;
+  XYZZ v = XYZZ::identity();
+  if (blockIdx.x < ctas_c) {
+    const uint32_t lo = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lo < L2) v = small_scalar_mul(load_rw(col_sum + (size_t)w * L2 + lo), lo);
+  } else {
+    const uint32_t hi = (blockIdx.x - ctas_c) * blockDim.x + threadIdx.x;
+    if (hi < H2) {
+      v = small_scalar_mul(load_rw(row_sum + (size_t)w * H2 + hi), hi);
+      for (int d = 0; d < log_l2; d++) xyzz_dbl(v);
+    }
+  }
+  XYZZ tot = block_sum_xyzz(v, sh);
+  if (threadIdx.x == 0) store_rw(part + (size_t)w * gridDim.x + blockIdx.x, tot);
+}
+
+// 9b. window total = sum W + L * (sum of weighted partials), times 2^(c*w) when windows keep their own
+//     bucket sets (variable_base.rs:168-175).  Lower half of the CTA tree-sums the weighted partials,
+//     upper half the W row sums, concurrently.
+__global__ void __launch_bounds__(2 * RED_THREADS)
+k_window_total(const XYZZ* __restrict__ part, uint32_t nparts, const XYZZ* __restrict__ wrow_sum, uint32_t H2, int log_l,
+               int c, int merged, XYZZ* __restrict__ win_sum) {
+  extern __shared__ uint4 sh_raw[];
+  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
+  const int w = blockIdx.x;
+  const uint32_t half = blockDim.x >> 1;
+  const uint32_t t = threadIdx.x % half;
+  const bool upper = threadIdx.x >= half;
+  const XYZZ* src = upper ? wrow_sum + (size_t)w * H2 : part + (size_t)w * nparts;
+  const uint32_t cnt = upper ? H2 : nparts;
+  XYZZ acc = XYZZ::identity();
+  for (uint32_t k = t; k < cnt; k += half) {
+    XYZZ v = load_rw(src + k);
+    xyzz_add(acc, v);
+  }
+  store_rw(sh + threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t s = half >> 1; s > 0; s >>= 1) {
+    if (t < s) {
+      XYZZ a = load_rw(sh + threadIdx.x);
+      XYZZ b2 = load_rw(sh + threadIdx.x + s);
+      xyzz_add(a, b2);
+      store_rw(sh + threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    XYZZ tot = load_rw(sh);
+    for (int d = 0; d < log_l; d++) xyzz_dbl(tot);
+    XYZZ wsum = load_rw(sh + half);
+    xyzz_add(tot, wsum);
+    if (!merged)
+      for (int d = 0; d < c * w; d++) xyzz_dbl(tot);
     store_rw(win_sum + w, tot);
   }
 }
@@ -631,7 +699,15 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   const size_t max_split = refs / SPLIT + 1;
   const size_t max_partials = 2 * max_split + 1;
   const size_t max_items = M + max_split + 1;
-  const uint32_t parts_per_win = (P.nchunks + RED_THREADS - 1) / RED_THREADS;
+  // chunk index t = hi * L2 + lo, an H2 x L2 matrix (both powers of two)
+  int log_t = 0;
+  while ((1u << log_t) < P.nchunks) log_t++;
+  const int log_l2 = (log_t + 1) / 2;
+  const uint32_t L2 = 1u << log_l2, H2 = P.nchunks >> log_l2;
+  int log_l = 0;
+  while ((1 << log_l) < P.L) log_l++;
+  const uint32_t ctas_c = (L2 + RED_THREADS - 1) / RED_THREADS, ctas_r = (H2 + RED_THREADS - 1) / RED_THREADS;
+  const uint32_t nparts = ctas_c + ctas_r;
 
   GM_TRY(S.digits.reserve(refs * 4));
   GM_TRY(S.sorted.reserve(refs * 4));
@@ -645,12 +721,15 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   GM_TRY(S.split.reserve(max_split * 4));
   const size_t ntiles = (M + SCAN_TILE - 1) / SCAN_TILE;
   GM_TRY(S.scan_tmp.reserve(ntiles * 4 + 16));
-  // small: Meta | chunk_s | chunk_w | block_part | win_sum
+  // small: Meta | chunk_s | chunk_w | row_sum | wrow_sum | col_sum | part | win_sum
   const size_t off_meta = 0;
   const size_t off_cs = 4096;
   const size_t off_cw = off_cs + (size_t)Weff * P.nchunks * sizeof(XYZZ);
-  const size_t off_bp = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
-  const size_t off_ws = off_bp + (size_t)Weff * parts_per_win * sizeof(XYZZ);
+  const size_t off_rs = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
+  const size_t off_wr = off_rs + (size_t)Weff * H2 * sizeof(XYZZ);
+  const size_t off_col = off_wr + (size_t)Weff * H2 * sizeof(XYZZ);
+  const size_t off_bp = off_col + (size_t)Weff * L2 * sizeof(XYZZ);
+  const size_t off_ws = off_bp + (size_t)Weff * nparts * sizeof(XYZZ);
   const size_t small_bytes = off_ws + (size_t)Weff * sizeof(XYZZ);
   static_assert(sizeof(Meta) <= 4096, "Meta fits its slot");
   GM_TRY(S.small.reserve(small_bytes));
@@ -658,7 +737,10 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   Meta* meta = reinterpret_cast<Meta*>(sm + off_meta);
   XYZZ* chunk_s = reinterpret_cast<XYZZ*>(sm + off_cs);
   XYZZ* chunk_w = reinterpret_cast<XYZZ*>(sm + off_cw);
-  XYZZ* block_part = reinterpret_cast<XYZZ*>(sm + off_bp);
+  XYZZ* row_sum = reinterpret_cast<XYZZ*>(sm + off_rs);
+  XYZZ* wrow_sum = reinterpret_cast<XYZZ*>(sm + off_wr);
+  XYZZ* col_sum = reinterpret_cast<XYZZ*>(sm + off_col);
+  XYZZ* part = reinterpret_cast<XYZZ*>(sm + off_bp);
   XYZZ* win_sum = reinterpret_cast<XYZZ*>(sm + off_ws);
 
   cudaStream_t st = ctx->stream;
@@ -683,8 +765,9 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
          S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, S.partials.as<XYZZ>(), S.buckets.as<XYZZ>());
   LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, S.buckets.as<XYZZ>(), S.counts.as<uint32_t>(), P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
-  LAUNCH(ctx, k_chunk_weight, dim3(parts_per_win, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.L, P.nchunks, block_part);
-  LAUNCH(ctx, k_window_finish, Weff, RED_THREADS, red_sh, block_part, parts_per_win, P.c, win_sum);
+  LAUNCH(ctx, k_rowcol, dim3(2 * H2 + L2, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
+  LAUNCH(ctx, k_weighted, dim3(nparts, Weff), RED_THREADS, red_sh, row_sum, col_sum, H2, L2, log_l2, ctas_c, part);
+  LAUNCH(ctx, k_window_total, Weff, 2 * RED_THREADS, 2 * red_sh, part, nparts, wrow_sum, H2, log_l, P.c, merged ? 1 : 0, win_sum);
   LAUNCH(ctx, k_final, 1, 32, 0, win_sum, Weff, d_acc);
   GM_CUDA(cudaEventRecord(ctx->ev[5], st));
   GM_CUDA(cudaGetLastError());

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Config 3 of BASELINE.json: subprotocols::sumcheck + herring fold over 2^logn Fr elements on one B200.
+
+Reports device time (CUDA events on the library stream) of (a) one fold_polynomial pass, (b) a full
+TimeProver run (all rounds, challenges fed back from the host), for twist = 1 and a random twist, as
+achieved HBM GB/s against the algorithmic bytes of SURVEY.md 8(d): fold 48 B per input element;
+full sumcheck 256*n B.  Prints one JSON object per line."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import numpy as np
+
+    import gemini_b200 as gm
+    from gemini_b200 import field
+    from gemini_b200._lib import check, lib
+    import ctypes as C
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--logn", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    n = 1 << args.logn
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    ctx = gm.Context(0)
+    d_f, d_g, d_o = ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 16)
+    ctx.fr_random_dev(d_f, n, 1)
+    ctx.fr_random_dev(d_g, n, 2)
+    r = field.fr_to_limbs([0x1234567890ABCDEF1234567890ABCDEF % field.R])
+    # (a) fold
+    times = []
+    for _ in range(args.reps + 2):
+        ctx.l2_flush()
+        check(lib.gm_fr_fold_dev(ctx._h, C.c_void_p(d_f), n, C.c_void_p(r.ctypes.data), C.c_void_p(d_o)))
+        times.append(ctx.last_device_ms(0))
+    ms = min(times[2:])
+    print(json.dumps({"kernel": "k_fr_fold", "n": n, "ms": ms, "GBps": n * 48 / ms / 1e6, "frac_of_hbm_peak": n * 48 / ms / 1e6 / peak}))
+    # (b) full sumcheck, device-resident inputs
+    import random
+    rng = random.Random(7)
+    for name, twist, flavour in (("gemini twist=1", 1, 0), ("gemini random twist", rng.randrange(field.R), 0), ("herring", rng.randrange(field.R), 1)):
+        best = None
+        for _ in range(max(2, args.reps // 2)):
+            tw = field.fr_to_limbs([twist])
+            h = C.c_void_p()
+            check(lib.gm_sumcheck_new_dev(ctx._h, C.c_void_p(d_f), n, C.c_void_p(d_g), n, C.c_void_p(tw.ctypes.data), flavour, C.byref(h)))
+            out = np.empty(8, dtype=np.uint64)
+            has = C.c_int(0)
+            chal = [field.fr_to_limbs([rng.randrange(field.R)]) for _ in range(args.logn + 1)]
+            ctx.l2_flush()
+            ctx.synchronize()
+            l0 = ctx.launch_count
+            t0 = time.perf_counter()
+            ctx.timer_start()
+            check(lib.gm_sumcheck_next_message(h, None, C.c_void_p(out.ctypes.data), C.byref(has)))
+            k = 0
+            first_ms = None
+            while has.value:
+                if first_ms is None:
+                    first_ms = ctx.last_device_ms(0)
+                check(lib.gm_sumcheck_next_message(h, C.c_void_p(chal[k].ctypes.data), C.c_void_p(out.ctypes.data), C.byref(has)))
+                k += 1
+            ms = ctx.timer_stop()
+            wall = 1e3 * (time.perf_counter() - t0)
+            lib.gm_sumcheck_free(h)
+            if best is None or ms < best[0]:
+                best = (ms, wall, k, ctx.launch_count - l0)
+        ms, wall, rounds, launches = best
+        print(json.dumps({"prover": name, "n": n, "rounds": rounds, "device_ms": ms, "wall_ms": wall, "launches": launches,
+                          "GBps_at_256n": 256 * n / ms / 1e6, "frac_of_hbm_peak": 256 * n / ms / 1e6 / peak,
+                          "elements_per_s": 2 * n / (ms / 1e3)}))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
