@@ -232,13 +232,16 @@ struct Fp {
 using Fq = Fp<FqParams>;
 using Fr = Fp<FrParams>;
 
-// a^(p-2) by square-and-multiply (field inversion; a != 0).  Loop is rolled on
-// purpose: it runs once per MSM (final normalisation), never in a hot loop.
+// ---------------------------------------------------------------------------
+// Inversion.  fp_inv_fermat: a^(p-2), ~570 Montgomery products.  fp_inv: Kaliski's "almost Montgomery
+// inverse" (binary extended Euclid: shifts, compares and subtractions on N-limb integers, no products)
+// followed by the power-of-two correction - about 5x fewer instructions, which matters because the
+// inversion sits on the serial tail of every MSM (normalisation of the result to Z = 1).
+// ---------------------------------------------------------------------------
 template <class P>
-GM_HD Fp<P> fp_inv(const Fp<P>& a) {
+GM_HD Fp<P> fp_inv_fermat(const Fp<P>& a) {
   constexpr int N = P::N;
   uint32_t e[N];
-  // e = p - 2 (p is odd and p mod 2^32 >= 2 for both fields? handled generally)
   uint32_t borrow = 0;
   for (int j = 0; j < N; j++) {
     uint64_t t = (uint64_t)P::mod(j) - (j == 0 ? 2u : 0u) - borrow;
@@ -252,6 +255,86 @@ GM_HD Fp<P> fp_inv(const Fp<P>& a) {
     if ((e[bit >> 5] >> (bit & 31)) & 1u) acc = acc * a;
   }
   return acc;
+}
+
+namespace detail {
+template <int N> GM_HD bool limbs_is_zero(const uint32_t* x) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < N; j++) acc |= x[j];
+  return acc == 0;
+}
+template <int N> GM_HD void limbs_shr1(uint32_t* x) {
+#pragma unroll
+  for (int j = 0; j < N - 1; j++) x[j] = (x[j] >> 1) | (x[j + 1] << 31);
+  x[N - 1] >>= 1;
+}
+template <int N> GM_HD void limbs_shl1(uint32_t* x) {
+#pragma unroll
+  for (int j = N - 1; j > 0; j--) x[j] = (x[j] << 1) | (x[j - 1] >> 31);
+  x[0] <<= 1;
+}
+// r = a - b, returns true if a < b (borrow)
+template <int N> GM_HD bool limbs_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int j = 1; j < N; j++) r[j] = subc_cc(a[j], b[j]);
+  return subc(0, 0) != 0;
+}
+template <int N> GM_HD void limbs_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int j = 1; j < N - 1; j++) r[j] = addc_cc(a[j], b[j]);
+  r[N - 1] = addc(a[N - 1], b[N - 1]);
+}
+}  // namespace detail
+
+// a != 0, a in Montgomery form; returns a^{-1} in Montgomery form.
+template <class P>
+GM_HD Fp<P> fp_inv(const Fp<P>& a) {
+  constexpr int N = P::N;
+  uint32_t u[N], v[N], r[N], s[N], t[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) { u[j] = P::mod(j); v[j] = a.v[j]; r[j] = 0; s[j] = (j == 0) ? 1u : 0u; }
+  int k = 0;
+  // invariant: p = u*s + v*r (so r, s <= p while u, v >= 1; they fit N limbs since 2p < 2^(32N))
+#pragma unroll 1
+  while (!detail::limbs_is_zero<N>(v) && k < 64 * N) {  // k <= 2 * bits(p) < 64N: the bound only guards against a hang
+    if ((u[0] & 1u) == 0) {
+      detail::limbs_shr1<N>(u); detail::limbs_shl1<N>(s);
+    } else if ((v[0] & 1u) == 0) {
+      detail::limbs_shr1<N>(v); detail::limbs_shl1<N>(r);
+    } else {
+      const bool v_lt_u = detail::limbs_sub<N>(t, v, u);   // t = v - u
+      if (v_lt_u) {                                         // u > v
+        detail::limbs_sub<N>(u, u, v);
+        detail::limbs_shr1<N>(u);
+        detail::limbs_add<N>(r, r, s);
+        detail::limbs_shl1<N>(s);
+      } else {                                              // v >= u (v == u ends the loop: v becomes 0)
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = t[j];
+        detail::limbs_shr1<N>(v);
+        detail::limbs_add<N>(s, s, r);
+        detail::limbs_shl1<N>(r);
+      }
+    }
+    k++;
+  }
+  // r = -a^{-1} 2^k (mod p), r < 2p
+  detail::cond_sub_p<P>(r, r);
+  Fp<P> x;
+  {
+    uint32_t pm[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) pm[j] = P::mod(j);
+    detail::limbs_sub<N>(x.v, pm, r);   // p - r in (0, p]
+    detail::cond_sub_p<P>(x.v, x.v);
+  }
+  // x = (aR)^{-1} 2^k = a'^{-1} 2^(k - 32N); the Montgomery form of the inverse is a'^{-1} 2^(32N): double 64N - k times
+#pragma unroll 1
+  for (int i = k; i < 64 * N; i++) x = x.dbl();
+  return x;
 }
 
 }  // namespace gm

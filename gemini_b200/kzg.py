@@ -85,6 +85,33 @@ class CommitterKey:
     def commit_raw(self, polynomial) -> np.ndarray:
         return self.ctx.msm(self.srs, polynomial)
 
+    def index_by(self, indices: Sequence[int]) -> "CommitterKey":
+        """time.rs:86-95: new key with powers_of_g[i] = sum of the g_j whose index is i (identity elsewhere).
+        Only psnark uses it (outside this tier's hot path): the group sums run on the device, one
+        gm_g1_sum per non-trivial target."""
+        pts = self.srs.read()
+        n = pts.shape[0]
+        groups: dict = {}
+        for j, i in enumerate(list(indices)[:n]):
+            groups.setdefault(i, []).append(j)
+        out = np.zeros_like(pts)
+        one = field.affine_to_jacobian_limbs((0, 0))[12:18]
+        for i, js in groups.items():
+            if len(js) == 1:
+                out[i] = pts[js[0]]
+                continue
+            jac = np.zeros((len(js), 18), dtype=np.uint64)
+            for k, j in enumerate(js):
+                if pts[j].any():
+                    jac[k, :12] = pts[j]
+                    jac[k, 12:] = one
+                else:
+                    jac[k] = field.affine_to_jacobian_limbs(None)
+            tot = self.ctx.g1_sum(jac)
+            if tot[12:].any():
+                out[i] = tot[:12]
+        return CommitterKey(self.ctx, out)
+
     def batch_commit(self, polynomials) -> List[field.Point]:
         """time.rs:98-107."""
         return [self.commit(p) for p in polynomials]

@@ -231,6 +231,34 @@ class Sumcheck:
         return cls(messages, challenges, prover.rounds(), [prover.final_foldings()])
 
     @classmethod
+    def prove_batch(cls, provers, coefficient_fn: Callable[[], int], challenge_fn) -> "Sumcheck":
+        """proof.rs:69-122: random linear combination of the messages of several provers.  The transcript is
+        abstracted as ``coefficient_fn() -> batch-sumcheck challenge`` and ``challenge_fn(message)``.  The
+        reference drives the provers from rayon workers (proof.rs:85); handles here are independent and the
+        device kernels of different provers are queued back to back on the context's stream."""
+        R = field.R
+        rounds = max((p.rounds() for p in provers), default=0) + 1
+        coefficients = [coefficient_fn() % R for _ in provers]
+        messages, challenges = [], []
+        vm = None
+        for _ in range(rounds):
+            a_tot = b_tot = 0
+            for p, c in zip(provers, coefficients):
+                msg = p.next_message(vm)
+                if msg is None:
+                    ff = p.final_foldings()
+                    assert ff is not None, "If next_message is None, we expect final foldings to be available"
+                    msg = (ff[0] * ff[1] % R, 0)
+                a_tot = (a_tot + msg[0] * c) % R
+                b_tot = (b_tot + msg[1] * c) % R
+            message = (a_tot, b_tot)
+            ch = challenge_fn(message) % R
+            vm = ch
+            messages.append(message)
+            challenges.append(ch)
+        return cls(messages, challenges, rounds, [p.final_foldings() for p in provers])
+
+    @classmethod
     def new_time(cls, ctx: Context, challenge_fn, f, g, twist: int) -> "Sumcheck":
         return cls.prove(TimeProver(ctx, f, g, twist), challenge_fn)
 

@@ -723,6 +723,36 @@ def sumcheck_prove(prover, challenge_fn: Callable[[Tuple[int, int]], int]):
     return messages, challenges, prover.final_foldings()
 
 
+def sumcheck_prove_batch(provers, coefficient_fn, challenge_fn):
+    """Sumcheck::prove_batch, proof.rs:69-122."""
+    rounds = max((p.tot_rounds for p in provers), default=0) + 1
+    coefficients = [coefficient_fn() % R for _ in provers]
+    messages, challenges = [], []
+    vm = None
+    for _ in range(rounds):
+        a_tot = b_tot = 0
+        for p, c in zip(provers, coefficients):
+            msg = p.next_message(vm)
+            if msg is None:
+                ff = p.final_foldings()
+                msg = (ff[0] * ff[1] % R, 0)
+            a_tot = (a_tot + msg[0] * c) % R
+            b_tot = (b_tot + msg[1] * c) % R
+        ch = challenge_fn((a_tot, b_tot)) % R
+        vm = ch
+        messages.append((a_tot, b_tot))
+        challenges.append(ch)
+    return messages, challenges, [p.final_foldings() for p in provers]
+
+
+def kzg_index_by(powers_of_g: Sequence[Point], indices: Sequence[int]) -> List[Point]:
+    """CommitterKey::index_by, kzg/time.rs:86-95."""
+    out: List[Point] = [None] * len(powers_of_g)
+    for i, g in zip(indices, powers_of_g):
+        out[i] = g1_add(out[i], g)
+    return out
+
+
 def subclaim_reduce(messages, challenges, asserted_sum: int) -> int:
     """Verifier recurrence, subclaim.rs:77-97."""
     claim = asserted_sum % R

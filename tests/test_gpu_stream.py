@@ -97,3 +97,14 @@ def test_commit_folding(ctx, n, k):
     chals = rand_scalars(k, 38)
     cks = gm.CommitterKeyStream(ctx, srs[::-1])
     assert cks.commit_folding(poly_be, chals, 20) == o.kzg_commit_folding(srs[::-1], poly_be, chals, 20)
+
+
+def test_index_by(ctx):
+    """kzg/time.rs:86-95 (psnark's row/column keys): merged and permuted SRS, identity where unused."""
+    srs = rand_points(12, 60)
+    idx = [3, 0, 3, 7, 7, 7, 1, 0, 11, 5, 5, 2]
+    ck = gm.CommitterKey(ctx, srs).index_by(idx)
+    want = o.kzg_index_by(srs, idx)
+    assert ck.srs.points() == want
+    poly = rand_scalars(12, 61)
+    assert ck.commit(poly) == o.kzg_commit(want, poly)

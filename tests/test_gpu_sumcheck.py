@@ -114,3 +114,19 @@ def test_elastic_explicit_fold_switches_to_time(ctx):
         assert dev.is_space == ref.is_space
         assert dev.next_message(None) == ref.next_message(None)
     assert dev.final_foldings() == ref.final_foldings()
+
+
+def test_prove_batch(ctx):
+    """sumcheck/tests.rs:226-269: several provers of different sizes under one random linear combination."""
+    specs = [(64, 64, 5), (16, 16, 1), (100, 100, 7), (1, 1, 1)]
+    mk_ref, mk_dev = [], []
+    for nf, ng, tw in specs:
+        f, g = rand_scalars(nf, nf + 11), rand_scalars(ng, ng + 12)
+        mk_ref.append(o.TimeProver(f, g, tw))
+        mk_dev.append(gm.TimeProver(ctx, f, g, tw))
+    coeffs = rand_scalars(len(specs), 77)
+    c1, c2 = iter(coeffs), iter(coeffs)
+    want = o.sumcheck_prove_batch(mk_ref, lambda: next(c1), challenge_fn_factory(5))
+    got = gm.Sumcheck.prove_batch(mk_dev, lambda: next(c2), challenge_fn_factory(5))
+    assert (got.messages, got.challenges, got.final_foldings) == want
+    assert got.rounds == 8
