@@ -79,6 +79,16 @@ SIGNATURES = {
     "gm_dev_upload": (_i, [_vp, _vp, _vp, _sz]),
     "gm_dev_download": (_i, [_vp, _vp, _vp, _sz]),
     "gm_fr_random_dev": (_i, [_vp, _vp, _sz, _u64]),
+    "gm_dev_memset": (_i, [_vp, _vp, _i, _sz]),
+    "gm_dev_copy": (_i, [_vp, _vp, _vp, _sz]),
+    "gm_fr_powers_dev": (_i, [_vp, _vp, _sz, _vp]),
+    "gm_fr_eval_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "gm_fr_tensor_dev": (_i, [_vp, _vp, _sz, _vp]),
+    "gm_fr_hadamard_dev": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "gm_fr_axpy_dev": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "gm_fr_spmv_dev": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "gm_fr_div_linear_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "gm_fr_fold_chain_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "gm_selftest_field": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     "gm_selftest_curve": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
 }

@@ -99,6 +99,8 @@ int gm_shutdown(gm_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->d_flush) cudaFree(ctx->d_flush);
+  ctx->fr_red.release();
+  ctx->fr_div.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);

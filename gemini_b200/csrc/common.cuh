@@ -95,6 +95,8 @@ struct gm_ctx {
   size_t pinned_bytes = 0;
   void* d_result = nullptr;  // device result slot (accumulator + normalised output)
   void* d_flush = nullptr;   // 256 MB scratch written by gm_l2_flush
+  gm::DevBuf fr_red;         // reduction partials + ticket + result of the Fr vector helpers
+  gm::DevBuf fr_div;         // level arrays of the synthetic-division scan
 };
 
 struct gm_srs {

@@ -13,6 +13,8 @@
 //   herring : the same with twist = 1 (herring/time_prover.rs:91-123 applies the twist only in fold)
 // Missing elements (odd tails, unequal lengths) read as zero, exactly like the reference's
 // `unwrap_or(&zero)` / zip-to-shorter (a product with a zero partner vanishes).
+#include <vector>
+
 #include "common.cuh"
 #include "fp.cuh"
 #include "fr.cuh"
@@ -216,6 +218,143 @@ __global__ void k_fr_random(Fr* __restrict__ out, size_t n, uint64_t seed) {
   }
 }
 
+// =============================================================================================
+// Fr vector helpers of the time prover: everything between the MSMs and the
+// sumchecks of snark::Proof::new_time (/root/reference/src/snark/time_prover.rs:19-117) and
+// TensorcheckProof::new_time (/root/reference/src/subprotocols/tensorcheck/mod.rs:190-275) so that the
+// prover's vectors never leave HBM.  The CPU reference runs all of these as serial O(n) loops.
+// =============================================================================================
+
+// out[i] = x^i  (misc::powers, src/misc.rs:59-65); tab.p[k] = x^(2^k)
+__global__ void __launch_bounds__(SC_THREADS)
+k_fr_powers(Fr* __restrict__ out, size_t n, PowTable tab) {
+  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  if (i0 >= n) return;
+  Fr t = pow_from_table(tab, i0);
+  const Fr step = tab.p[8];  // x^SC_THREADS
+#pragma unroll 1
+  for (int k = 0; k < SC_K; k++) {
+    const size_t i = i0 + (size_t)k * SC_THREADS;
+    if (i >= n) break;
+    store_fr(out + i, t);
+    t = t * step;
+  }
+}
+
+// (E, O) = (sum_{i even} f_i x^i, sum_{i odd} f_i x^i): f(x) = E + O and f(-x) = E - O in one pass
+// (misc::evaluate_le, src/misc.rs:194-199; tensorcheck evaluates every polynomial at beta and -beta,
+// tensorcheck/mod.rs:228-247).  tab.p[k] = (x^2)^(2^k).
+__global__ void __launch_bounds__(SC_THREADS)
+k_fr_eval_even_odd(const Fr* __restrict__ f, size_t n, Fr x, PowTable tab, Fr* partials, unsigned int* ticket, Fr* out) {
+  const size_t npairs = (n + 1) / 2;
+  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  Fr e = Fr::zero(), o = Fr::zero();
+  Fr t = Fr::one(), step = Fr::one();
+  if (i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }
+#pragma unroll 1
+  for (int k = 0; k < SC_K; k++) {
+    const size_t i = i0 + (size_t)k * SC_THREADS;
+    if (i >= npairs) break;
+    e = e + load_fr(f + 2 * i) * t;
+    if (2 * i + 1 < n) o = o + load_fr(f + 2 * i + 1) * t;
+    t = t * step;
+  }
+  o = o * x;  // sum f_{2i+1} x^(2i) times x
+  sc_reduce_and_publish(e, o, partials, ticket, out);
+}
+
+// out[idx] = prod_{bit j of idx set} rho_j  (misc::tensor, src/misc.rs:133-149).  Each thread owns 16
+// consecutive indices: the product over the high bits once, then the 16 combinations of rho_0..rho_3.
+struct TensorArgs {
+  Fr rho[32];
+  int k;
+};
+__global__ void __launch_bounds__(256)
+k_fr_tensor(Fr* __restrict__ out, size_t n, TensorArgs args) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = g * 16;
+  if (base >= n) return;
+  Fr hi = Fr::one();
+  for (int j = 4; j < args.k; j++)
+    if ((base >> j) & 1) hi = hi * args.rho[j];
+  Fr low[16];
+  low[0] = Fr::one();
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (j < args.k) {
+#pragma unroll
+      for (int m = 0; m < (1 << j); m++) low[(1 << j) + m] = low[m] * args.rho[j];
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 16; m++)
+    if (base + m < n) store_fr(out + base + m, m == 0 ? hi : hi * low[m]);
+}
+
+// out[i] = a[i] * b[i]  (misc::hadamard, src/misc.rs:205-208)
+__global__ void __launch_bounds__(256)
+k_fr_hadamard(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t n, Fr* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    store_fr(out + i, load_fr(a + i) * load_fr(b + i));
+}
+
+// acc[i] += c * x[i], i < n  (misc::linear_combination, src/misc.rs:37-48, one term at a time)
+__global__ void __launch_bounds__(256)
+k_fr_axpy(Fr* __restrict__ acc, const Fr* __restrict__ x, size_t n, Fr c, int c_is_one) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v = load_fr(x + i);
+    if (!c_is_one) v = v * c;
+    store_fr(acc + i, load_fr(acc + i) + v);
+  }
+}
+
+// y[r] = sum_k vals[k] * x[col[k]] over the CSR row r  (misc::product_matrix_vector, src/misc.rs:100-110;
+// with the transposed matrices it is the abc_tensored accumulation of snark/time_prover.rs:63-81)
+__global__ void __launch_bounds__(256)
+k_fr_spmv(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const Fr* __restrict__ vals, size_t nrows,
+          const Fr* __restrict__ x, Fr* __restrict__ y) {
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (size_t)gridDim.x * blockDim.x) {
+    Fr acc = Fr::zero();
+    for (uint32_t k = rowptr[r]; k < rowptr[r + 1]; k++) acc = acc + load_fr(vals + k) * load_fr(x + col[k]);
+    store_fr(y + r, acc);
+  }
+}
+
+// Synthetic division by (X - a) as a hierarchical suffix-Horner scan (KZG quotients, kzg/time.rs:112-145).
+//   S_i = sum_{k>=i} f_k a^(k-i):  quotient q_j = S_{j+1}, remainder = S_0.
+// up-sweep:  next[j] = sum_{k<DIV_K} cur[j*DIV_K + k] * a_l^k        (a_l = a^(DIV_K^level))
+// down-sweep: within run j start from the carry S_next[j+1] and Horner down, writing every S.
+static constexpr int DIV_K = 32;
+__global__ void __launch_bounds__(128)
+k_fr_div_up(const Fr* __restrict__ cur, size_t n, Fr a_l, Fr* __restrict__ next) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t lo = j * DIV_K;
+  if (lo >= n) return;
+  const size_t hi = min(lo + (size_t)DIV_K, n);
+  Fr acc = Fr::zero();
+  for (size_t k = hi; k-- > lo;) acc = load_fr(cur + k) + a_l * acc;
+  store_fr(next + j, acc);
+}
+// suffix: S of the next level (nullptr at the top level); out_shift = 1 at level 0 (q_j = S_{j+1}) else 0
+__global__ void __launch_bounds__(128)
+k_fr_div_down(const Fr* __restrict__ cur, size_t n, Fr a_l, const Fr* __restrict__ suffix_next, size_t n_next,
+              Fr* __restrict__ out, int out_shift, Fr* __restrict__ rem) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t lo = j * DIV_K;
+  if (lo >= n) return;
+  const size_t hi = min(lo + (size_t)DIV_K, n);
+  Fr acc = (suffix_next != nullptr && j + 1 < n_next) ? load_fr(suffix_next + j + 1) : Fr::zero();
+  for (size_t k = hi; k-- > lo;) {
+    acc = load_fr(cur + k) + a_l * acc;
+    if (out_shift) {
+      if (k >= 1) store_fr(out + k - 1, acc);
+      else store_fr(rem, acc);
+    } else {
+      store_fr(out + k, acc);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -291,6 +430,112 @@ int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, si
     PowTable tab;
     LAUNCH(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab,
            d_partials, d_ticket, d_out);
+  }
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+// ---- vector helpers ---------------------------------------------------------------------------
+static PowTable make_pow_table_base(const Fr& base, size_t count) {
+  PowTable tab;
+  Fr x = base;
+  int need = 9;
+  while (need < 40 && (count >> need)) need++;
+  for (int k = 0; k < 40; k++) {
+    if (k < need) { tab.p[k] = x; x = x.sqr(); }
+    else tab.p[k] = Fr::one();
+  }
+  return tab;
+}
+
+int fr_powers_dev(gm_ctx* ctx, const Fr& x, size_t n, Fr* d_out) {
+  if (n == 0) return GM_OK;
+  PowTable tab = make_pow_table_base(x, n);
+  LAUNCH(ctx, k_fr_powers, (unsigned)((n + SC_TILE - 1) / SC_TILE), SC_THREADS, 0, d_out, n, tab);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_eval_even_odd_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& x, Fr* d_partials, unsigned int* d_ticket, Fr* d_out) {
+  const size_t npairs = (n + 1) / 2;
+  PowTable tab = make_pow_table_base(x.sqr(), npairs);
+  const unsigned grid = (unsigned)std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+  LAUNCH(ctx, k_fr_eval_even_odd, grid, SC_THREADS, 0, d_f, n, x, tab, d_partials, d_ticket, d_out);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_tensor_dev(gm_ctx* ctx, const Fr* rho, int k, Fr* d_out) {
+  if (k < 0 || k > 32) { set_error("tensor: 0..32 challenges supported"); return GM_ERR_ARG; }
+  TensorArgs args;
+  for (int j = 0; j < 32; j++) args.rho[j] = j < k ? rho[j] : Fr::one();
+  args.k = k;
+  const size_t n = (size_t)1 << k;
+  const size_t threads = (n + 15) / 16;
+  LAUNCH(ctx, k_fr_tensor, (unsigned)((threads + 255) / 256), 256, 0, d_out, n, args);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_hadamard_dev(gm_ctx* ctx, const Fr* d_a, const Fr* d_b, size_t n, Fr* d_out) {
+  if (n == 0) return GM_OK;
+  LAUNCH(ctx, k_fr_hadamard, fold_grid(ctx, n), 256, 0, d_a, d_b, n, d_out);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_axpy_dev(gm_ctx* ctx, Fr* d_acc, const Fr* d_x, size_t n, const Fr& c) {
+  if (n == 0) return GM_OK;
+  LAUNCH(ctx, k_fr_axpy, fold_grid(ctx, n), 256, 0, d_acc, d_x, n, c, c == Fr::one() ? 1 : 0);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_spmv_dev(gm_ctx* ctx, const uint32_t* d_rowptr, const uint32_t* d_col, const Fr* d_vals, size_t nrows, const Fr* d_x, Fr* d_y) {
+  if (nrows == 0) return GM_OK;
+  LAUNCH(ctx, k_fr_spmv, fold_grid(ctx, nrows), 256, 0, d_rowptr, d_col, d_vals, nrows, d_x, d_y);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+size_t fr_div_scratch_elems(size_t n) {
+  size_t tot = 0;
+  while (n > 1) { n = (n + DIV_K - 1) / DIV_K; tot += 2 * n; }
+  return tot + 2;
+}
+
+// q (n-1 elements) and remainder of f / (X - a); d_scratch holds fr_div_scratch_elems(n) elements
+int fr_div_linear_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& a, Fr* d_q, Fr* d_rem, Fr* d_scratch) {
+  if (n == 0) { GM_CUDA(cudaMemsetAsync(d_rem, 0, 32, ctx->stream)); return GM_OK; }
+  // level arrays: A^l (aggregates) and S^l (suffixes), l >= 1
+  std::vector<size_t> sizes{n};
+  std::vector<Fr> apow{a};
+  while (sizes.back() > 1) {
+    sizes.push_back((sizes.back() + DIV_K - 1) / DIV_K);
+    Fr p = apow.back();
+    for (int k = 0; k < 5; k++) p = p.sqr();  // ^32 = DIV_K
+    apow.push_back(p);
+  }
+  const int levels = (int)sizes.size() - 1;
+  std::vector<Fr*> A(levels + 1), S(levels + 1);
+  A[0] = const_cast<Fr*>(d_f);
+  Fr* cursor = d_scratch;
+  for (int l = 1; l <= levels; l++) { A[l] = cursor; cursor += sizes[l]; S[l] = cursor; cursor += sizes[l]; }
+  for (int l = 0; l < levels; l++) {
+    const size_t runs = sizes[l + 1];
+    LAUNCH(ctx, k_fr_div_up, (unsigned)((runs + 127) / 128), 128, 0, A[l], sizes[l], apow[l], A[l + 1]);
+  }
+  // top level has one element: its suffix is itself
+  if (levels >= 1) GM_CUDA(cudaMemcpyAsync(S[levels], A[levels], 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int l = levels - 1; l >= 0; l--) {
+    const size_t runs = sizes[l + 1];
+    if (l == 0)
+      LAUNCH(ctx, k_fr_div_down, (unsigned)((runs + 127) / 128), 128, 0, A[0], sizes[0], apow[0], S[1], sizes[1], d_q, 1, d_rem);
+    else
+      LAUNCH(ctx, k_fr_div_down, (unsigned)((runs + 127) / 128), 128, 0, A[l], sizes[l], apow[l], S[l + 1], sizes[l + 1], S[l], 0, d_rem);
+  }
+  if (levels == 0) {  // n == 1: quotient empty, remainder f_0
+    GM_CUDA(cudaMemcpyAsync(d_rem, d_f, 32, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   GM_CUDA(cudaGetLastError());
   return GM_OK;

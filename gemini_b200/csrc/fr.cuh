@@ -20,4 +20,14 @@ int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, si
                         Fr* d_f_out, Fr* d_g_out, const Fr& new_twist, bool use_twist, Fr* d_partials,
                         unsigned int* d_ticket, Fr* d_out);
 
+// ---- vector helpers of the time prover (all asynchronous on ctx->stream) ----
+int fr_powers_dev(gm_ctx* ctx, const Fr& x, size_t n, Fr* d_out);
+int fr_eval_even_odd_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& x, Fr* d_partials, unsigned int* d_ticket, Fr* d_out);
+int fr_tensor_dev(gm_ctx* ctx, const Fr* rho, int k, Fr* d_out);
+int fr_hadamard_dev(gm_ctx* ctx, const Fr* d_a, const Fr* d_b, size_t n, Fr* d_out);
+int fr_axpy_dev(gm_ctx* ctx, Fr* d_acc, const Fr* d_x, size_t n, const Fr& c);
+int fr_spmv_dev(gm_ctx* ctx, const uint32_t* d_rowptr, const uint32_t* d_col, const Fr* d_vals, size_t nrows, const Fr* d_x, Fr* d_y);
+size_t fr_div_scratch_elems(size_t n);
+int fr_div_linear_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& a, Fr* d_q, Fr* d_rem, Fr* d_scratch);
+
 }  // namespace gm

@@ -151,6 +151,32 @@ int gm_dev_download(gm_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
  * (splitmix64 counter stream; bench / full-size property tests) */
 int gm_fr_random_dev(gm_ctx* ctx, void* out_dev, size_t n, uint64_t seed);
 
+/* ---- Fr vectors of the time prover, device resident.  All pointers are device
+ *      pointers of the ctx's GPU; calls are queued on the ctx stream and return without synchronising
+ *      unless they hand a scalar back to the host. ---- */
+int gm_dev_memset(gm_ctx* ctx, void* dev, int byte, size_t bytes);
+int gm_dev_copy(gm_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+/* out[i] = x^i, i < n: misc::powers (src/misc.rs:59-65) */
+int gm_fr_powers_dev(gm_ctx* ctx, const uint64_t x[4], size_t n, void* out_dev);
+/* out = (E, O) = (sum_{i even} f_i x^i, sum_{i odd} f_i x^i): f(x) = E + O and f(-x) = E - O;
+ * misc::evaluate_le (src/misc.rs:194-199) at beta and -beta in one pass */
+int gm_fr_eval_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t x[4], uint64_t out_even_odd[8]);
+/* out[idx] = prod_{bit j of idx} rho[j], 2^k elements: misc::tensor (src/misc.rs:133-149) */
+int gm_fr_tensor_dev(gm_ctx* ctx, const uint64_t* rho, size_t k, void* out_dev);
+/* out[i] = a[i] * b[i]: misc::hadamard (src/misc.rs:205-208) */
+int gm_fr_hadamard_dev(gm_ctx* ctx, const void* a_dev, const void* b_dev, size_t n, void* out_dev);
+/* acc[i] += c * x[i], i < n: one term of misc::linear_combination (src/misc.rs:37-48) */
+int gm_fr_axpy_dev(gm_ctx* ctx, void* acc_dev, const void* x_dev, size_t n, const uint64_t c[4]);
+/* y = M x for a CSR matrix (u32 rowptr[nrows+1], u32 col[], Fr vals[]): misc::product_matrix_vector
+ * (src/misc.rs:100-110); with the transposed matrices, the abc_tensored sums of snark/time_prover.rs:63-81 */
+int gm_fr_spmv_dev(gm_ctx* ctx, const void* rowptr_dev, const void* col_dev, const void* vals_dev, size_t nrows,
+                   const void* x_dev, void* y_dev);
+/* f = q * (X - a) + rem: q (n-1 coefficients, little-endian) and rem; the quotients of CommitterKey::open /
+ * open_multi_points (src/kzg/time.rs:112-145) as a parallel suffix-Horner scan */
+int gm_fr_div_linear_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t a[4], void* q_dev, uint64_t out_rem[4]);
+/* gm_fr_fold_chain with input and output resident on the device */
+int gm_fr_fold_chain_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t* challenges, size_t k, void* out_levels_dev);
+
 /* ---- self-test kernels (parity tests of the device field / curve arithmetic) ---- */
 /* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 sqr;  field: 0 = Fq (12 u32), 1 = Fr (8 u32) */
 int gm_selftest_field(gm_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, size_t n);

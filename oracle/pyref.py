@@ -841,3 +841,129 @@ def evaluate_folding(coeffs_be, challenges, x: int) -> List[int]:
     for level, c in folded_polynomial_tree(coeffs_be, challenges):
         result[level - 1] = (result[level - 1] * x + c) % R
     return result
+
+
+# --------------------------------------------------------------------------
+# snark::Proof::new_time and TensorcheckProof::new_time (time prover, config 4)
+# --------------------------------------------------------------------------
+def product_matrix_vector(matrix, z: Sequence[int]) -> List[int]:
+    """misc.rs:100-110; matrix = list of rows, each a list of (value, column)."""
+    return [sum(v * z[c] for v, c in row) % R for row in matrix]
+
+
+def tensor(elements: Sequence[int]) -> List[int]:
+    """misc.rs:133-149."""
+    assert len(elements) > 0
+    out = [1] * (1 << len(elements))
+    for i, e in enumerate(elements):
+        for j in range(1 << i):
+            out[(1 << i) + j] = out[j] * e % R
+    return out
+
+
+def linear_combination(polys: Sequence[Sequence[int]], coeffs: Sequence[int]) -> List[int]:
+    """misc.rs:37-48 (zip to the shorter list; DensePolynomial drops trailing zeros)."""
+    n = max((len(p) for p, _ in zip(polys, coeffs)), default=0)
+    out = [0] * n
+    for p, c in zip(polys, coeffs):
+        for i, v in enumerate(p):
+            out[i] = (out[i] + c * v) % R
+    while out and out[-1] == 0:
+        out.pop()
+    return out
+
+
+def kzg_batch_open_multi_points(powers_of_g, polys, points, eval_chal: int) -> Point:
+    """kzg/time.rs:149-159."""
+    etas = powers(eval_chal, len(polys))
+    return kzg_open_multi_points(powers_of_g, linear_combination(polys, etas), points)
+
+
+def sumcheck_prove_transcript(prover, transcript):
+    """Sumcheck::prove with the transcript calls of proof.rs:36-66."""
+    messages, challenges = [], []
+    vm = None
+    while True:
+        msg = prover.next_message(vm)
+        if msg is None:
+            break
+        transcript.append_serializable(b"evaluations", msg)
+        ch = transcript.get_challenge(b"challenge")
+        vm = ch
+        messages.append(msg)
+        challenges.append(ch)
+    ff = prover.final_foldings()
+    transcript.append_serializable(b"final-folding", ff[0])
+    transcript.append_serializable(b"final-folding", ff[1])
+    return {"messages": messages, "challenges": challenges, "rounds": prover.tot_rounds, "final_foldings": [ff]}
+
+
+def tensorcheck_new_time(transcript, powers_of_g, base_polynomials, body_polynomials):
+    """TensorcheckProof::new_time, tensorcheck/mod.rs:190-275.
+    body_polynomials: list of (list of polynomials, challenges)."""
+    max_len = max(len(polys) for polys, _ in body_polynomials)
+    batch_challenge = transcript.get_challenge(b"batch_challenge")
+    batch_challenges = powers(batch_challenge, max_len)
+    foldings = []
+    for polys, chals in body_polynomials:
+        foldings += foldings_polynomial(linear_combination(polys, batch_challenges), chals)
+    commitments = [kzg_commit(powers_of_g, f) for f in foldings]
+    for c in commitments:
+        transcript.append_g1(b"commitment", c)
+    eval_chal = transcript.get_challenge(b"evaluation-chal")
+    minus = (-eval_chal) % R
+    eval_chal2 = eval_chal * eval_chal % R
+    base_evals = [[evaluate_le(p, eval_chal2), evaluate_le(p, eval_chal), evaluate_le(p, minus)] for p in base_polynomials]
+    fold_evals = [[evaluate_le(f, eval_chal), evaluate_le(f, minus)] for f in foldings]
+    for row in base_evals:
+        for e in row:
+            transcript.append_serializable(b"eval", e)
+    for row in fold_evals:
+        for e in row:
+            transcript.append_serializable(b"eval", e)
+    open_chal = transcript.get_challenge(b"open-chal")
+    proof = kzg_batch_open_multi_points(powers_of_g, list(base_polynomials) + foldings, [eval_chal2, eval_chal, minus], open_chal)
+    return {"base_polynomials_evaluations": base_evals, "folded_polynomials_evaluations": fold_evals,
+            "evaluation_proof": proof, "folded_polynomials_commitments": commitments}
+
+
+def dummy_r1cs(e: int, n: int):
+    """circuit.rs:349-365: A = B = C = diag(1/e), z = [e; n], w = [e; n-1], x = [e]."""
+    inv_e = pow(e, -1, R)
+    diag = [[(inv_e, i)] for i in range(n)]
+    return {"a": diag, "b": diag, "c": diag, "z": [e % R] * n, "w": [e % R] * (n - 1), "x": [e % R]}
+
+
+def snark_new_time(r1cs, powers_of_g, transcript):
+    """snark::Proof::new_time, snark/time_prover.rs:19-117."""
+    z = r1cs["z"]
+    z_a = product_matrix_vector(r1cs["a"], z)
+    z_b = product_matrix_vector(r1cs["b"], z)
+    z_c = product_matrix_vector(r1cs["c"], z)
+    witness_commitment = kzg_commit(powers_of_g, r1cs["w"])
+    transcript.append_g1(b"witness", witness_commitment)
+    alpha = transcript.get_challenge(b"alpha")
+    zc_alpha = evaluate_le(z_c, alpha)
+    transcript.append_serializable(b"zc(alpha)", zc_alpha)
+    first = sumcheck_prove_transcript(TimeProver(z_a, z_b, alpha), transcript)
+    b_ch = tensor(first["challenges"])
+    c_ch = powers(alpha, len(b_ch))
+    a_ch = hadamard(b_ch, c_ch)
+    eta = transcript.get_challenge(b"eta")
+    eta2 = eta * eta % R
+    abc = [0] * len(z)
+    for i, row in enumerate(r1cs["a"]):
+        for val, col in row:
+            abc[col] = (abc[col] + a_ch[i] * val) % R
+    for i, row in enumerate(r1cs["b"]):
+        for val, col in row:
+            abc[col] = (abc[col] + eta * b_ch[i] * val) % R
+    for i, row in enumerate(r1cs["c"]):
+        for val, col in row:
+            abc[col] = (abc[col] + eta2 * c_ch[i] * val) % R
+    second = sumcheck_prove_transcript(TimeProver(abc, z, 1), transcript)
+    tc = tensorcheck_new_time(transcript, powers_of_g, [r1cs["w"]], [([abc, z], second["challenges"])])
+    return {"witness_commitment": witness_commitment, "zc_alpha": zc_alpha,
+            "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
+            "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),
+            "tensorcheck_proof": tc}

@@ -3,6 +3,7 @@
 // compare them with Python big integers without a GPU.  Test scaffolding only.
 #include "../../gemini_b200/csrc/fp.cuh"
 #include "../../gemini_b200/csrc/g1.cuh"
+#include "../../gemini_b200/csrc/fq_f64.cuh"
 #include <string.h>
 using namespace gm;
 
@@ -21,10 +22,11 @@ template <class F> static void f_inv(F& z, const F& x, const F&) { z = fp_inv(x)
 template <class F> static void f_redc(F& z, const F& x, const F&) { z = x.from_mont(); }
 template <class F> static void f_tom(F& z, const F& x, const F&) { z = x.to_mont(); }
 template <class F> static void f_sqr(F& z, const F& x, const F&) { z = x.sqr(); }
+static void f_mul_f64(Fq& z, const Fq& x, const Fq& y) { f64::fq_mul_f64(z.v, x.v, y.v); }
 
 extern "C" {
 void hc_fq(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
-  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>};
+  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64};
   bin<Fq>(ops[op], a, b, r, n);
 }
 void hc_fr(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {

@@ -1,0 +1,59 @@
+// Throughput of Fq Montgomery multiplication on B200: integer (IMAD.WIDE) path, FP64 (DFMA) path, and both
+// at once with the warps of each CTA split between the two pipes.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gemini_b200/csrc -o tools/bin/mul_microbench tools/mul_microbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "fq_f64.cuh"
+using namespace gm;
+
+#define ITERS 512
+
+// mode 0: all warps integer; 1: all warps FP64; 2: warps with (warp % den) < num use FP64
+__global__ void __launch_bounds__(128) bench(const Fq* in, Fq* out, int mode, int num, int den) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  Fq x = in[tid & 1023], y = in[(tid + 7) & 1023], b = in[(tid + 13) & 1023];
+  const int warp = threadIdx.x >> 5;
+  const bool fp = mode == 1 || (mode == 2 && (warp % den) < num);
+  if (fp) {
+    for (int it = 0; it < ITERS; it++) {
+      f64::fq_mul_f64(x.v, x.v, b.v);
+      f64::fq_mul_f64(y.v, y.v, b.v);
+    }
+  } else {
+    for (int it = 0; it < ITERS; it++) {
+      x = x * b;
+      y = y * b;
+    }
+  }
+  out[tid] = x + y;
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  const int blocks = p.multiProcessorCount * 8, threads = 128;
+  Fq* in; Fq* out;
+  cudaMalloc(&in, 1024 * sizeof(Fq)); cudaMalloc(&out, (size_t)blocks * threads * sizeof(Fq));
+  Fq h[1024];
+  for (int i = 0; i < 1024; i++) for (int j = 0; j < 12; j++) h[i].v[j] = (j == 11) ? (0x0a000000u + i) : (0x9e3779b9u * (i * 12 + j + 1));
+  cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+  struct { const char* name; int mode, num, den; } cfg[] = {
+      {"integer only (IMAD.WIDE)", 0, 0, 1}, {"FP64 only (DFMA)", 1, 0, 1}, {"split 1/4 FP64", 2, 1, 4},
+      {"split 2/4 FP64", 2, 2, 4}, {"split 3/4 FP64", 2, 3, 4}};
+  Fq ref[4];
+  for (auto& c : cfg) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bench<<<blocks, threads>>>(in, out, c.mode, c.num, c.den);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    bench<<<blocks, threads>>>(in, out, c.mode, c.num, c.den);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    Fq got[4]; cudaMemcpy(got, out, sizeof(got), cudaMemcpyDeviceToHost);
+    bool same = true;
+    if (c.mode == 0) for (int k = 0; k < 4; k++) ref[k] = got[k];
+    else for (int k = 0; k < 4; k++) same = same && (got[k] == ref[k]);
+    double muls = (double)blocks * threads * ITERS * 2;
+    printf("%-28s %8.3f ms  %7.2f G Fq-mul/s  %s (%s)\n", c.name, ms, muls / ms / 1e6, cudaGetErrorString(cudaGetLastError()), same ? "results match integer path" : "MISMATCH");
+  }
+  return 0;
+}
