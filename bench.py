@@ -234,6 +234,9 @@ def run_own(args):
     h_scal = []
     for k in range(nbuf):
         ctx.fr_random_dev(d_scal[k], n, 1000 + 7919 * k + 104729 * rank)
+        if args.scalars == "equal":  # dummy_r1cs (src/circuit.rs:349-365): every scalar identical
+            one = ctx.dev_download(d_scal[k], 32).reshape(1, 4)
+            ctx.dev_upload(d_scal[k], np.ascontiguousarray(np.broadcast_to(one, (n, 4))))
         t = torch.empty(n * 4, dtype=torch.int64).pin_memory()
         arr = ctx.dev_download(d_scal[k], n * 32)
         t.copy_(torch.from_numpy(arr.view(np.int64)))
@@ -329,7 +332,7 @@ def run_own(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"kzg::commit n=2^{args.logn} BLS12-381 G1 per GPU (BASELINE.json configs[1] at logn=20)",
-                   "bases": "P_i=[i+1]G generated on device, resident in HBM", "scalars": "uniform Fr (splitmix64), 2 alternating sets",
+                   "bases": "P_i=[i+1]G generated on device, resident in HBM", "scalars": "uniform Fr (splitmix64), 2 alternating sets" if args.scalars == "uniform" else "all scalars equal (dummy_r1cs)",
                    "window_bits": plan_c, "srs_precompute": {"window_bits": pre_c, "levels": pre_levels, "hbm_bytes": pre_levels * n * 96},
                    "l2": "256 MB flush between timed iterations",
                    "timing": "CUDA events on the library stream" if world == 1 else "synchronised wall clock incl. NCCL all-gather, max over ranks",
@@ -370,6 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--logn", type=int, default=20, help="log2 of the number of MSM terms per GPU")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--scalars", default="uniform", choices=["uniform", "equal"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the table of 2^(c*w) multiples of the SRS")
     args = ap.parse_args()

@@ -141,15 +141,15 @@ __device__ __forceinline__ void pair_contrib(Fr& a, Fr& b, const Fr& fe, const F
 
 template <bool TW>
 __global__ void __launch_bounds__(SC_THREADS)
-k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr twist, PowTable tab,
+k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr twist, PowTable tab, int kpt,
              Fr* partials, unsigned int* ticket, Fr* out) {
   const size_t npairs = min((nf + 1) / 2, (ng + 1) / 2);
-  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
   Fr a = Fr::zero(), b = Fr::zero();
   Fr t = Fr::one(), step = Fr::one();
   if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }  // (twist^2)^SC_THREADS
 #pragma unroll 1
-  for (int k = 0; k < SC_K; k++) {
+  for (int k = 0; k < kpt; k++) {
     const size_t i = i0 + (size_t)k * SC_THREADS;
     if (i >= npairs) break;
     Fr fe = load_fr_or_zero(f, 2 * i, nf), fo = load_fr_or_zero(f, 2 * i + 1, nf);
@@ -165,16 +165,16 @@ k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size
 template <bool TW>
 __global__ void __launch_bounds__(SC_THREADS)
 k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr rf, Fr rg,
-                  Fr* __restrict__ f_out, Fr* __restrict__ g_out, Fr twist, PowTable tab,
+                  Fr* __restrict__ f_out, Fr* __restrict__ g_out, Fr twist, PowTable tab, int kpt,
                   Fr* partials, unsigned int* ticket, Fr* out) {
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
   const size_t npairs = max((nf2 + 1) / 2, (ng2 + 1) / 2);  // every element must be folded
-  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
   Fr a = Fr::zero(), b = Fr::zero();
   Fr t = Fr::one(), step = Fr::one();
   if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }
 #pragma unroll 1
-  for (int k = 0; k < SC_K; k++) {
+  for (int k = 0; k < kpt; k++) {
     const size_t i = i0 + (size_t)k * SC_THREADS;
     if (i >= npairs) break;
     Fr fe = load_fr_or_zero(f, 4 * i, nf);
@@ -245,14 +245,14 @@ k_fr_powers(Fr* __restrict__ out, size_t n, PowTable tab) {
 // (misc::evaluate_le, src/misc.rs:194-199; tensorcheck evaluates every polynomial at beta and -beta,
 // tensorcheck/mod.rs:228-247).  tab.p[k] = (x^2)^(2^k).
 __global__ void __launch_bounds__(SC_THREADS)
-k_fr_eval_even_odd(const Fr* __restrict__ f, size_t n, Fr x, PowTable tab, Fr* partials, unsigned int* ticket, Fr* out) {
+k_fr_eval_even_odd(const Fr* __restrict__ f, size_t n, Fr x, PowTable tab, int kpt, Fr* partials, unsigned int* ticket, Fr* out) {
   const size_t npairs = (n + 1) / 2;
-  const size_t i0 = (size_t)blockIdx.x * SC_TILE + threadIdx.x;
+  const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
   Fr e = Fr::zero(), o = Fr::zero();
   Fr t = Fr::one(), step = Fr::one();
   if (i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }
 #pragma unroll 1
-  for (int k = 0; k < SC_K; k++) {
+  for (int k = 0; k < kpt; k++) {
     const size_t i = i0 + (size_t)k * SC_THREADS;
     if (i >= npairs) break;
     e = e + load_fr(f + 2 * i) * t;
@@ -396,21 +396,31 @@ static PowTable make_pow_table(const Fr& twist, size_t npairs) {
   return tab;
 }
 
+// pairs per thread: 8 amortises the power-table walk on long vectors; short vectors (the late, latency-bound
+// rounds) use every thread for one pair so that a round costs one short dependency chain
+static inline int sc_pairs_per_thread(size_t npairs) {
+  return npairs > ((size_t)1 << 19) ? 8 : npairs > ((size_t)1 << 17) ? 4 : npairs > ((size_t)1 << 16) ? 2 : 1;
+}
+static inline unsigned sc_grid(size_t npairs, int kpt) {
+  return (unsigned)std::max<size_t>(1, (npairs + (size_t)SC_THREADS * kpt - 1) / ((size_t)SC_THREADS * kpt));
+}
+
 size_t sc_max_ctas(size_t nf, size_t ng) {
   size_t npairs = std::max((nf + 1) / 2, (ng + 1) / 2);
-  return std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+  return std::max<size_t>(1024, (npairs + SC_TILE - 1) / SC_TILE);  // >= the largest grid of any later round
 }
 
 int sc_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
                    Fr* d_partials, unsigned int* d_ticket, Fr* d_out) {
   const size_t npairs = std::min((nf + 1) / 2, (ng + 1) / 2);
-  const unsigned grid = (unsigned)std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+  const int kpt = sc_pairs_per_thread(npairs);
+  const unsigned grid = sc_grid(npairs, kpt);
   if (use_twist) {
     PowTable tab = make_pow_table(twist, npairs);
-    LAUNCH(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, d_partials, d_ticket, d_out);
+    LAUNCH(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
   } else {
     PowTable tab;  // unused
-    LAUNCH(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, d_partials, d_ticket, d_out);
+    LAUNCH(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
   }
   GM_CUDA(cudaGetLastError());
   return GM_OK;
@@ -421,14 +431,15 @@ int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, si
                         unsigned int* d_ticket, Fr* d_out) {
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
   const size_t npairs = std::max((nf2 + 1) / 2, (ng2 + 1) / 2);
-  const unsigned grid = (unsigned)std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
+  const int kpt = sc_pairs_per_thread(npairs);
+  const unsigned grid = sc_grid(npairs, kpt);
   if (use_twist) {
     PowTable tab = make_pow_table(new_twist, npairs);
-    LAUNCH(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab,
+    LAUNCH(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out);
   } else {
     PowTable tab;
-    LAUNCH(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab,
+    LAUNCH(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out);
   }
   GM_CUDA(cudaGetLastError());
@@ -459,8 +470,9 @@ int fr_powers_dev(gm_ctx* ctx, const Fr& x, size_t n, Fr* d_out) {
 int fr_eval_even_odd_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& x, Fr* d_partials, unsigned int* d_ticket, Fr* d_out) {
   const size_t npairs = (n + 1) / 2;
   PowTable tab = make_pow_table_base(x.sqr(), npairs);
-  const unsigned grid = (unsigned)std::max<size_t>(1, (npairs + SC_TILE - 1) / SC_TILE);
-  LAUNCH(ctx, k_fr_eval_even_odd, grid, SC_THREADS, 0, d_f, n, x, tab, d_partials, d_ticket, d_out);
+  const int kpt = sc_pairs_per_thread(npairs);
+  const unsigned grid = sc_grid(npairs, kpt);
+  LAUNCH(ctx, k_fr_eval_even_odd, grid, SC_THREADS, 0, d_f, n, x, tab, kpt, d_partials, d_ticket, d_out);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

@@ -36,7 +36,7 @@ namespace gm {
 
 static constexpr uint32_t SKIP = 0xFFFFFFFFu;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
-static constexpr int SPLIT = 256;          // max point references per work item
+static constexpr int SPLIT = 1024;         // max point references per work item
 static constexpr int ACC_THREADS = 128;
 static constexpr int RED_THREADS = 128;    // CTA size of the XYZZ tree reductions
 
@@ -70,6 +70,23 @@ __device__ __forceinline__ void store_rw(T* p, const T& v) {
   for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = s[k];
 }
 
+// Warp-aggregated atomicAdd: lanes that target the same counter elect a leader which adds the group size
+// once; every lane gets its own slot.  For uniformly random keys this is a no-op in cost terms, for the
+// reference's default all-equal scalars (one hot bucket per window) it removes 31/32 of the contended
+// L2 atomics.  Must be called by all 32 lanes (inactive lanes pass active = false).
+__device__ __forceinline__ uint32_t warp_agg_atomic_inc(uint32_t* counters, size_t key, bool active) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return 0;
+  const unsigned peers = __match_any_sync(mask, (unsigned long long)key);
+  const int leader = __ffs(peers) - 1;
+  const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + rank;
+}
+
 struct Meta {
   uint32_t n_items;
   uint32_t n_split;
@@ -86,9 +103,9 @@ struct Meta {
 __global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, int is_bigint, int c, int W, int merged,
                               uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s;
-  {
+  const bool live = i < n;
+  Fr s = Fr::zero();
+  if (live) {
     const uint4* p = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
     uint4 lo = __ldg(p), hi = __ldg(p + 1);
     s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
@@ -128,9 +145,9 @@ __global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, 
       else if (carry) code = ((1u << c) - coef - 1) | 0x80000000u;  // digit = coef - 2^c < 0
       else code = coef - 1;
     }
-    digits[(size_t)w * n + i] = code;
+    if (live) digits[(size_t)w * n + i] = code;
     // merged: every window shares one bucket set (the bases are pre-multiplied by 2^(c*w))
-    if (code != SKIP) atomicAdd(&counts[(merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu)], 1u);
+    warp_agg_atomic_inc(counts, (merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu), live && code != SKIP);
   }
 }
 
@@ -207,12 +224,11 @@ __global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W
                           uint32_t ref_stride, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = blockIdx.y;
-  if (i >= n) return;
-  const uint32_t code = digits[(size_t)w * n + i];
-  if (code == SKIP) return;
-  const uint32_t pos = atomicAdd(&cursor[(merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu)], 1u);
+  const uint32_t code = i < n ? digits[(size_t)w * n + i] : SKIP;
+  const bool live = code != SKIP;
+  const uint32_t pos = warp_agg_atomic_inc(cursor, (merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu), live);
   // reference into the base table: level w of the precomputed table when merged
-  sorted[pos] = (i + ref_offset + (uint32_t)w * ref_stride) | (code & 0x80000000u);
+  if (live) sorted[pos] = (i + ref_offset + (uint32_t)w * ref_stride) | (code & 0x80000000u);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -723,7 +739,7 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   GM_TRY(S.scan_tmp.reserve(ntiles * 4 + 16));
   // small: Meta | chunk_s | chunk_w | row_sum | wrow_sum | col_sum | part | win_sum
   const size_t off_meta = 0;
-  const size_t off_cs = 4096;
+  const size_t off_cs = 16384;
   const size_t off_cw = off_cs + (size_t)Weff * P.nchunks * sizeof(XYZZ);
   const size_t off_rs = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
   const size_t off_wr = off_rs + (size_t)Weff * H2 * sizeof(XYZZ);
@@ -731,7 +747,7 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   const size_t off_bp = off_col + (size_t)Weff * L2 * sizeof(XYZZ);
   const size_t off_ws = off_bp + (size_t)Weff * nparts * sizeof(XYZZ);
   const size_t small_bytes = off_ws + (size_t)Weff * sizeof(XYZZ);
-  static_assert(sizeof(Meta) <= 4096, "Meta fits its slot");
+  static_assert(sizeof(Meta) <= 16384, "Meta fits its slot");
   GM_TRY(S.small.reserve(small_bytes));
   uint8_t* sm = S.small.as<uint8_t>();
   Meta* meta = reinterpret_cast<Meta*>(sm + off_meta);

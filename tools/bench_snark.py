@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Config 4 of BASELINE.json: `examples/snark --time-prover -i LOGSIZE` (src/examples/snark.rs:69-79) on one B200.
+
+dummy_r1cs(n = 2^logn) (all scalars identical - the reference's default, degenerate workload), SRS resident on
+the device (+ precomputed table, key-setup time), Proof::new_time with a Merlin transcript on the host.
+Prints one JSON line with the prover wall time and the phases the reference instruments with start_timer!."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import gemini_b200 as gm
+    from gemini_b200 import snark
+    from gemini_b200.transcript import MerlinTranscript
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--logn", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-precompute", action="store_true")
+    args = ap.parse_args()
+    n = 1 << args.logn
+    ctx = gm.Context(0)
+    t0 = time.perf_counter()
+    srs = ctx.srs_generate(n, first_multiple=1)
+    if not args.no_precompute:
+        srs.precompute()
+    ctx.synchronize()
+    setup_s = time.perf_counter() - t0
+    ck = gm.CommitterKey(ctx, srs)
+    e = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % gm.field.R
+    r1cs = snark.R1cs.dummy(ctx, n, e)
+    best = None
+    for rep in range(args.reps):
+        timers = {}
+        l0 = ctx.launch_count
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        proof = snark.new_time(ctx, r1cs, ck, MerlinTranscript(), timers)
+        ctx.synchronize()
+        wall = time.perf_counter() - t0
+        if best is None or wall < best[0]:
+            best = (wall, timers, ctx.launch_count - l0)
+    wall, timers, launches = best
+    print(json.dumps({
+        "metric": "snark_time_prover_wall_s", "value": wall, "unit": "s", "logsize": args.logn, "n_gpus": 1,
+        "workload": "examples/snark --time-prover: dummy_r1cs, Merlin transcript on host, all vectors device resident",
+        "phases_s": {k: round(v, 6) for k, v in timers.items()}, "gpu_launches": launches,
+        "srs_setup_s": setup_s, "srs_precompute": srs.precompute_info(),
+        "msm_terms": 3 * n, "proof_commitments": len(proof["tensorcheck_proof"]["folded_polynomials_commitments"]) + 2,
+    }))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
