@@ -260,36 +260,57 @@ int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** 
   return GM_OK;
 }
 
+static void srs_drop_tables(gm_srs* srs) {
+  for (int k = 0; k < srs->npre; k++) {
+    if (srs->pre[k].d_table) cudaFree(srs->pre[k].d_table);
+    srs->pre[k] = gm_srs::PreTable();
+  }
+  srs->npre = 0;
+}
+
 int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len) {
   GM_ARG(ctx && srs, "NULL argument");
   GM_TRY(set_device(ctx));
   if (srs->n == 0) return GM_OK;
-  if (srs->d_table) { cudaFree(srs->d_table); srs->d_table = nullptr; srs->pre_c = srs->pre_W = 0; }
-  const MsmPlan P = msm_plan_merged(expected_msm_len ? expected_msm_len : srs->n, 0);
-  GM_ARG((double)P.W * (double)srs->n < 2147483648.0, "SRS too large for a precomputed table (W * n must stay below 2^31)");
-  void* table = nullptr;
-  cudaError_t e = cudaMalloc(&table, (size_t)P.W * srs->n * sizeof(Affine));
-  if (e != cudaSuccess) {
-    set_error("precompute: cudaMalloc of %zu bytes failed: %s", (size_t)P.W * srs->n * sizeof(Affine), cudaGetErrorString(e));
-    return GM_ERR_OOM;
+  srs_drop_tables(srs);
+  // table 0 covers the whole SRS; tables 1, 2 cover prefixes 8x and 64x shorter (kept while >= 2^12 points)
+  size_t prefix = srs->n;
+  size_t expect = expected_msm_len ? std::min(expected_msm_len, srs->n) : srs->n;
+  for (int k = 0; k < 3; k++) {
+    if (k > 0 && prefix < ((size_t)1 << 12)) break;
+    const MsmPlan P = msm_plan_merged(std::min(expect, prefix), 0);
+    GM_ARG((double)P.W * (double)prefix < 2147483648.0, "SRS too large for a precomputed table (W * n must stay below 2^31)");
+    void* table = nullptr;
+    const size_t bytes = (size_t)P.W * prefix * sizeof(Affine);
+    cudaError_t e = cudaMalloc(&table, bytes);
+    if (e != cudaSuccess) {
+      set_error("precompute: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+      srs_drop_tables(srs);
+      return GM_ERR_OOM;
+    }
+    int rc = msm_precompute(ctx, reinterpret_cast<const Affine*>(srs->d_points), prefix, P.c, P.W, reinterpret_cast<Affine*>(table));
+    e = cudaStreamSynchronize(ctx->stream);
+    if (rc != GM_OK || e != cudaSuccess) {
+      if (rc == GM_OK) { set_error("precompute: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+      cudaFree(table);
+      srs_drop_tables(srs);
+      return rc;
+    }
+    srs->pre[k].d_table = table;
+    srs->pre[k].prefix = prefix;
+    srs->pre[k].c = P.c;
+    srs->pre[k].W = P.W;
+    srs->npre = k + 1;
+    prefix >>= 3;
+    expect = prefix;
   }
-  int rc = msm_precompute(ctx, reinterpret_cast<const Affine*>(srs->d_points), srs->n, P.c, P.W, reinterpret_cast<Affine*>(table));
-  e = cudaStreamSynchronize(ctx->stream);
-  if (rc != GM_OK || e != cudaSuccess) {
-    if (rc == GM_OK) { set_error("precompute: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
-    cudaFree(table);
-    return rc;
-  }
-  srs->d_table = table;
-  srs->pre_c = P.c;
-  srs->pre_W = P.W;
   return GM_OK;
 }
 
 int gm_srs_precompute_info(const gm_srs* srs, int* out_window_bits, int* out_levels) {
   GM_ARG(srs, "NULL argument");
-  if (out_window_bits) *out_window_bits = srs->pre_c;
-  if (out_levels) *out_levels = srs->pre_W;
+  if (out_window_bits) *out_window_bits = srs->npre ? srs->pre[0].c : 0;
+  if (out_levels) *out_levels = srs->npre ? srs->pre[0].W : 0;
   return GM_OK;
 }
 
@@ -312,7 +333,7 @@ int gm_srs_free(gm_srs* srs) {
     cudaStreamSynchronize(srs->ctx->stream);
   }
   if (srs->owned && srs->d_points) cudaFree(srs->d_points);
-  if (srs->d_table) cudaFree(srs->d_table);
+  srs_drop_tables(srs);
   delete srs;
   return GM_OK;
 }
@@ -331,13 +352,20 @@ static void record_phases(gm_ctx* ctx) {
   cudaEventElapsedTime(&ctx->last_ms[3], ctx->ev[4], ctx->ev[5]);
 }
 
-static MsmBases bases_of_srs(const gm_srs* srs) {
+// bases for an MSM over srs[base_offset, base_offset + n): the smallest precomputed table that covers the range
+static MsmBases bases_of_srs(const gm_srs* srs, size_t base_offset, size_t n) {
   MsmBases b;
   b.points = reinterpret_cast<const Affine*>(srs->d_points);
-  b.table = reinterpret_cast<const Affine*>(srs->d_table);
   b.n = srs->n;
-  b.c = srs->pre_c;
-  b.W = srs->pre_W;
+  for (int k = srs->npre - 1; k >= 0; k--) {  // tables are ordered by decreasing prefix
+    if (base_offset + n <= srs->pre[k].prefix) {
+      b.table = reinterpret_cast<const Affine*>(srs->pre[k].d_table);
+      b.n = srs->pre[k].prefix;
+      b.c = srs->pre[k].c;
+      b.W = srs->pre[k].W;
+      break;
+    }
+  }
   return b;
 }
 static MsmBases bases_of_points(const Affine* pts, size_t n) {
@@ -368,7 +396,7 @@ int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void
   GM_TRY(set_device(ctx));
   n = std::min(n, srs->n - base_offset);  // msm_unchecked truncates to the shorter input
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  return msm_common(ctx, bases_of_srs(srs), base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0,
+  return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0,
                     out_jacobian);
 }
 
@@ -381,7 +409,7 @@ int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
   if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return msm_common(ctx, bases_of_srs(srs), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
+  return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
 }
 
 int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t bases_len, const uint64_t* scalars,
@@ -479,7 +507,7 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   } else {
     GM_ARG(s->srs != nullptr, "stream has no SRS and no points were supplied");
     GM_ARG(base_offset <= s->srs->n && m <= s->srs->n - base_offset, "base range outside the SRS");
-    bases = bases_of_srs(s->srs);
+    bases = bases_of_srs(s->srs, base_offset, m);
     boff = base_offset;
   }
   GM_CUDA(cudaEventRecord(s->copied[b], ctx->copy_stream));

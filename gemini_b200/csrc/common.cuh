@@ -104,9 +104,16 @@ struct gm_srs {
   void* d_points = nullptr;  // n * 96 B, Montgomery x|y, (0,0) = identity
   size_t n = 0;
   bool owned = true;
-  // optional precomputed multiples: table[w][i] = 2^(c*w) * P_i, W levels of n points (gm_srs_precompute)
-  void* d_table = nullptr;
-  int pre_c = 0, pre_W = 0;
+  // optional precomputed multiples (gm_srs_precompute): table[w][i] = 2^(c*w) * P_i for i < prefix.  Several
+  // tables over nested prefixes, each with the window size that suits MSMs of about that length: a short
+  // commitment against a long SRS (the fold levels of tensorcheck) must not pay the bucket reduction of c = 22.
+  struct PreTable {
+    void* d_table = nullptr;
+    size_t prefix = 0;
+    int c = 0, W = 0;
+  };
+  PreTable pre[3];
+  int npre = 0;
 };
 
 namespace gm {

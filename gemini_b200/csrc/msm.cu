@@ -36,7 +36,7 @@ namespace gm {
 
 static constexpr uint32_t SKIP = 0xFFFFFFFFu;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
-static constexpr int SPLIT = 1024;         // max point references per work item
+static constexpr int SPLIT = 1024;         // upper bound of the point references per work item (runtime value: Meta::split)
 static constexpr int ACC_THREADS = 128;
 static constexpr int RED_THREADS = 128;    // CTA size of the XYZZ tree reductions
 
@@ -77,6 +77,12 @@ __device__ __forceinline__ void store_rw(T* p, const T& v) {
 __device__ __forceinline__ uint32_t warp_agg_atomic_inc(uint32_t* counters, size_t key, bool active) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned mask = __ballot_sync(0xffffffffu, active);
+  // cheap filter: a hot counter shows up as equal keys in neighbouring lanes; uniformly random keys almost
+  // never do, and then the plain atomic is cheaper than the match
+  const unsigned long long nb_key = __shfl_down_sync(0xffffffffu, (unsigned long long)key, 1);
+  const bool nb_active = __shfl_down_sync(0xffffffffu, active ? 1 : 0, 1) != 0;
+  const bool dup = active && nb_active && lane < 31 && nb_key == (unsigned long long)key;
+  if (!__any_sync(0xffffffffu, dup)) return active ? atomicAdd(counters + key, 1u) : 0u;
   if (!active) return 0;
   const unsigned peers = __match_any_sync(mask, (unsigned long long)key);
   const int leader = __ffs(peers) - 1;
@@ -91,7 +97,7 @@ struct Meta {
   uint32_t n_items;
   uint32_t n_split;
   uint32_t n_partials;
-  uint32_t pad;
+  uint32_t split;  // references per work item for this call (<= SPLIT), set by the host
   uint32_t size_hist[SPLIT + 1];
   uint32_t size_base[SPLIT + 1];
   uint32_t size_fill[SPLIT + 1];
@@ -234,21 +240,21 @@ __global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W
 // -------------------------------------------------------------------------------------------
 // 4. work list, largest items first
 // -------------------------------------------------------------------------------------------
-__global__ void k_classify(const uint32_t* __restrict__ counts, uint32_t M, uint32_t* __restrict__ poff,
+__global__ void k_classify(const uint32_t* __restrict__ counts, uint32_t M, uint32_t split, uint32_t* __restrict__ poff,
                            uint32_t* __restrict__ split_list, Meta* meta) {
   __shared__ uint32_t sh[SPLIT + 1];
-  for (int k = threadIdx.x; k <= SPLIT; k += blockDim.x) sh[k] = 0;
+  for (uint32_t k = threadIdx.x; k <= split; k += blockDim.x) sh[k] = 0;
   __syncthreads();
   const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb < M) {
     const uint32_t cnt = counts[gb];
     uint32_t po = NONE;
     if (cnt) {
-      const uint32_t m = (cnt + SPLIT - 1) / SPLIT;
-      const uint32_t tail = cnt - (m - 1) * SPLIT;
+      const uint32_t m = (cnt + split - 1) / split;
+      const uint32_t tail = cnt - (m - 1) * split;
       atomicAdd(&sh[tail], 1u);
       if (m > 1) {
-        atomicAdd(&sh[SPLIT], m - 1);
+        atomicAdd(&sh[split], m - 1);
         const uint32_t si = atomicAdd(&meta->n_split, 1u);
         po = atomicAdd(&meta->n_partials, m);
         split_list[si] = gb;
@@ -257,43 +263,43 @@ __global__ void k_classify(const uint32_t* __restrict__ counts, uint32_t M, uint
     poff[gb] = po;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k <= SPLIT; k += blockDim.x)
+  for (uint32_t k = threadIdx.x; k <= split; k += blockDim.x)
     if (sh[k]) atomicAdd(&meta->size_hist[k], sh[k]);
 }
 
-__global__ void k_size_scan(Meta* meta) {
+__global__ void k_size_scan(Meta* meta, uint32_t split) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     uint32_t run = 0;
-    for (int s = SPLIT; s >= 1; s--) { meta->size_base[s] = run; run += meta->size_hist[s]; }
+    for (int s = (int)split; s >= 1; s--) { meta->size_base[s] = run; run += meta->size_hist[s]; }
     meta->size_base[0] = run;
     meta->n_items = run;
   }
 }
 
-__global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M, uint2* __restrict__ work, Meta* meta) {
+__global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M, uint32_t split, uint2* __restrict__ work, Meta* meta) {
   __shared__ uint32_t blk_cnt[SPLIT + 1];
   __shared__ uint32_t blk_base[SPLIT + 1];
-  for (int k = threadIdx.x; k <= SPLIT; k += blockDim.x) blk_cnt[k] = 0;
+  for (uint32_t k = threadIdx.x; k <= split; k += blockDim.x) blk_cnt[k] = 0;
   __syncthreads();
   const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t cnt = 0, m = 0, tail = 0, r_tail = 0, r_full = 0;
   if (gb < M) {
     cnt = counts[gb];
     if (cnt) {
-      m = (cnt + SPLIT - 1) / SPLIT;
-      tail = cnt - (m - 1) * SPLIT;
+      m = (cnt + split - 1) / split;
+      tail = cnt - (m - 1) * split;
       r_tail = atomicAdd(&blk_cnt[tail], 1u);
-      if (m > 1) r_full = atomicAdd(&blk_cnt[SPLIT], m - 1);
+      if (m > 1) r_full = atomicAdd(&blk_cnt[split], m - 1);
     }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k <= SPLIT; k += blockDim.x)
+  for (uint32_t k = threadIdx.x; k <= split; k += blockDim.x)
     if (blk_cnt[k]) blk_base[k] = meta->size_base[k] + atomicAdd(&meta->size_fill[k], blk_cnt[k]);
   __syncthreads();
   if (cnt) {
     work[blk_base[tail] + r_tail] = make_uint2(gb, m - 1);
     if (m > 1) {
-      const uint32_t p = blk_base[SPLIT] + r_full;
+      const uint32_t p = blk_base[split] + r_full;
       for (uint32_t k = 0; k + 1 < m; k++) work[p + k] = make_uint2(gb, k);
     }
   }
@@ -305,14 +311,14 @@ __global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M,
 __global__ void __launch_bounds__(ACC_THREADS)
 k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ starts, const uint32_t* __restrict__ poff, const uint2* __restrict__ work,
-             const Meta* __restrict__ meta, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials) {
+             const Meta* __restrict__ meta, uint32_t split, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= meta->n_items) return;
   const uint2 item = work[j];
   const uint32_t gb = item.x, k = item.y;
   const uint32_t cnt = counts[gb];
-  const uint32_t first = starts[gb] + k * SPLIT;
-  const uint32_t len = min((uint32_t)SPLIT, cnt - k * SPLIT);
+  const uint32_t first = starts[gb] + k * split;
+  const uint32_t len = min(split, cnt - k * split);
   XYZZ acc = XYZZ::identity();
   for (uint32_t e = 0; e < len; e++) {
     const uint32_t ref = __ldg(sorted + first + e);
@@ -343,16 +349,43 @@ __device__ __forceinline__ XYZZ block_sum_xyzz(XYZZ v, XYZZ* sh) {
   return r;
 }
 
-// 6. split buckets: bucket = sum of its partials
+// 6. split buckets: bucket = sum of its partials.  Buckets with at most 32 partials are summed by one warp
+//    (shuffle tree, no CTA barrier); larger ones (a bucket that holds a large share of all points) by a CTA.
+__device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
+  XYZZ r;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < 48; k++) dst[k] = __shfl_down_sync(0xffffffffu, src[k], delta);
+  return r;
+}
+
 __global__ void __launch_bounds__(RED_THREADS)
 k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ poff,
-                const Meta* __restrict__ meta, const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets) {
+                const Meta* __restrict__ meta, uint32_t split, const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets) {
   extern __shared__ uint4 sh_raw[];
   XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
   const uint32_t ns = meta->n_split;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t gwarp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  for (uint32_t s = gwarp; s < ns; s += gridDim.x * warps_per_cta) {
+    const uint32_t gb = split_list[s];
+    const uint32_t m = (counts[gb] + split - 1) / split;
+    if (m > 32) continue;
+    XYZZ acc = XYZZ::identity();
+    if (lane < m) acc = load_rw(partials + poff[gb] + lane);
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+      XYZZ other = shfl_down_xyzz(acc, d);
+      if (lane + d < 32) xyzz_add(acc, other);
+    }
+    if (lane == 0) store_rw(buckets + gb, acc);
+  }
   for (uint32_t s = blockIdx.x; s < ns; s += gridDim.x) {
     const uint32_t gb = split_list[s];
-    const uint32_t m = (counts[gb] + SPLIT - 1) / SPLIT;
+    const uint32_t m = (counts[gb] + split - 1) / split;
+    if (m <= 32) continue;
     const XYZZ* src = partials + poff[gb];
     XYZZ acc = XYZZ::identity();
     for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {
@@ -712,7 +745,12 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   const uint32_t ref_offset = merged ? (uint32_t)base_offset : 0u;
   const uint32_t ref_stride = merged ? (uint32_t)B.n : 0u;
   const size_t refs = (size_t)P.W * n;
-  const size_t max_split = refs / SPLIT + 1;
+  // references per work item: enough items to keep every SM busy with several waves, but long enough that the
+  // per-item partial sums of a hot bucket stay few
+  uint32_t split = SPLIT;
+  const size_t avg_load = refs / M + 1;
+  while (split > 32 && split / 2 >= 4 * avg_load && refs / split < (size_t)ctx->sm_count * 384 * 4) split >>= 1;
+  const size_t max_split = refs / split + 1;
   const size_t max_partials = 2 * max_split + 1;
   const size_t max_items = M + max_split + 1;
   // chunk index t = hi * L2 + lo, an H2 x L2 matrix (both powers of two)
@@ -770,16 +808,16 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
   LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), (uint32_t)M);
   LAUNCH(ctx, k_scatter, dim3((n32 + 255) / 256, P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, merged ? 1 : 0, ref_offset, ref_stride, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
-  LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
-  LAUNCH(ctx, k_size_scan, 1, 32, 0, meta);
-  LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, S.work.as<uint2>(), meta);
+  LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, split, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
+  LAUNCH(ctx, k_size_scan, 1, 32, 0, meta, split);
+  LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, split, S.work.as<uint2>(), meta);
   GM_CUDA(cudaEventRecord(ctx->ev[3], st));
   LAUNCH(ctx, k_accumulate, (unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, d_bases, S.sorted.as<uint32_t>(),
-         S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, S.buckets.as<XYZZ>(), S.partials.as<XYZZ>());
+         S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, split, S.buckets.as<XYZZ>(), S.partials.as<XYZZ>());
   GM_CUDA(cudaEventRecord(ctx->ev[4], st));
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
-         S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, S.partials.as<XYZZ>(), S.buckets.as<XYZZ>());
+         S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), S.buckets.as<XYZZ>());
   LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, S.buckets.as<XYZZ>(), S.counts.as<uint32_t>(), P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
   LAUNCH(ctx, k_rowcol, dim3(2 * H2 + L2, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
   LAUNCH(ctx, k_weighted, dim3(nparts, Weff), RED_THREADS, red_sh, row_sum, col_sum, H2, L2, log_l2, ctas_c, part);

@@ -151,10 +151,8 @@ def test_precompute_matches_plain_path(ctx):
     # all-equal scalars: the single hot bucket per window is split into work items
     s = rand_scalars(1, 52)[0]
     assert field.jacobian_to_affine(ctx.msm(srs, [s] * len(bases))) == o.g1_mul(o.naive_msm(bases, [1] * len(bases)), s)
-    # table levels really are 2^(c*w) multiples
-    srs_small = ctx.srs_load(pts[:3]).precompute(expected_msm_len=1 << 20)
-    c2, lv2 = srs_small.precompute_info()
-    assert (c2, lv2) == (20, 13)
+    # the cost model picks c = 20 (13 table levels) for a 2^20-point key
+    assert ctx.srs_generate(1 << 20).precompute().precompute_info() == (20, 13)
 
 
 @pytest.mark.parametrize("logn", [14, 20])
@@ -165,6 +163,10 @@ def test_precompute_closed_form_large(ctx, logn):
     rinv = pow(1 << 256, -1, R)
     tot = sum(v * (i + 1) for i, v in enumerate(limbs_to_ints(limbs))) % R * rinv % R
     assert field.jacobian_to_affine(ctx.msm(srs, limbs)) == o.g1_mul(o.G1_GEN, tot)
+    # short commitments against the long key use the nested short-prefix tables (tensorcheck fold levels)
+    for m in (1, 100, n >> 7, (n >> 3) + 1):
+        tot_m = sum(v * (i + 1) for i, v in enumerate(limbs_to_ints(limbs[:m]))) % R * rinv % R
+        assert field.jacobian_to_affine(ctx.msm(srs, limbs[:m])) == o.g1_mul(o.G1_GEN, tot_m)
     # streamed chunks against the same table (msm_chunks, chunk 2^12) give the same point
     st = gm.msm._DeviceStream(ctx, srs, 1 << 12)
     for s0 in range(0, min(n, 1 << 15), 1 << 12):
