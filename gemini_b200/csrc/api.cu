@@ -85,8 +85,14 @@ int gm_init(int device_id, gm_ctx** out_ctx) {
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) GM_CUDA(cudaEventCreate(&ev));
-  ctx->pinned_bytes = 4096;
+  ctx->pinned_bytes = 65536;  // slot 0 (first 4 KB): call results; 64-byte slots after it: sumcheck round messages
   GM_CUDA(cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault));
+  // short-lived vectors (prover state, DeviceFr temporaries) come from the stream-ordered pool: keep freed
+  // blocks cached instead of returning them to the driver at every synchronisation
+  cudaMemPool_t pool;
+  GM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_id));
+  unsigned long long keep = ~0ull;
+  GM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   *out_ctx = ctx;
   return GM_OK;
 }
@@ -144,14 +150,13 @@ int gm_l2_flush(gm_ctx* ctx) {
 int gm_dev_alloc(gm_ctx* ctx, size_t bytes, void** out_dev) {
   GM_ARG(ctx && out_dev, "NULL argument");
   GM_TRY(set_device(ctx));
-  GM_CUDA(cudaMalloc(out_dev, bytes ? bytes : 16));
+  GM_CUDA(cudaMallocAsync(out_dev, bytes ? bytes : 16, ctx->stream));
   return GM_OK;
 }
 int gm_dev_free(gm_ctx* ctx, void* dev) {
   GM_ARG(ctx, "ctx is NULL");
   GM_TRY(set_device(ctx));
-  GM_CUDA(cudaStreamSynchronize(ctx->stream));
-  GM_CUDA(cudaFree(dev));
+  if (dev) GM_CUDA(cudaFreeAsync(dev, ctx->stream));  // stream ordered: queued work that uses it finishes first
   return GM_OK;
 }
 int gm_dev_upload(gm_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
@@ -637,7 +642,7 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
   p->tot_rounds = flavour == GM_SUMCHECK_GEMINI_TIME ? ceil_log2(std::max(f_len, g_len)) : ceil_log2(std::min(f_len, g_len));
   const size_t ctas = sc_max_ctas(f_len, g_len);
   cudaError_t e = cudaSuccess;
-  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, std::max<size_t>(bytes, 32)); };
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMallocAsync(ptr, std::max<size_t>(bytes, 32), ctx->stream); };
   alloc((void**)&p->f[0], f_len * 32);
   alloc((void**)&p->f[1], ((f_len + 1) / 2) * 32);
   alloc((void**)&p->g[0], g_len * 32);
@@ -646,7 +651,10 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
   alloc((void**)&p->d_ticket, 16);
   alloc((void**)&p->d_out, 64);
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ticket, 0, 16, ctx->stream);
-  if (e == cudaSuccess) e = cudaHostAlloc((void**)&p->h_out, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) {
+    const size_t slots = (ctx->pinned_bytes - 4096) / 64;
+    p->h_out = reinterpret_cast<Fr*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 4096 + 64 * (ctx->next_slot++ % slots));
+  }
   if (e != cudaSuccess) {
     set_error("sumcheck alloc: %s", cudaGetErrorString(e));
     gm_sumcheck_free(p);
@@ -799,15 +807,12 @@ int gm_sumcheck_read_state(gm_sumcheck* p, uint64_t* out_f, size_t* f_len, uint6
 
 int gm_sumcheck_free(gm_sumcheck* p) {
   if (!p) return GM_OK;
-  if (p->ctx) {
-    cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
-  }
-  for (int k = 0; k < 2; k++) { if (p->f[k]) cudaFree(p->f[k]); if (p->g[k]) cudaFree(p->g[k]); }
-  if (p->d_partials) cudaFree(p->d_partials);
-  if (p->d_ticket) cudaFree(p->d_ticket);
-  if (p->d_out) cudaFree(p->d_out);
-  if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->ctx) cudaSetDevice(p->ctx->device);
+  cudaStream_t st = p->ctx ? p->ctx->stream : nullptr;
+  for (int k = 0; k < 2; k++) { if (p->f[k]) cudaFreeAsync(p->f[k], st); if (p->g[k]) cudaFreeAsync(p->g[k], st); }
+  if (p->d_partials) cudaFreeAsync(p->d_partials, st);
+  if (p->d_ticket) cudaFreeAsync(p->d_ticket, st);
+  if (p->d_out) cudaFreeAsync(p->d_out, st);
   delete p;
   return GM_OK;
 }

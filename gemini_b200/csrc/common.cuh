@@ -93,6 +93,7 @@ struct gm_ctx {
   gm::MsmScratch msm;
   void* pinned = nullptr;  // small pinned staging block (results, challenges)
   size_t pinned_bytes = 0;
+  unsigned next_slot = 0;    // round-robin 64-byte pinned slots for sumcheck handles
   void* d_result = nullptr;  // device result slot (accumulator + normalised output)
   void* d_flush = nullptr;   // 256 MB scratch written by gm_l2_flush
   gm::DevBuf fr_red;         // reduction partials + ticket + result of the Fr vector helpers
