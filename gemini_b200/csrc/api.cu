@@ -33,6 +33,11 @@ struct gm_msm_stream {
   size_t chunk_cap = 0;
   XYZZ* d_acc = nullptr;
   DevBuf scal[2], pts_raw[2], pts[2];
+  // device-resident buckets: every chunk only sorts and accumulates into them; the bucket reduction runs once,
+  // at finalize (or when the kind of bases changes)
+  DevBuf buckets, live;
+  MsmPlan plan{};
+  bool plan_set = false, plan_srs = false, dirty = false;
   cudaEvent_t copied[2] = {}, consumed[2] = {};
   bool used[2] = {false, false};
   unsigned turn = 0;
@@ -358,11 +363,11 @@ static void record_phases(gm_ctx* ctx) {
 }
 
 // bases for an MSM over srs[base_offset, base_offset + n): the smallest precomputed table that covers the range
-static MsmBases bases_of_srs(const gm_srs* srs, size_t base_offset, size_t n) {
+static MsmBases bases_of_srs(const gm_srs* srs, size_t base_offset, size_t n, bool full_table_only = false) {
   MsmBases b;
   b.points = reinterpret_cast<const Affine*>(srs->d_points);
   b.n = srs->n;
-  for (int k = srs->npre - 1; k >= 0; k--) {  // tables are ordered by decreasing prefix
+  for (int k = full_table_only ? 0 : srs->npre - 1; k >= 0; k--) {  // tables are ordered by decreasing prefix
     if (base_offset + n <= srs->pre[k].prefix) {
       b.table = reinterpret_cast<const Affine*>(srs->pre[k].d_table);
       b.n = srs->pre[k].prefix;
@@ -467,6 +472,16 @@ int gm_g1_sum(gm_ctx* ctx, const uint64_t* jacobians, size_t k, uint64_t out_jac
 }
 
 // ---- streamed MSM ------------------------------------------------------------------------
+static int stream_flush(gm_msm_stream* s) {
+  if (s->plan_set && s->dirty) {
+    GM_TRY(msm_stream_reduce(s->ctx, s->plan, s->buckets.as<XYZZ>(), s->live.as<uint32_t>(), s->d_acc));
+    GM_CUDA(cudaMemsetAsync(s->live.p, 0, msm_plan_buckets(s->plan) * 4, s->ctx->stream));
+  }
+  s->dirty = false;
+  s->plan_set = false;
+  return GM_OK;
+}
+
 int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, gm_msm_stream** out) {
   GM_ARG(ctx && out, "NULL argument");
   GM_TRY(set_device(ctx));
@@ -504,7 +519,8 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   GM_TRY(s->scal[b].reserve(m * 32));
   GM_CUDA(cudaMemcpyAsync(s->scal[b].p, scalars, m * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
   bool need_pack = false;
-  if (points) {
+  const bool from_srs = points == nullptr;
+  if (!from_srs) {
     GM_TRY(s->pts[b].reserve(m * sizeof(Affine)));
     GM_TRY(upload_points(ctx, points, m, stride_bytes, inf_offset, s->pts_raw[b], s->pts[b].as<Affine>(), ctx->copy_stream));
     need_pack = !(stride_bytes == 96 && inf_offset < 0);
@@ -512,7 +528,7 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   } else {
     GM_ARG(s->srs != nullptr, "stream has no SRS and no points were supplied");
     GM_ARG(base_offset <= s->srs->n && m <= s->srs->n - base_offset, "base range outside the SRS");
-    bases = bases_of_srs(s->srs, base_offset, m);
+    bases = bases_of_srs(s->srs, base_offset, m, /*full_table_only=*/true);
     boff = base_offset;
   }
   GM_CUDA(cudaEventRecord(s->copied[b], ctx->copy_stream));
@@ -521,7 +537,22 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   GM_CUDA(cudaEventSynchronize(s->copied[b]));
   GM_CUDA(cudaStreamWaitEvent(ctx->stream, s->copied[b], 0));
   if (need_pack) GM_TRY(srs_pack(ctx, s->pts_raw[b].as<uint8_t>(), m, stride_bytes, inf_offset, s->pts[b].as<Affine>()));
-  GM_TRY(msm_accumulate(ctx, bases, boff, s->scal[b].as<uint32_t>(), m, scalars_are_bigint != 0, s->d_acc));
+  // one bucket layout per stream; a change of the kind of bases (SRS range <-> ad-hoc points) or a chunk larger
+  // than the plan was made for first folds the current buckets into the accumulator
+  if (s->plan_set && (s->plan_srs != from_srs || m > std::max<size_t>(s->chunk_cap, 1))) GM_TRY(stream_flush(s));
+  if (!s->plan_set) {
+    s->plan = msm_stream_plan(bases, std::max(s->chunk_cap, m));
+    s->chunk_cap = std::max(s->chunk_cap, m);
+    s->plan_srs = from_srs;
+    s->plan_set = true;
+    const size_t M = msm_plan_buckets(s->plan);
+    GM_TRY(s->buckets.reserve(M * sizeof(XYZZ)));
+    GM_TRY(s->live.reserve(M * 4));
+    GM_CUDA(cudaMemsetAsync(s->live.p, 0, M * 4, ctx->stream));
+  }
+  GM_TRY(msm_stream_push(ctx, bases, boff, s->scal[b].as<uint32_t>(), m, scalars_are_bigint != 0, s->plan, s->buckets.as<XYZZ>(),
+                         s->live.as<uint32_t>()));
+  s->dirty = true;
   GM_CUDA(cudaEventRecord(s->consumed[b], ctx->stream));
   s->used[b] = true;
   s->turn++;
@@ -534,6 +565,7 @@ int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]) {
   GM_TRY(set_device(ctx));
   ResultSlot* slot;
   GM_TRY(ensure_result(ctx, &slot));
+  GM_TRY(stream_flush(s));
   GM_TRY(msm_acc_normalize(ctx, s->d_acc, &slot->out));
   GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -551,6 +583,7 @@ int gm_msm_stream_free(gm_msm_stream* s) {
   if (s->d_acc) cudaFree(s->d_acc);
   for (int k = 0; k < 2; k++) {
     s->scal[k].release(); s->pts_raw[k].release(); s->pts[k].release();
+    if (k == 0) { s->buckets.release(); s->live.release(); }
     if (s->copied[k]) cudaEventDestroy(s->copied[k]);
     if (s->consumed[k]) cudaEventDestroy(s->consumed[k]);
   }

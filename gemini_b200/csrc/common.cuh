@@ -70,13 +70,14 @@ struct MsmScratch {
   DevBuf partials;   // XYZZ partial sums of split buckets
   DevBuf work;       // work items
   DevBuf split;      // split-bucket list
-  DevBuf small;      // counters, size histogram, chunk sums, window sums, result
+  DevBuf small;      // chunk sums, row / column sums, window sums
+  DevBuf meta;       // counters and size histogram of the work list
   DevBuf scan_tmp;
   DevBuf bases_tmp;  // ad-hoc bases (hostbases / stream pushes with points)
   void release() {
     scalars.release(); digits.release(); sorted.release(); counts.release(); starts.release();
     cursor.release(); poff.release(); buckets.release(); partials.release(); work.release();
-    split.release(); small.release(); scan_tmp.release(); bases_tmp.release();
+    split.release(); small.release(); meta.release(); scan_tmp.release(); bases_tmp.release();
   }
 };
 

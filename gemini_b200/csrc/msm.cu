@@ -311,7 +311,8 @@ __global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M,
 __global__ void __launch_bounds__(ACC_THREADS)
 k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ starts, const uint32_t* __restrict__ poff, const uint2* __restrict__ work,
-             const Meta* __restrict__ meta, uint32_t split, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials) {
+             const Meta* __restrict__ meta, uint32_t split, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
+             uint32_t* __restrict__ live) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= meta->n_items) return;
   const uint2 item = work[j];
@@ -319,16 +320,18 @@ k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sort
   const uint32_t cnt = counts[gb];
   const uint32_t first = starts[gb] + k * split;
   const uint32_t len = min(split, cnt - k * split);
-  XYZZ acc = XYZZ::identity();
+  const uint32_t po = poff[gb];
+  // streamed MSM: the bucket persists across chunks (live[gb] != 0 once it has been written)
+  XYZZ acc = (live != nullptr && po == NONE && live[gb]) ? load_rw(buckets + gb) : XYZZ::identity();
   for (uint32_t e = 0; e < len; e++) {
     const uint32_t ref = __ldg(sorted + first + e);
     Affine p = load_ro(bases + (ref & 0x7FFFFFFFu));
     if (ref >> 31) p.y = p.y.neg();
     xyzz_madd(acc, p);
   }
-  const uint32_t po = poff[gb];
   XYZZ* dst = (po == NONE) ? (buckets + gb) : (partials + po + k);
   store_rw(dst, acc);
+  if (live != nullptr && po == NONE) live[gb] = 1u;
 }
 
 // CTA-wide sum of one XYZZ per thread (shared-memory tree); result valid in thread 0.
@@ -362,7 +365,8 @@ __device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
 
 __global__ void __launch_bounds__(RED_THREADS)
 k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ poff,
-                const Meta* __restrict__ meta, uint32_t split, const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets) {
+                const Meta* __restrict__ meta, uint32_t split, const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets,
+                uint32_t* __restrict__ live) {
   extern __shared__ uint4 sh_raw[];
   XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
   const uint32_t ns = meta->n_split;
@@ -380,7 +384,13 @@ k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restr
       XYZZ other = shfl_down_xyzz(acc, d);
       if (lane + d < 32) xyzz_add(acc, other);
     }
-    if (lane == 0) store_rw(buckets + gb, acc);
+    if (lane == 0) {
+      if (live != nullptr) {
+        if (live[gb]) { XYZZ prev = load_rw(buckets + gb); xyzz_add(acc, prev); }
+        live[gb] = 1u;
+      }
+      store_rw(buckets + gb, acc);
+    }
   }
   for (uint32_t s = blockIdx.x; s < ns; s += gridDim.x) {
     const uint32_t gb = split_list[s];
@@ -393,7 +403,13 @@ k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restr
       xyzz_add(acc, b);
     }
     XYZZ tot = block_sum_xyzz(acc, sh);
-    if (threadIdx.x == 0) store_rw(buckets + gb, tot);
+    if (threadIdx.x == 0) {
+      if (live != nullptr) {
+        if (live[gb]) { XYZZ prev = load_rw(buckets + gb); xyzz_add(tot, prev); }
+        live[gb] = 1u;
+      }
+      store_rw(buckets + gb, tot);
+    }
   }
 }
 
@@ -734,11 +750,17 @@ MsmPlan msm_plan_merged(size_t n, int c_forced) {
     (ctx)->launches++;                                                     \
   } while (0)
 
-static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
+// Plan of one MSM pass over these bases: merged (one bucket set) when a precomputed table is present.
+static MsmPlan plan_for(const MsmBases& B, size_t n) { return B.table != nullptr ? msm_plan_merged(n, B.c) : msm_plan(n); }
+
+// Phase A: digits, counting sort, work list, bucket accumulation.  Buckets go to `buckets`; when `live` is given the
+// buckets persist across calls (streamed MSM) and are updated in place, otherwise they are (re)written and the
+// per-call counts (ctx->msm.counts) tell which ones are valid.
+static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint,
+                               const MsmPlan& P, XYZZ* buckets, uint32_t* live) {
   if (n == 0) return GM_OK;
   MsmScratch& S = ctx->msm;
-  const bool merged = B.table != nullptr;
-  const MsmPlan P = merged ? msm_plan_merged(n, B.c) : msm_plan(n);
+  const bool merged = P.merged;
   const int Weff = merged ? 1 : P.W;            // bucket sets
   const size_t M = (size_t)Weff * P.nb;
   const Affine* d_bases = merged ? B.table : B.points + base_offset;
@@ -752,16 +774,7 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   while (split > 32 && split / 2 >= 4 * avg_load && refs / split < (size_t)ctx->sm_count * 384 * 4) split >>= 1;
   const size_t max_split = refs / split + 1;
   const size_t max_partials = 2 * max_split + 1;
-  const size_t max_items = M + max_split + 1;
-  // chunk index t = hi * L2 + lo, an H2 x L2 matrix (both powers of two)
-  int log_t = 0;
-  while ((1u << log_t) < P.nchunks) log_t++;
-  const int log_l2 = (log_t + 1) / 2;
-  const uint32_t L2 = 1u << log_l2, H2 = P.nchunks >> log_l2;
-  int log_l = 0;
-  while ((1 << log_l) < P.L) log_l++;
-  const uint32_t ctas_c = (L2 + RED_THREADS - 1) / RED_THREADS, ctas_r = (H2 + RED_THREADS - 1) / RED_THREADS;
-  const uint32_t nparts = ctas_c + ctas_r;
+  const size_t max_items = std::min<size_t>(M, refs) + max_split + 1;
 
   GM_TRY(S.digits.reserve(refs * 4));
   GM_TRY(S.sorted.reserve(refs * 4));
@@ -769,33 +782,14 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   GM_TRY(S.starts.reserve(M * 4));
   GM_TRY(S.cursor.reserve(M * 4));
   GM_TRY(S.poff.reserve(M * 4));
-  GM_TRY(S.buckets.reserve(M * sizeof(XYZZ)));
   GM_TRY(S.partials.reserve(max_partials * sizeof(XYZZ)));
   GM_TRY(S.work.reserve(max_items * sizeof(uint2)));
   GM_TRY(S.split.reserve(max_split * 4));
   const size_t ntiles = (M + SCAN_TILE - 1) / SCAN_TILE;
   GM_TRY(S.scan_tmp.reserve(ntiles * 4 + 16));
-  // small: Meta | chunk_s | chunk_w | row_sum | wrow_sum | col_sum | part | win_sum
-  const size_t off_meta = 0;
-  const size_t off_cs = 16384;
-  const size_t off_cw = off_cs + (size_t)Weff * P.nchunks * sizeof(XYZZ);
-  const size_t off_rs = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
-  const size_t off_wr = off_rs + (size_t)Weff * H2 * sizeof(XYZZ);
-  const size_t off_col = off_wr + (size_t)Weff * H2 * sizeof(XYZZ);
-  const size_t off_bp = off_col + (size_t)Weff * L2 * sizeof(XYZZ);
-  const size_t off_ws = off_bp + (size_t)Weff * nparts * sizeof(XYZZ);
-  const size_t small_bytes = off_ws + (size_t)Weff * sizeof(XYZZ);
   static_assert(sizeof(Meta) <= 16384, "Meta fits its slot");
-  GM_TRY(S.small.reserve(small_bytes));
-  uint8_t* sm = S.small.as<uint8_t>();
-  Meta* meta = reinterpret_cast<Meta*>(sm + off_meta);
-  XYZZ* chunk_s = reinterpret_cast<XYZZ*>(sm + off_cs);
-  XYZZ* chunk_w = reinterpret_cast<XYZZ*>(sm + off_cw);
-  XYZZ* row_sum = reinterpret_cast<XYZZ*>(sm + off_rs);
-  XYZZ* wrow_sum = reinterpret_cast<XYZZ*>(sm + off_wr);
-  XYZZ* col_sum = reinterpret_cast<XYZZ*>(sm + off_col);
-  XYZZ* part = reinterpret_cast<XYZZ*>(sm + off_bp);
-  XYZZ* win_sum = reinterpret_cast<XYZZ*>(sm + off_ws);
+  GM_TRY(S.meta.reserve(16384));
+  Meta* meta = S.meta.as<Meta>();
 
   cudaStream_t st = ctx->stream;
   GM_CUDA(cudaMemsetAsync(S.counts.p, 0, M * 4, st));
@@ -813,17 +807,55 @@ static int msm_chunk(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const u
   LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, split, S.work.as<uint2>(), meta);
   GM_CUDA(cudaEventRecord(ctx->ev[3], st));
   LAUNCH(ctx, k_accumulate, (unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, d_bases, S.sorted.as<uint32_t>(),
-         S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, split, S.buckets.as<XYZZ>(), S.partials.as<XYZZ>());
+         S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, split, buckets, S.partials.as<XYZZ>(), live);
   GM_CUDA(cudaEventRecord(ctx->ev[4], st));
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
-         S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), S.buckets.as<XYZZ>());
-  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, S.buckets.as<XYZZ>(), S.counts.as<uint32_t>(), P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
+         S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), buckets, live);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+// Phase B: bucket reduction (running sums, weights, windows) and *d_acc += result.  `valid[gb] != 0` marks the
+// buckets that hold a point (per-call counts, or the persistent live flags of a stream).
+static int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_t* valid, XYZZ* d_acc) {
+  MsmScratch& S = ctx->msm;
+  const bool merged = P.merged;
+  const int Weff = merged ? 1 : P.W;
+  // chunk index t = hi * L2 + lo, an H2 x L2 matrix (both powers of two)
+  int log_t = 0;
+  while ((1u << log_t) < P.nchunks) log_t++;
+  const int log_l2 = (log_t + 1) / 2;
+  const uint32_t L2 = 1u << log_l2, H2 = P.nchunks >> log_l2;
+  int log_l = 0;
+  while ((1 << log_l) < P.L) log_l++;
+  const uint32_t ctas_c = (L2 + RED_THREADS - 1) / RED_THREADS, ctas_r = (H2 + RED_THREADS - 1) / RED_THREADS;
+  const uint32_t nparts = ctas_c + ctas_r;
+  // small: chunk_s | chunk_w | row_sum | wrow_sum | col_sum | part | win_sum
+  const size_t off_cs = 0;
+  const size_t off_cw = off_cs + (size_t)Weff * P.nchunks * sizeof(XYZZ);
+  const size_t off_rs = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
+  const size_t off_wr = off_rs + (size_t)Weff * H2 * sizeof(XYZZ);
+  const size_t off_col = off_wr + (size_t)Weff * H2 * sizeof(XYZZ);
+  const size_t off_bp = off_col + (size_t)Weff * L2 * sizeof(XYZZ);
+  const size_t off_ws = off_bp + (size_t)Weff * nparts * sizeof(XYZZ);
+  const size_t small_bytes = off_ws + (size_t)Weff * sizeof(XYZZ);
+  GM_TRY(S.small.reserve(small_bytes));
+  uint8_t* sm = S.small.as<uint8_t>();
+  XYZZ* chunk_s = reinterpret_cast<XYZZ*>(sm + off_cs);
+  XYZZ* chunk_w = reinterpret_cast<XYZZ*>(sm + off_cw);
+  XYZZ* row_sum = reinterpret_cast<XYZZ*>(sm + off_rs);
+  XYZZ* wrow_sum = reinterpret_cast<XYZZ*>(sm + off_wr);
+  XYZZ* col_sum = reinterpret_cast<XYZZ*>(sm + off_col);
+  XYZZ* part = reinterpret_cast<XYZZ*>(sm + off_bp);
+  XYZZ* win_sum = reinterpret_cast<XYZZ*>(sm + off_ws);
+  const size_t red_sh = RED_THREADS * sizeof(XYZZ);
+  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, buckets, valid, P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
   LAUNCH(ctx, k_rowcol, dim3(2 * H2 + L2, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
   LAUNCH(ctx, k_weighted, dim3(nparts, Weff), RED_THREADS, red_sh, row_sum, col_sum, H2, L2, log_l2, ctas_c, part);
   LAUNCH(ctx, k_window_total, Weff, 2 * RED_THREADS, 2 * red_sh, part, nparts, wrow_sum, H2, log_l, P.c, merged ? 1 : 0, win_sum);
   LAUNCH(ctx, k_final, 1, 32, 0, win_sum, Weff, d_acc);
-  GM_CUDA(cudaEventRecord(ctx->ev[5], st));
+  GM_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
@@ -833,9 +865,32 @@ int msm_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uin
   const size_t max_pass = (size_t)1 << 27;
   for (size_t off = 0; off < n; off += max_pass) {
     const size_t m = std::min(max_pass, n - off);
-    GM_TRY(msm_chunk(ctx, B, base_offset + off, d_scalars + off * 8, m, bigint, d_acc));
+    const MsmPlan P = plan_for(B, m);
+    const size_t M = (size_t)(P.merged ? 1 : P.W) * P.nb;
+    GM_TRY(ctx->msm.buckets.reserve(M * sizeof(XYZZ)));
+    GM_TRY(msm_sort_accumulate(ctx, B, base_offset + off, d_scalars + off * 8, m, bigint, P, ctx->msm.buckets.as<XYZZ>(), nullptr));
+    GM_TRY(msm_reduce(ctx, P, ctx->msm.buckets.as<XYZZ>(), ctx->msm.counts.as<uint32_t>(), d_acc));
   }
   return GM_OK;
+}
+
+// ---- streamed MSM with device-resident buckets: chunks only sort + accumulate, the reduction runs once ----
+MsmPlan msm_stream_plan(const MsmBases& B, size_t chunk_cap) { return plan_for(B, std::max<size_t>(chunk_cap, 1)); }
+
+size_t msm_plan_buckets(const MsmPlan& P) { return (size_t)(P.merged ? 1 : P.W) * P.nb; }
+
+int msm_stream_push(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint,
+                    const MsmPlan& P, XYZZ* d_buckets, uint32_t* d_live) {
+  const size_t max_pass = (size_t)1 << 27;
+  for (size_t off = 0; off < n; off += max_pass) {
+    const size_t m = std::min(max_pass, n - off);
+    GM_TRY(msm_sort_accumulate(ctx, B, base_offset + off, d_scalars + off * 8, m, bigint, P, d_buckets, d_live));
+  }
+  return GM_OK;
+}
+
+int msm_stream_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* d_buckets, const uint32_t* d_live, XYZZ* d_acc) {
+  return msm_reduce(ctx, P, d_buckets, d_live, d_acc);
 }
 
 int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, Affine* d_table) {

@@ -26,6 +26,13 @@ struct MsmBases {
 
 // *d_acc (XYZZ, device) += sum_i scalars[i] * bases[i]; asynchronous on ctx->stream
 int msm_accumulate(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc);
+// streamed MSM: buckets (msm_plan_buckets(P) XYZZ) and live flags (same count of u32, zero-initialised) persist
+// across pushes; every push must use the same plan and the same kind of bases
+MsmPlan msm_stream_plan(const MsmBases& bases, size_t chunk_cap);
+size_t msm_plan_buckets(const MsmPlan& P);
+int msm_stream_push(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint,
+                    const MsmPlan& P, XYZZ* d_buckets, uint32_t* d_live);
+int msm_stream_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* d_buckets, const uint32_t* d_live, XYZZ* d_acc);
 int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, Affine* d_table);
 int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);
