@@ -308,7 +308,7 @@ __global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M,
 // -------------------------------------------------------------------------------------------
 // 5. bucket accumulation: one thread per work item
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ACC_THREADS)
+__global__ void __launch_bounds__(ACC_THREADS, 3)  // 3 CTAs/SM: at most 168 registers per thread
 k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ starts, const uint32_t* __restrict__ poff, const uint2* __restrict__ work,
              const Meta* __restrict__ meta, uint32_t split, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
