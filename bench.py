@@ -360,6 +360,21 @@ def run_own(args):
                                 "sample": f"first 2^{m.bit_length() - 1} terms of the same workload, one MSM, arkworks window c={c_used}, "
                                           f"one thread per window; CPU and GPU results equal: {cpu_pt == gpu_out}"}
         assert cpu_pt == gpu_out, "GPU result differs from the CPU restatement"
+    if world == 1 and args.extras:
+        # the other BASELINE configs on the same box, as extra keys (never allowed to break the headline line)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_snark
+            import bench_sumcheck
+
+            srs.free()
+            for p in d_scal:
+                ctx.dev_free(p)
+            rows = []
+            bench_sumcheck.run(ctx, 24, 3, rows.append)
+            line["extra"] = {"sumcheck_2^24": rows, "snark_time_prover": bench_snark.run(ctx, args.extras_logn, 2)}
+        except Exception as exc:  # pragma: no cover
+            line["extra"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -374,6 +389,8 @@ def main():
     ap.add_argument("--logn", type=int, default=20, help="log2 of the number of MSM terms per GPU")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--scalars", default="uniform", choices=["uniform", "equal"])
+    ap.add_argument("--extras", action="store_true", help="also time config 3 (sumcheck 2^24) and config 4 (snark time prover) into an `extra` key")
+    ap.add_argument("--extras-logn", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the table of 2^(c*w) multiples of the SRS")
     args = ap.parse_args()

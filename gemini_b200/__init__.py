@@ -14,9 +14,12 @@ from .msm import VariableBaseMSM, ChunkedPippenger, HashMapPippenger, msm_chunks
 from .kzg import CommitterKey, CommitterKeyStream  # noqa: F401
 from .sumcheck import TimeProver, HerringTimeProver, SpaceProver, ElasticProver, Sumcheck, fold_polynomial  # noqa: F401
 from .tensorcheck import foldings_polynomial  # noqa: F401
+from .devvec import DeviceFr, DeviceCsr  # noqa: F401
+from .transcript import MerlinTranscript  # noqa: F401
+from . import snark  # noqa: F401
 
 __all__ = [
     "Context", "Srs", "GeminiError", "VariableBaseMSM", "ChunkedPippenger", "HashMapPippenger", "msm_chunks",
     "CommitterKey", "CommitterKeyStream", "TimeProver", "HerringTimeProver", "SpaceProver", "ElasticProver",
-    "Sumcheck", "fold_polynomial", "foldings_polynomial", "field",
+    "Sumcheck", "fold_polynomial", "foldings_polynomial", "field", "DeviceFr", "DeviceCsr", "MerlinTranscript", "snark",
 ]

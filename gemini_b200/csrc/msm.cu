@@ -36,7 +36,7 @@ namespace gm {
 
 static constexpr uint32_t SKIP = 0xFFFFFFFFu;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
-static constexpr int SPLIT = 1024;         // upper bound of the point references per work item (runtime value: Meta::split)
+static constexpr int SPLIT = 1024;         // upper bound of the point references per work item (the runtime value is a kernel argument)
 static constexpr int ACC_THREADS = 128;
 static constexpr int RED_THREADS = 128;    // CTA size of the XYZZ tree reductions
 
@@ -97,7 +97,7 @@ struct Meta {
   uint32_t n_items;
   uint32_t n_split;
   uint32_t n_partials;
-  uint32_t split;  // references per work item for this call (<= SPLIT), set by the host
+  uint32_t pad;
   uint32_t size_hist[SPLIT + 1];
   uint32_t size_base[SPLIT + 1];
   uint32_t size_fill[SPLIT + 1];

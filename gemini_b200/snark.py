@@ -137,7 +137,7 @@ def new_time(ctx: Context, r1cs: R1cs, ck: CommitterKey, transcript, timers: Opt
     transcript.append_serializable(b"zc(alpha)", zc_alpha)
 
     t0 = time.perf_counter()
-    first = _prove_sumcheck(transcript, TimeProver(ctx, _as_tensor(z_a), _as_tensor(z_b), alpha))
+    first = _prove_sumcheck(transcript, TimeProver(ctx, z_a, z_b, alpha))
     lap("First sumcheck", t0)
 
     t0 = time.perf_counter()
@@ -152,7 +152,7 @@ def new_time(ctx: Context, r1cs: R1cs, ck: CommitterKey, transcript, timers: Opt
     lap("abc_tensored", t0)
 
     t0 = time.perf_counter()
-    second = _prove_sumcheck(transcript, TimeProver(ctx, _as_tensor(abc), _as_tensor(r1cs.z), 1))
+    second = _prove_sumcheck(transcript, TimeProver(ctx, abc, r1cs.z, 1))
     lap("Second sumcheck", t0)
 
     t0 = time.perf_counter()
@@ -162,27 +162,3 @@ def new_time(ctx: Context, r1cs: R1cs, ck: CommitterKey, transcript, timers: Opt
             "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
             "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),
             "tensorcheck_proof": tc}
-
-
-class _DevView:
-    """Adapter so that TimeProver's constructor takes a DeviceFr through its device-pointer path."""
-
-    def __init__(self, v: DeviceFr):
-        self.v = v
-        self.is_cuda = True
-
-    def data_ptr(self) -> int:
-        return self.v.ptr
-
-    def is_contiguous(self) -> bool:
-        return True
-
-    def numel(self) -> int:
-        return self.v.n * 4
-
-    def element_size(self) -> int:
-        return 8
-
-
-def _as_tensor(v: DeviceFr) -> _DevView:
-    return _DevView(v)

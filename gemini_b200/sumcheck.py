@@ -36,7 +36,11 @@ def fold_polynomial(ctx: Context, f, r: int) -> List[int]:
 class _DeviceProver:
     def __init__(self, ctx: Context, f, g, twist: int, flavour: int):
         self.ctx = ctx
-        if hasattr(f, "data_ptr") and f.is_cuda:
+        if hasattr(f, "ptr") and hasattr(f, "n"):  # gemini_b200.devvec.DeviceFr: device-resident inputs
+            tw = field.fr_to_limbs([twist])
+            h = C.c_void_p()
+            check(lib.gm_sumcheck_new_dev(ctx._h, C.c_void_p(f.ptr), f.n, C.c_void_p(g.ptr), g.n, _ptr(tw), flavour, C.byref(h)))
+        elif hasattr(f, "data_ptr") and f.is_cuda:
             nf = f.numel() * f.element_size() // 32
             ng = g.numel() * g.element_size() // 32
             tw = field.fr_to_limbs([twist])

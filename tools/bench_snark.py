@@ -14,18 +14,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run(ctx, logn, reps, no_precompute=False):
     import gemini_b200 as gm
     from gemini_b200 import snark
     from gemini_b200.transcript import MerlinTranscript
 
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--logn", type=int, default=24)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--no-precompute", action="store_true")
-    args = ap.parse_args()
+    class _A:
+        pass
+
+    args = _A()
+    args.logn, args.reps, args.no_precompute = logn, reps, no_precompute
     n = 1 << args.logn
-    ctx = gm.Context(0)
     t0 = time.perf_counter()
     srs = ctx.srs_generate(n, first_multiple=1)
     if not args.no_precompute:
@@ -47,13 +46,28 @@ def main():
         if best is None or wall < best[0]:
             best = (wall, timers, ctx.launch_count - l0)
     wall, timers, launches = best
-    print(json.dumps({
+    srs_info = srs.precompute_info()
+    res = ({
         "metric": "snark_time_prover_wall_s", "value": wall, "unit": "s", "logsize": args.logn, "n_gpus": 1,
         "workload": "examples/snark --time-prover: dummy_r1cs, Merlin transcript on host, all vectors device resident",
         "phases_s": {k: round(v, 6) for k, v in timers.items()}, "gpu_launches": launches,
-        "srs_setup_s": setup_s, "srs_precompute": srs.precompute_info(),
+        "srs_setup_s": setup_s, "srs_precompute": srs_info,
         "msm_terms": 3 * n, "proof_commitments": len(proof["tensorcheck_proof"]["folded_polynomials_commitments"]) + 2,
-    }))
+    })
+    srs.free()
+    return res
+
+
+def main():
+    import gemini_b200 as gm
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--logn", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-precompute", action="store_true")
+    args = ap.parse_args()
+    ctx = gm.Context(0)
+    print(json.dumps(run(ctx, args.logn, args.reps, args.no_precompute)))
     ctx.close()
 
 

@@ -15,21 +15,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    import numpy as np
-
-    import gemini_b200 as gm
-    from gemini_b200 import field
-    from gemini_b200._lib import check, lib
+def run(ctx, logn, reps, emit):
+    """emit(dict) is called once per measured line"""
     import ctypes as C
 
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--logn", type=int, default=24)
-    ap.add_argument("--reps", type=int, default=5)
-    args = ap.parse_args()
+    import numpy as np
+
+    from gemini_b200 import field
+    from gemini_b200._lib import check, lib
+
+    class _A:
+        pass
+
+    args = _A()
+    args.logn, args.reps = logn, reps
     n = 1 << args.logn
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    ctx = gm.Context(0)
     d_f, d_g, d_o = ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 16)
     ctx.fr_random_dev(d_f, n, 1)
     ctx.fr_random_dev(d_g, n, 2)
@@ -41,7 +42,7 @@ def main():
         check(lib.gm_fr_fold_dev(ctx._h, C.c_void_p(d_f), n, C.c_void_p(r.ctypes.data), C.c_void_p(d_o)))
         times.append(ctx.last_device_ms(0))
     ms = min(times[2:])
-    print(json.dumps({"kernel": "k_fr_fold", "n": n, "ms": ms, "GBps": n * 48 / ms / 1e6, "frac_of_hbm_peak": n * 48 / ms / 1e6 / peak}))
+    emit(({"kernel": "k_fr_fold", "n": n, "ms": ms, "GBps": n * 48 / ms / 1e6, "frac_of_hbm_peak": n * 48 / ms / 1e6 / peak}))
     # (b) full sumcheck, device-resident inputs
     import random
     rng = random.Random(7)
@@ -73,9 +74,22 @@ def main():
             if best is None or ms < best[0]:
                 best = (ms, wall, k, ctx.launch_count - l0)
         ms, wall, rounds, launches = best
-        print(json.dumps({"prover": name, "n": n, "rounds": rounds, "device_ms": ms, "wall_ms": wall, "launches": launches,
+        emit(({"prover": name, "n": n, "rounds": rounds, "device_ms": ms, "wall_ms": wall, "launches": launches,
                           "GBps_at_256n": 256 * n / ms / 1e6, "frac_of_hbm_peak": 256 * n / ms / 1e6 / peak,
                           "elements_per_s": 2 * n / (ms / 1e3)}))
+    for p in (d_f, d_g, d_o):
+        ctx.dev_free(p)
+
+
+def main():
+    import gemini_b200 as gm
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--logn", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    ctx = gm.Context(0)
+    run(ctx, args.logn, args.reps, lambda d: print(json.dumps(d)))
     ctx.close()
 
 
