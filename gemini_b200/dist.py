@@ -8,7 +8,7 @@ identically on every rank (``combine`` = Context.g1_sum on the device).
 """
 from __future__ import annotations
 
-from typing import Callable, Tuple
+from typing import Callable, Sequence, Tuple
 
 import numpy as np
 
@@ -43,3 +43,121 @@ def sharded_msm(ctx, srs_shard, scalars_shard, group=None, device=None) -> np.nd
     """Each rank: local MSM over its shard (device), then the exchange."""
     partial = ctx.msm(srs_shard, scalars_shard)
     return allreduce_g1(partial, ctx.g1_sum, group=group, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sumcheck / fold across ranks (SURVEY.md 8e, "Sumcheck / fold (Time prover)")
+# ---------------------------------------------------------------------------------------------------
+def _ark_log2(x: int) -> int:
+    return 0 if x <= 1 else (x - 1).bit_length()
+
+
+def sumcheck_block(n_f: int, n_g: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """Block layout of the sharded TimeProver: the index space is padded to 2^L, L = ceil(log2(max(|f|,|g|)))
+    (sumcheck/time_prover.rs:35-38), and cut into ``world`` contiguous blocks of B = 2^L / world indices.
+    Returns (start, B, L); rank r owns indices [start, start + B) of f and of g (clipped to their lengths,
+    the remainder reads as zero - exactly the reference's zip-to-shorter / `unwrap_or(zero)` behaviour)."""
+    if world & (world - 1):
+        raise ValueError("world size must be a power of two")
+    L = _ark_log2(max(n_f, n_g))
+    if (1 << L) < world:
+        raise ValueError("vectors shorter than the world size: run the replicated prover")
+    B = (1 << L) // world
+    return rank * B, B, L
+
+
+def _gather_rows(row: np.ndarray, group, device) -> np.ndarray:
+    """all-gather one small uint64 row per rank -> (world, len) uint64 (same on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint64).view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return torch.stack(out).cpu().numpy().view(np.uint64)
+
+
+class ShardedTimeProver:
+    """trait Prover (sumcheck/prover.rs:30-45) with f and g split across ranks; messages, challenges and final
+    foldings are those of the single-process TimeProver (sumcheck/time_prover.rs:42-137) on the whole vectors.
+
+    Every rank holds one zero-padded block of B = 2^L / world consecutive coefficients and runs an ordinary
+    local prover on it (``make_local(f_block, g_block, twist)``: the device TimeProver in production, the
+    oracle in the CPU tests).  Folding is purely local.  The pair i of the local block is the pair
+    i + rank * B_k / 2 of the whole vector in round k (B_k = B / 2^k), and the twist of round k is
+    twist^(2^k), so the local sums miss the factor (twist^(2^k))^(rank * B_k) = twist^(rank * B) - the same
+    in every round.  The only exchange per round is an all-gather of the 64-byte local message; every rank
+    then forms  sum_r twist^(r B) (a_r, b_r).  After log2(B) rounds one coefficient is left per rank: these
+    are gathered (2 x 32 B per rank) and the last log2(world) rounds run replicated on every rank.
+    """
+
+    def __init__(self, make_local: Callable, f_block: Sequence, g_block: Sequence, twist: int, n_f: int, n_g: int,
+                 group=None, device=None, modulus: int = None):
+        import torch.distributed as dist
+
+        from . import field
+
+        self._field = field
+        self.R = modulus or field.R
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.start, self.B, self.L = sumcheck_block(n_f, n_g, self.rank, self.world)
+        if len(f_block) > self.B or len(g_block) > self.B:
+            raise ValueError("block longer than 2^L / world")
+        self.make_local = make_local
+        self.twist0 = twist % self.R
+        self._round = 0
+        self.local_rounds = _ark_log2(self.B)
+        self.scales = [pow(self.twist0, r * self.B, self.R) for r in range(self.world)]
+        f_block = list(f_block) + [0] * (self.B - len(f_block))
+        g_block = list(g_block) + [0] * (self.B - len(g_block))
+        self.local = make_local(f_block, g_block, self.twist0)
+        self.tail = None
+        if self.local_rounds == 0:
+            self._start_tail()
+
+    # -- the two exchanges ------------------------------------------------------------------------
+    def _combine(self, msg: Tuple[int, int]) -> Tuple[int, int]:
+        rows = _gather_rows(self._field.fr_to_limbs(list(msg), montgomery=False).reshape(-1), self.group, self.device)
+        a = b = 0
+        for r in range(self.world):
+            ar, br = self._field.fr_from_limbs(rows[r].reshape(2, 4), montgomery=False)
+            a = (a + self.scales[r] * ar) % self.R
+            b = (b + self.scales[r] * br) % self.R
+        return a, b
+
+    def _start_tail(self) -> None:
+        f, g, tw = self.local.state()
+        assert len(f) == 1 and len(g) == 1
+        rows = _gather_rows(self._field.fr_to_limbs([f[0], g[0]], montgomery=False).reshape(-1), self.group, self.device)
+        vals = [self._field.fr_from_limbs(rows[r].reshape(2, 4), montgomery=False) for r in range(self.world)]
+        self.tail = self.make_local([v[0] for v in vals], [v[1] for v in vals], tw)
+
+    # -- trait Prover -----------------------------------------------------------------------------
+    def next_message(self, verifier_message):
+        assert self._round <= self.L, "More rounds than needed."
+        if self.tail is not None:
+            msg = self.tail.next_message(verifier_message)
+        elif self._round == self.local_rounds:          # the fold that leaves one coefficient per rank
+            self.local.fold(verifier_message)
+            self._start_tail()
+            msg = self.tail.next_message(None)
+        else:
+            msg = self._combine(self.local.next_message(verifier_message))
+        if msg is not None:
+            self._round += 1
+        return msg
+
+    def fold(self, r: int) -> None:
+        (self.tail or self.local).fold(r)
+
+    def rounds(self) -> int:
+        return self.L
+
+    def round(self) -> int:
+        return self._round
+
+    def final_foldings(self):
+        return self.tail.final_foldings() if self.tail is not None else None

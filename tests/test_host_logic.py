@@ -102,3 +102,69 @@ def test_allreduce_g1_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+class _OracleLocal:
+    """Stand-in for the device TimeProver in the CPU tests: the oracle plus the ``state()`` accessor."""
+
+    def __init__(self, f, g, twist):
+        self.p = o.TimeProver(f, g, twist)
+
+    def next_message(self, vm):
+        return self.p.next_message(vm)
+
+    def fold(self, r):
+        self.p.fold(r)
+
+    def state(self):
+        return self.p.f, self.p.g, self.p.twist
+
+    def final_foldings(self):
+        return self.p.final_foldings()
+
+
+def _gloo_sumcheck_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for nf, ng, twist in ((64, 64, 1), (37, 64, 12345), (50, 9, R - 2), (2, 2, 7), (5, 3, 3)):
+            f, g = rand_scalars(nf, 10 + nf), rand_scalars(ng, 20 + ng)
+            chal = rand_scalars(16, 30)
+            it1, it2 = iter(chal), iter(chal)
+            want = o.sumcheck_prove(o.TimeProver(f, g, twist), lambda m: next(it1))
+            start, B, L = gdist.sumcheck_block(nf, ng, rank, world)
+            sp = gdist.ShardedTimeProver(_OracleLocal, f[start:start + B], g[start:start + B], twist, nf, ng)
+            got = o.sumcheck_prove(sp, lambda m: next(it2))
+            ok = ok and got[0] == want[0] and got[1] == want[1] and got[2] == want[2] and sp.rounds() == L
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_time_prover_gloo_world2():
+    """f, g split into contiguous blocks, local folds, one 64-byte all-gather per round; the messages
+    and final foldings must equal the single-process TimeProver's (sumcheck/time_prover.rs:83-137)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + random.randrange(2000)
+    procs = [ctx.Process(target=_gloo_sumcheck_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_sumcheck_block_layout():
+    assert gdist.sumcheck_block(1 << 24, 1 << 24, 3, 8) == (3 << 21, 1 << 21, 24)
+    assert gdist.sumcheck_block(17, 5, 1, 2) == (16, 16, 5)
+    with pytest.raises(ValueError):
+        gdist.sumcheck_block(8, 8, 0, 3)
+    with pytest.raises(ValueError):
+        gdist.sumcheck_block(2, 2, 0, 4)
