@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "g1.cuh"
+#include "g1_affine.cuh"
 #include "msm.cuh"
 
 namespace gm {
@@ -238,6 +239,144 @@ __global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W
 }
 
 // -------------------------------------------------------------------------------------------
+// 3b. affine pre-reduction: the references of every bucket are summed pairwise, level by level, in AFFINE
+//     coordinates with shared inversions (g1_affine.cuh): 6 Fq products per addition instead of the 10 of the
+//     XYZZ mixed addition of k_accumulate.  One level = three launches:
+//       k_aff_prepare  classify each pair, denominators, per-thread exclusive prefix products (to HBM),
+//                      per-warp butterfly giving every lane the product of the OTHER lanes' totals
+//       k_aff_invert   one Kaliski inversion per warp total
+//       k_aff_finish   back-substitution through the prefix products, chord / tangent formulas, 96 B out
+//     Output slot s of bucket gb holds in[2j] + in[2j+1] (j = s - out_starts[gb]); an odd leftover passes
+//     through.  A warp owns 32*G consecutive slots, lane l the slots base + k*32 + l (coalesced).
+//     After R levels the surviving points (ceil(cnt / 2^R) per bucket) go through the XYZZ work-list path.
+// -------------------------------------------------------------------------------------------
+static constexpr int AFF_THREADS = 128;
+
+__global__ void k_aff_counts(const uint32_t* __restrict__ in_counts, uint32_t M, uint32_t* __restrict__ out_counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) out_counts[i] = (in_counts[i] + 1u) >> 1;
+}
+
+// largest b in [lo, hi] with starts[b] <= s (starts = exclusive scan of the counts; starts[lo] <= s)
+__device__ __forceinline__ uint32_t bucket_of_slot(const uint32_t* __restrict__ starts, uint32_t lo, uint32_t hi, uint32_t s) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+    if (__ldg(starts + mid) <= s) lo = mid; else hi = mid - 1u;
+  }
+  return lo;
+}
+
+template <bool FIRST>
+__device__ __forceinline__ Affine aff_load_input(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e) {
+  if (FIRST) {
+    const uint32_t ref = __ldg(refs + e);
+    Affine p = load_ro(in + (ref & 0x7FFFFFFFu));
+    if (ref >> 31) p.y = p.y.neg();   // -(0,0) = (0,0): the identity stays the identity
+    return p;
+  }
+  return load_ro(in + e);
+}
+
+__device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, int m) {
+  Fq r;
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = __shfl_xor_sync(0xffffffffu, v.v[k], m);
+  return r;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(AFF_THREADS)
+k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ in_counts,
+              const uint32_t* __restrict__ in_starts, const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts,
+              uint32_t M, int G, Fq* __restrict__ prefix, uint2* __restrict__ slot_meta, Fq* __restrict__ others,
+              Fq* __restrict__ warp_totals) {
+  const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
+  if (base64 >= n_slots) return;                      // whole warp out of range
+  const uint32_t base = (uint32_t)base64;
+  const uint32_t last = (uint32_t)min((uint64_t)n_slots - 1u, base64 + 32u * (uint32_t)G - 1u);
+  const uint32_t b_lo = bucket_of_slot(out_starts, 0, M - 1, base);
+  const uint32_t b_hi = bucket_of_slot(out_starts, b_lo, M - 1, last);
+  Fq run = Fq::one();
+#pragma unroll 1
+  for (int k = 0; k < G; k++) {
+    const uint32_t s = base + (uint32_t)k * 32u + lane;
+    if (s >= n_slots) break;
+    const uint32_t gb = bucket_of_slot(out_starts, b_lo, b_hi, s);
+    const uint32_t j = s - __ldg(out_starts + gb);
+    const uint32_t e0 = __ldg(in_starts + gb) + 2u * j;
+    const bool has2 = 2u * j + 1u < __ldg(in_counts + gb);
+    const Affine p1 = aff_load_input<FIRST>(in, refs, e0);
+    Affine p2 = p1;
+    if (has2) p2 = aff_load_input<FIRST>(in, refs, e0 + 1u);
+    Fq den;
+    const uint32_t kind = aff_pair_kind(p1, p2, has2, den);
+    slot_meta[s] = make_uint2(e0, kind);
+    if (aff_kind_needs_inverse(kind)) {
+      store_rw(prefix + s, run);
+      run = run * den;
+    }
+  }
+  // butterfly: g = product of the lanes of my group, o = product of the group WITHOUT my own total
+  Fq g = run, o = Fq::one();
+#pragma unroll 1
+  for (int m = 1; m < 32; m <<= 1) {
+    const Fq pg = shfl_xor_fq(g, m);
+    o = (m == 1) ? pg : o * pg;
+    g = g * pg;
+  }
+  store_rw(others + (size_t)warp * 32u + lane, o);
+  if (lane == 0) store_rw(warp_totals + warp, g);
+}
+
+__global__ void __launch_bounds__(64)
+k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts, uint32_t M, int G, Fq* __restrict__ warp_totals) {
+  const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
+  const uint64_t n_warps = ((uint64_t)n_slots + 32u * (uint32_t)G - 1u) / (32u * (uint32_t)G);
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_warps) return;
+  store_rw(warp_totals + i, fp_inv(load_rw(warp_totals + i)));
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(AFF_THREADS)
+k_aff_finish(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ out_counts,
+             const uint32_t* __restrict__ out_starts, uint32_t M, int G, const Fq* __restrict__ prefix,
+             const uint2* __restrict__ slot_meta, const Fq* __restrict__ others, const Fq* __restrict__ warp_totals,
+             Affine* __restrict__ out) {
+  const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
+  if (base64 >= n_slots) return;
+  const uint32_t base = (uint32_t)base64;
+  // 1 / (my total) = 1 / (warp total) * (product of the other lanes' totals)
+  Fq inv = load_rw(warp_totals + warp) * load_rw(others + (size_t)warp * 32u + lane);
+#pragma unroll 1
+  for (int k = G - 1; k >= 0; k--) {
+    const uint32_t s = base + (uint32_t)k * 32u + lane;
+    if (s >= n_slots) continue;
+    const uint2 sm = slot_meta[s];
+    const uint32_t e0 = sm.x, kind = sm.y;
+    Affine r;
+    if (kind == PK_ZERO) { r.x = Fq::zero(); r.y = Fq::zero(); }
+    else if (kind == PK_PASS1) r = aff_load_input<FIRST>(in, refs, e0);
+    else if (kind == PK_PASS2) r = aff_load_input<FIRST>(in, refs, e0 + 1u);
+    else {
+      const Affine p1 = aff_load_input<FIRST>(in, refs, e0);
+      const Affine p2 = aff_load_input<FIRST>(in, refs, e0 + 1u);
+      const Fq den = (kind == PK_ADD) ? (p2.x - p1.x) : p1.y.dbl();
+      const Fq inv_den = inv * load_rw(prefix + s);
+      inv = inv * den;
+      r = aff_pair_finish(kind, p1, p2, inv_den);
+    }
+    store_rw(out + s, r);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // 4. work list, largest items first
 // -------------------------------------------------------------------------------------------
 __global__ void k_classify(const uint32_t* __restrict__ counts, uint32_t M, uint32_t split, uint32_t* __restrict__ poff,
@@ -308,6 +447,8 @@ __global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M,
 // -------------------------------------------------------------------------------------------
 // 5. bucket accumulation: one thread per work item
 // -------------------------------------------------------------------------------------------
+// DIRECT: the input is the point array left by the affine levels (slot = position, no sign), not a reference list
+template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 3)  // 3 CTAs/SM: at most 168 registers per thread
 k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ starts, const uint32_t* __restrict__ poff, const uint2* __restrict__ work,
@@ -324,9 +465,14 @@ k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sort
   // streamed MSM: the bucket persists across chunks (live[gb] != 0 once it has been written)
   XYZZ acc = (live != nullptr && po == NONE && live[gb]) ? load_rw(buckets + gb) : XYZZ::identity();
   for (uint32_t e = 0; e < len; e++) {
-    const uint32_t ref = __ldg(sorted + first + e);
-    Affine p = load_ro(bases + (ref & 0x7FFFFFFFu));
-    if (ref >> 31) p.y = p.y.neg();
+    Affine p;
+    if (DIRECT) {
+      p = load_ro(bases + first + e);
+    } else {
+      const uint32_t ref = __ldg(sorted + first + e);
+      p = load_ro(bases + (ref & 0x7FFFFFFFu));
+      if (ref >> 31) p.y = p.y.neg();
+    }
     xyzz_madd(acc, p);
   }
   XYZZ* dst = (po == NONE) ? (buckets + gb) : (partials + po + k);
@@ -753,6 +899,27 @@ MsmPlan msm_plan_merged(size_t n, int c_forced) {
 // Plan of one MSM pass over these bases: merged (one bucket set) when a precomputed table is present.
 static MsmPlan plan_for(const MsmBases& B, size_t n) { return B.table != nullptr ? msm_plan_merged(n, B.c) : msm_plan(n); }
 
+// Affine levels before the XYZZ accumulation.  GM_MSM_AFFINE = k forces k levels (0 = off, tests force them on tiny
+// inputs); otherwise: none for small MSMs (each level costs three launches and one serial field inversion, about
+// 0.1 ms), else as many as leave 2..4 points per bucket on average.
+static int affine_levels(size_t refs, size_t M) {
+  const char* env = getenv("GM_MSM_AFFINE");
+  if (env && *env) { int v = atoi(env); if (v >= 0) return std::min(v, 8); }
+  if (refs < ((size_t)1 << 22)) return 0;
+  const size_t avg = refs / M;
+  int r = 0;
+  while (r < 8 && (avg >> (r + 1)) >= 2) r++;
+  return r;
+}
+
+// pairs per thread of one affine level: long runs amortise the warp butterfly (10 products per thread), but the
+// level must still spread over >= 64 warps per SM
+static int aff_pick_g(const gm_ctx* ctx, size_t slots) {
+  int G = 64;
+  while (G > 4 && slots / (32 * (size_t)G) < (size_t)ctx->sm_count * 64) G >>= 1;
+  return G;
+}
+
 // Phase A: digits, counting sort, work list, bucket accumulation.  Buckets go to `buckets`; when `live` is given the
 // buckets persist across calls (streamed MSM) and are updated in place, otherwise they are (re)written and the
 // per-call counts (ctx->msm.counts) tell which ones are valid.
@@ -767,14 +934,6 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   const uint32_t ref_offset = merged ? (uint32_t)base_offset : 0u;
   const uint32_t ref_stride = merged ? (uint32_t)B.n : 0u;
   const size_t refs = (size_t)P.W * n;
-  // references per work item: enough items to keep every SM busy with several waves, but long enough that the
-  // per-item partial sums of a hot bucket stay few
-  uint32_t split = SPLIT;
-  const size_t avg_load = refs / M + 1;
-  while (split > 32 && split / 2 >= 4 * avg_load && refs / split < (size_t)ctx->sm_count * 384 * 4) split >>= 1;
-  const size_t max_split = refs / split + 1;
-  const size_t max_partials = 2 * max_split + 1;
-  const size_t max_items = std::min<size_t>(M, refs) + max_split + 1;
 
   GM_TRY(S.digits.reserve(refs * 4));
   GM_TRY(S.sorted.reserve(refs * 4));
@@ -782,36 +941,105 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   GM_TRY(S.starts.reserve(M * 4));
   GM_TRY(S.cursor.reserve(M * 4));
   GM_TRY(S.poff.reserve(M * 4));
-  GM_TRY(S.partials.reserve(max_partials * sizeof(XYZZ)));
-  GM_TRY(S.work.reserve(max_items * sizeof(uint2)));
-  GM_TRY(S.split.reserve(max_split * 4));
   const size_t ntiles = (M + SCAN_TILE - 1) / SCAN_TILE;
   GM_TRY(S.scan_tmp.reserve(ntiles * 4 + 16));
   static_assert(sizeof(Meta) <= 16384, "Meta fits its slot");
   GM_TRY(S.meta.reserve(16384));
   Meta* meta = S.meta.as<Meta>();
 
+  // affine levels before the XYZZ accumulation (0 = none); their scratch is optional: without it the XYZZ path runs alone
+  int levels = affine_levels(refs, M);
+  size_t slot_bound[9];
+  slot_bound[0] = refs;
+  for (int r = 0; r < levels; r++) slot_bound[r + 1] = (slot_bound[r] + std::min(M, slot_bound[r])) / 2 + 1;
+  if (levels > 0) {
+    const size_t s1 = slot_bound[1], s2 = levels > 1 ? slot_bound[2] : 0;
+    const size_t warps1 = s1 / (32 * 4) + 1;   // G >= 4
+    const bool ok = S.aff_a.reserve(s1 * sizeof(Affine)) == GM_OK && S.aff_b.reserve(s2 * sizeof(Affine) + 16) == GM_OK &&
+                    S.aff_prefix.reserve(s1 * sizeof(Fq)) == GM_OK && S.aff_meta.reserve(s1 * sizeof(uint2)) == GM_OK &&
+                    S.aff_others.reserve(warps1 * 32 * sizeof(Fq)) == GM_OK && S.aff_totals.reserve(warps1 * sizeof(Fq)) == GM_OK &&
+                    S.aff_counts[0].reserve(M * 4) == GM_OK && S.aff_counts[1].reserve(M * 4) == GM_OK &&
+                    S.aff_starts[0].reserve(M * 4) == GM_OK && S.aff_starts[1].reserve(M * 4) == GM_OK;
+    if (!ok) {
+      S.aff_a.release(); S.aff_b.release(); S.aff_prefix.release(); S.aff_meta.release();
+      cudaGetLastError();
+      levels = 0;
+    }
+  }
+  const size_t refs_eff = slot_bound[levels];   // upper bound of the points the XYZZ accumulation still has to add
+
+  // references per work item: enough items to keep every SM busy with several waves, but long enough that the
+  // per-item partial sums of a hot bucket stay few
+  uint32_t split = SPLIT;
+  const size_t avg_load = refs_eff / M + 1;
+  while (split > 32 && split / 2 >= 4 * avg_load && refs_eff / split < (size_t)ctx->sm_count * 384 * 4) split >>= 1;
+  const size_t max_split = refs_eff / split + 1;
+  const size_t max_partials = 2 * max_split + 1;
+  const size_t max_items = std::min<size_t>(M, refs_eff) + max_split + 1;
+  GM_TRY(S.partials.reserve(max_partials * sizeof(XYZZ)));
+  GM_TRY(S.work.reserve(max_items * sizeof(uint2)));
+  GM_TRY(S.split.reserve(max_split * 4));
+
   cudaStream_t st = ctx->stream;
   GM_CUDA(cudaMemsetAsync(S.counts.p, 0, M * 4, st));
   GM_CUDA(cudaMemsetAsync(meta, 0, sizeof(Meta), st));
 
   const uint32_t n32 = (uint32_t)n;
+  const uint32_t M32 = (uint32_t)M;
   GM_CUDA(cudaEventRecord(ctx->ev[2], st));
   LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
-  LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), (uint32_t)M);
+  LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
-  LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), (uint32_t)M);
+  LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
   LAUNCH(ctx, k_scatter, dim3((n32 + 255) / 256, P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, merged ? 1 : 0, ref_offset, ref_stride, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
-  LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, split, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
-  LAUNCH(ctx, k_size_scan, 1, 32, 0, meta, split);
-  LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, S.counts.as<uint32_t>(), (uint32_t)M, split, S.work.as<uint2>(), meta);
   GM_CUDA(cudaEventRecord(ctx->ev[3], st));
-  LAUNCH(ctx, k_accumulate, (unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, d_bases, S.sorted.as<uint32_t>(),
-         S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, split, buckets, S.partials.as<XYZZ>(), live);
+
+  // ---- affine levels ----
+  const uint32_t* cur_counts = S.counts.as<uint32_t>();
+  const uint32_t* cur_starts = S.starts.as<uint32_t>();
+  const Affine* cur_pts = d_bases;
+  for (int r = 0; r < levels; r++) {
+    uint32_t* oc = S.aff_counts[r & 1].as<uint32_t>();
+    uint32_t* os = S.aff_starts[r & 1].as<uint32_t>();
+    Affine* out = (r & 1) ? S.aff_b.as<Affine>() : S.aff_a.as<Affine>();
+    LAUNCH(ctx, k_aff_counts, (unsigned)((M + 255) / 256), 256, 0, cur_counts, M32, oc);
+    LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, oc, os, S.scan_tmp.as<uint32_t>(), M32);
+    LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
+    LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, os, S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
+    const size_t bound = slot_bound[r + 1];
+    const int G = aff_pick_g(ctx, bound);
+    const size_t warps = (bound + 32 * (size_t)G - 1) / (32 * (size_t)G);
+    const unsigned ctas = (unsigned)((warps * 32 + AFF_THREADS - 1) / AFF_THREADS);
+    Fq* prefix = S.aff_prefix.as<Fq>();
+    uint2* smeta = S.aff_meta.as<uint2>();
+    Fq* others = S.aff_others.as<Fq>();
+    Fq* totals = S.aff_totals.as<Fq>();
+    if (r == 0)
+      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, cur_pts, S.sorted.as<uint32_t>(), cur_counts, cur_starts, oc, os, M32, G, prefix, smeta, others, totals);
+    else
+      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, cur_pts, (const uint32_t*)nullptr, cur_counts, cur_starts, oc, os, M32, G, prefix, smeta, others, totals);
+    LAUNCH(ctx, k_aff_invert, (unsigned)((warps + 63) / 64), 64, 0, oc, os, M32, G, totals);
+    if (r == 0)
+      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, cur_pts, S.sorted.as<uint32_t>(), oc, os, M32, G, prefix, smeta, others, totals, out);
+    else
+      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, cur_pts, (const uint32_t*)nullptr, oc, os, M32, G, prefix, smeta, others, totals, out);
+    cur_counts = oc; cur_starts = os; cur_pts = out;
+  }
+
+  LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, cur_counts, M32, split, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
+  LAUNCH(ctx, k_size_scan, 1, 32, 0, meta, split);
+  LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, cur_counts, M32, split, S.work.as<uint2>(), meta);
+  const unsigned acc_ctas = (unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS);
+  if (levels > 0)
+    LAUNCH(ctx, k_accumulate<true>, acc_ctas, ACC_THREADS, 0, cur_pts, (const uint32_t*)nullptr, cur_counts, cur_starts, S.poff.as<uint32_t>(),
+           S.work.as<uint2>(), meta, split, buckets, S.partials.as<XYZZ>(), live);
+  else
+    LAUNCH(ctx, k_accumulate<false>, acc_ctas, ACC_THREADS, 0, d_bases, S.sorted.as<uint32_t>(), cur_counts, cur_starts, S.poff.as<uint32_t>(),
+           S.work.as<uint2>(), meta, split, buckets, S.partials.as<XYZZ>(), live);
   GM_CUDA(cudaEventRecord(ctx->ev[4], st));
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
-         S.counts.as<uint32_t>(), S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), buckets, live);
+         cur_counts, S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), buckets, live);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

@@ -3,6 +3,7 @@
 // compare them with Python big integers without a GPU.  Test scaffolding only.
 #include "../../gemini_b200/csrc/fp.cuh"
 #include "../../gemini_b200/csrc/g1.cuh"
+#include "../../gemini_b200/csrc/g1_affine.cuh"
 #include "../../gemini_b200/csrc/fq_f64.cuh"
 #include <string.h>
 using namespace gm;
@@ -64,5 +65,32 @@ void hc_xyzz_to_jacobian(const uint32_t* acc, uint32_t* out, int n) {
     Jacobian J = xyzz_to_jacobian_normalized(A);
     memcpy(out + 36 * i, &J, 144);
   }
+}
+// One batch of affine pair additions with ONE shared inversion, walked exactly like a thread of
+// k_aff_prepare / k_aff_finish (msm.cu): exclusive prefix products forward, back-substitution backward.
+// p1, p2: n x 24 u32; has2: n flags; out: n x 24 u32; kinds: n
+void hc_aff_batch(const uint32_t* p1, const uint32_t* p2, const int* has2, int n, uint32_t* out, uint32_t* kinds) {
+  Fq* prefix = new Fq[n];
+  Fq run = Fq::one();
+  for (int i = 0; i < n; i++) {
+    Affine a, b; memcpy(&a, p1 + 24 * i, 96); memcpy(&b, p2 + 24 * i, 96);
+    Fq den;
+    kinds[i] = aff_pair_kind(a, b, has2[i] != 0, den);
+    if (aff_kind_needs_inverse(kinds[i])) { prefix[i] = run; run = run * den; }
+  }
+  Fq inv = fp_inv(run);
+  for (int i = n - 1; i >= 0; i--) {
+    Affine a, b; memcpy(&a, p1 + 24 * i, 96); memcpy(&b, p2 + 24 * i, 96);
+    Fq inv_den = Fq::one();
+    if (aff_kind_needs_inverse(kinds[i])) {
+      Fq den;
+      aff_pair_kind(a, b, has2[i] != 0, den);
+      inv_den = inv * prefix[i];
+      inv = inv * den;
+    }
+    Affine r = aff_pair_finish(kinds[i], a, b, inv_den);
+    memcpy(out + 24 * i, &r, 96);
+  }
+  delete[] prefix;
 }
 }

@@ -114,3 +114,28 @@ def test_xyzz_formulas_complete(hc):
     hc.hc_xyzz_to_jacobian(P(acc), P(out), n)
     for i, (a, _) in enumerate(cases):
         assert from_jac(out[i]) == o.g1_double(a), i
+
+
+def test_affine_pair_batch_shared_inversion(hc):
+    """g1_affine.cuh: pair classification, chord / tangent formulas and the prefix-product walk that shares one
+    inversion across a whole batch (the per-thread schedule of k_aff_prepare / k_aff_finish)."""
+    rng = random.Random(7)
+    pts = [o.g1_mul(o.G1_GEN, rng.randrange(1, o.R)) for _ in range(12)]
+    cases = [(a, b, 1) for a in pts[:6] for b in pts[6:]]
+    cases += [(None, pts[0], 1), (pts[0], None, 1), (None, None, 1), (pts[1], pts[1], 1), (pts[2], o.g1_neg(pts[2]), 1),
+              (pts[3], pts[4], 0), (None, pts[4], 0), (pts[5], pts[5], 1)]
+    rng.shuffle(cases)
+    n = len(cases)
+    enc = lambda p: [0] * 24 if p is None else fq_l(p[0]) + fq_l(p[1])
+    p1 = np.array([enc(a) for a, _, _ in cases], dtype=np.uint32)
+    p2 = np.array([enc(b) for _, b, _ in cases], dtype=np.uint32)
+    has2 = np.array([h for _, _, h in cases], dtype=np.int32)
+    out = np.zeros((n, 24), dtype=np.uint32)
+    kinds = np.zeros(n, dtype=np.uint32)
+    hc.hc_aff_batch(P(p1), P(p2), P(has2), n, P(out), P(kinds))
+    for i, (a, b, h) in enumerate(cases):
+        want = o.g1_add(a, b) if h else a
+        x, y = l_fq(out[i, :12]), l_fq(out[i, 12:])
+        got = None if (x, y) == (0, 0) else (x, y)
+        assert got == want, (i, int(kinds[i]))
+    assert set(int(k) for k in kinds) == {0, 1, 2, 3, 4}
