@@ -21,6 +21,7 @@ namespace gm {
 struct FqParams {
   static constexpr int N = 12;
   static constexpr uint32_t INV = 0xfffcfffdu;  // -q^{-1} mod 2^32
+  GM_HD static constexpr uint32_t inv() { return INV; }
   GM_HD static constexpr uint32_t mod(int j) {
     constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
                                 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
@@ -40,9 +41,24 @@ struct FqParams {
   }
 };
 
+// -r^{-1} mod 2^32 is 0xffffffff, so the Montgomery quotient digit is m = -E[0].  When ptxas sees that negation it
+// rewrites the products m * r_j and un-fuses every (mad.lo.cc, madc.hi.cc) pair of the reduction rows into
+// IMAD + IMAD.HI (48 + 64 instructions instead of 64 IMAD.WIDE; IMAD.HI runs at 26 lanes/clk/SM).  Reading the
+// constant from the constant bank keeps m opaque: one extra IMAD per row, all rows fused (checked with cuobjdump).
+#if defined(__CUDACC__)
+static __constant__ uint32_t FR_INV_BANK = 0xffffffffu;
+#endif
+
 struct FrParams {
   static constexpr int N = 8;
   static constexpr uint32_t INV = 0xffffffffu;  // -r^{-1} mod 2^32
+  GM_HD static uint32_t inv() {
+#if defined(__CUDA_ARCH__)
+    return FR_INV_BANK;
+#else
+    return INV;
+#endif
+  }
   GM_HD static constexpr uint32_t mod(int j) {
     constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
                                0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -79,7 +95,7 @@ GM_HD void row_first(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t w) {
 template <class P>
 GM_HD void mont_reduce_step(uint32_t* E, uint32_t* O) {
   constexpr int N = P::N;
-  const uint32_t m = E[0] * P::INV;
+  const uint32_t m = E[0] * P::inv();
   mad_wide_cc(O[0], O[1], m, P::mod(1), O[0], O[1]);
 #pragma unroll
   for (int j = 3; j < N; j += 2) madc_wide_cc(O[j - 1], O[j], m, P::mod(j), O[j - 1], O[j]);
@@ -331,9 +347,17 @@ GM_HD Fp<P> fp_inv(const Fp<P>& a) {
     detail::limbs_sub<N>(x.v, pm, r);   // p - r in (0, p]
     detail::cond_sub_p<P>(x.v, x.v);
   }
-  // x = (aR)^{-1} 2^k = a'^{-1} 2^(k - 32N); the Montgomery form of the inverse is a'^{-1} 2^(32N): double 64N - k times
+  // x = (aR)^{-1} 2^k = a'^{-1} 2^(k - 32N); the Montgomery form of the inverse is a'^{-1} 2^(32N): multiply by
+  // 2^m, m = 64N - k (k >= bits(p), so m < 32N + a few).  2^sh as a plain integer times R^2 does it in two
+  // products, mont(mont(x, 2^sh), R^2) = x 2^sh, instead of up to 32N modular doublings on the serial tail.
+  const int m = 64 * N - k;
+  const int sh = m < 32 * N - 1 ? m : 32 * N - 1;
+  Fp<P> e, r2;
+#pragma unroll
+  for (int j = 0; j < N; j++) { e.v[j] = (j == (sh >> 5)) ? (1u << (sh & 31)) : 0u; r2.v[j] = P::r2(j); }
+  x = (x * e) * r2;   // e is not reduced (it may exceed p) but it is the row operand: a < p, b < R is all CIOS needs
 #pragma unroll 1
-  for (int i = k; i < 64 * N; i++) x = x.dbl();
+  for (int i = sh; i < m; i++) x = x.dbl();
   return x;
 }
 

@@ -284,15 +284,43 @@ __device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, int m) {
   return r;
 }
 
+// x coordinate only (48 of the 96 bytes): all the classification of a generic pair needs
 template <bool FIRST>
-__global__ void __launch_bounds__(AFF_THREADS)
+__device__ __forceinline__ Fq aff_load_x(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e) {
+  const Affine* p = FIRST ? in + (__ldg(refs + e) & 0x7FFFFFFFu) : in + e;
+  return load_ro(&p->x);
+}
+
+struct AffSlot {
+  uint32_t e0;
+  bool valid, has2;
+  Fq x1, x2;
+};
+
+template <bool FIRST>
+__device__ __forceinline__ void aff_fetch_slot(AffSlot& sl, uint32_t s, uint32_t n_slots, uint32_t b_lo, uint32_t b_hi,
+                                               const Affine* __restrict__ in, const uint32_t* __restrict__ refs,
+                                               const uint32_t* __restrict__ in_counts, const uint32_t* __restrict__ in_starts,
+                                               const uint32_t* __restrict__ out_starts) {
+  sl.valid = s < n_slots;
+  if (!sl.valid) return;
+  const uint32_t gb = bucket_of_slot(out_starts, b_lo, b_hi, s);
+  const uint32_t j = s - __ldg(out_starts + gb);
+  sl.e0 = __ldg(in_starts + gb) + 2u * j;
+  sl.has2 = 2u * j + 1u < __ldg(in_counts + gb);
+  sl.x1 = aff_load_x<FIRST>(in, refs, sl.e0);
+  sl.x2 = sl.has2 ? aff_load_x<FIRST>(in, refs, sl.e0 + 1u) : sl.x1;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(AFF_THREADS, 4)
 k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ in_counts,
               const uint32_t* __restrict__ in_starts, const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts,
-              uint32_t M, int G, Fq* __restrict__ prefix, uint2* __restrict__ slot_meta, Fq* __restrict__ others,
-              Fq* __restrict__ warp_totals) {
+              uint32_t M, int G, uint32_t warp_base, Fq* __restrict__ prefix, uint2* __restrict__ slot_meta,
+              Fq* __restrict__ others, Fq* __restrict__ warp_totals) {
   const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t warp = warp_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
   if (base64 >= n_slots) return;                      // whole warp out of range
   const uint32_t base = (uint32_t)base64;
@@ -300,24 +328,31 @@ k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, 
   const uint32_t b_lo = bucket_of_slot(out_starts, 0, M - 1, base);
   const uint32_t b_hi = bucket_of_slot(out_starts, b_lo, M - 1, last);
   Fq run = Fq::one();
+  // the gathers of slot k+1 (bucket search, references, x coordinates) are issued before the product of slot k
+  AffSlot cur, nxt;
+  aff_fetch_slot<FIRST>(cur, base + lane, n_slots, b_lo, b_hi, in, refs, in_counts, in_starts, out_starts);
 #pragma unroll 1
   for (int k = 0; k < G; k++) {
+    if (!cur.valid) break;
     const uint32_t s = base + (uint32_t)k * 32u + lane;
-    if (s >= n_slots) break;
-    const uint32_t gb = bucket_of_slot(out_starts, b_lo, b_hi, s);
-    const uint32_t j = s - __ldg(out_starts + gb);
-    const uint32_t e0 = __ldg(in_starts + gb) + 2u * j;
-    const bool has2 = 2u * j + 1u < __ldg(in_counts + gb);
-    const Affine p1 = aff_load_input<FIRST>(in, refs, e0);
-    Affine p2 = p1;
-    if (has2) p2 = aff_load_input<FIRST>(in, refs, e0 + 1u);
-    Fq den;
-    const uint32_t kind = aff_pair_kind(p1, p2, has2, den);
-    slot_meta[s] = make_uint2(e0, kind);
+    nxt.valid = false;
+    if (k + 1 < G) aff_fetch_slot<FIRST>(nxt, s + 32u, n_slots, b_lo, b_hi, in, refs, in_counts, in_starts, out_starts);
+    Fq den = cur.x2 - cur.x1;
+    uint32_t kind = PK_ADD;
+    if (!cur.has2) {
+      kind = PK_PASS1;
+    } else if (den.is_zero() || cur.x1.is_zero() || cur.x2.is_zero()) {
+      // rare: equal x (P + P, P - P) or a possible identity (0, 0): classify with the full points
+      const Affine p1 = aff_load_input<FIRST>(in, refs, cur.e0);
+      const Affine p2 = aff_load_input<FIRST>(in, refs, cur.e0 + 1u);
+      kind = aff_pair_kind(p1, p2, true, den);
+    }
+    slot_meta[s] = make_uint2(cur.e0, kind);
     if (aff_kind_needs_inverse(kind)) {
       store_rw(prefix + s, run);
       run = run * den;
     }
+    cur = nxt;
   }
   // butterfly: g = product of the lanes of my group, o = product of the group WITHOUT my own total
   Fq g = run, o = Fq::one();
@@ -331,24 +366,30 @@ k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, 
   if (lane == 0) store_rw(warp_totals + warp, g);
 }
 
-__global__ void __launch_bounds__(64)
-k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts, uint32_t M, int G, Fq* __restrict__ warp_totals) {
+// spread = 32: one inversion per WARP (lane 0).  The binary almost-inverse branches three ways per step, so 32
+// different inputs in one warp run every branch every step; with few inversions (they are a serial stage of the
+// level) it is faster to leave 31 lanes idle.  spread = 1: one inversion per thread (large levels).
+__global__ void __launch_bounds__(128)
+k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts, uint32_t M, int G, int spread,
+             uint32_t warp_base, uint32_t warp_end, Fq* __restrict__ warp_totals) {
   const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
-  const uint64_t n_warps = ((uint64_t)n_slots + 32u * (uint32_t)G - 1u) / (32u * (uint32_t)G);
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n_warps = min((uint64_t)warp_end, ((uint64_t)n_slots + 32u * (uint32_t)G - 1u) / (32u * (uint32_t)G));
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t % (uint32_t)spread) return;
+  const uint64_t i = warp_base + t / (uint32_t)spread;
   if (i >= n_warps) return;
   store_rw(warp_totals + i, fp_inv(load_rw(warp_totals + i)));
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(AFF_THREADS)
+__global__ void __launch_bounds__(AFF_THREADS, 4)
 k_aff_finish(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ out_counts,
-             const uint32_t* __restrict__ out_starts, uint32_t M, int G, const Fq* __restrict__ prefix,
+             const uint32_t* __restrict__ out_starts, uint32_t M, int G, uint32_t warp_base, const Fq* __restrict__ prefix,
              const uint2* __restrict__ slot_meta, const Fq* __restrict__ others, const Fq* __restrict__ warp_totals,
              Affine* __restrict__ out) {
   const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t warp = warp_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
   if (base64 >= n_slots) return;
   const uint32_t base = (uint32_t)base64;
@@ -899,25 +940,41 @@ MsmPlan msm_plan_merged(size_t n, int c_forced) {
 // Plan of one MSM pass over these bases: merged (one bucket set) when a precomputed table is present.
 static MsmPlan plan_for(const MsmBases& B, size_t n) { return B.table != nullptr ? msm_plan_merged(n, B.c) : msm_plan(n); }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 // Affine levels before the XYZZ accumulation.  GM_MSM_AFFINE = k forces k levels (0 = off, tests force them on tiny
 // inputs); otherwise: none for small MSMs (each level costs three launches and one serial field inversion, about
-// 0.1 ms), else as many as leave 2..4 points per bucket on average.
+// 0.1 ms), else as many as leave 4..8 points per bucket on average.
 static int affine_levels(size_t refs, size_t M) {
   const char* env = getenv("GM_MSM_AFFINE");
   if (env && *env) { int v = atoi(env); if (v >= 0) return std::min(v, 8); }
   if (refs < ((size_t)1 << 22)) return 0;
   const size_t avg = refs / M;
   int r = 0;
-  while (r < 8 && (avg >> (r + 1)) >= 2) r++;
+  while (r < 8 && (avg >> (r + 1)) >= (size_t)env_int("GM_AFF_KEEP", 4)) r++;
   return r;
 }
 
-// pairs per thread of one affine level: long runs amortise the warp butterfly (10 products per thread), but the
-// level must still spread over >= 64 warps per SM
-static int aff_pick_g(const gm_ctx* ctx, size_t slots) {
-  int G = 64;
-  while (G > 4 && slots / (32 * (size_t)G) < (size_t)ctx->sm_count * 64) G >>= 1;
-  return G;
+// Shape of one affine level: every thread walks G slots.  Long runs amortise the 10 products of the warp butterfly
+// and mean fewer inversions; short runs give more warps to balance the SMs.  Measured on B200 (profiles/r01_summary.md):
+// at least 64 warps per SM wins at 2^20 and 2^24; one or two big waves, or cutting a level in two parts to overlap
+// the inversions on a second stream, were slower.  GM_AFF_WPS overrides the warps-per-SM floor.
+struct AffShape {
+  int G;
+  uint32_t warps;   // a multiple of the 4 warps of a CTA
+};
+static AffShape aff_shape(const gm_ctx* ctx, size_t slots) {
+  const size_t wps = (size_t)std::max(1, env_int("GM_AFF_WPS", 64));
+  size_t G = slots / (32 * (size_t)ctx->sm_count * wps);
+  G = std::min<size_t>(64, std::max<size_t>(4, G));
+  const size_t warps = (slots + 32 * G - 1) / (32 * G);
+  AffShape sh;
+  sh.warps = (uint32_t)((warps + 3) / 4 * 4);
+  sh.G = (int)G;
+  return sh;
 }
 
 // Phase A: digits, counting sort, work list, bucket accumulation.  Buckets go to `buckets`; when `live` is given the
@@ -954,7 +1011,7 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   for (int r = 0; r < levels; r++) slot_bound[r + 1] = (slot_bound[r] + std::min(M, slot_bound[r])) / 2 + 1;
   if (levels > 0) {
     const size_t s1 = slot_bound[1], s2 = levels > 1 ? slot_bound[2] : 0;
-    const size_t warps1 = s1 / (32 * 4) + 1;   // G >= 4
+    const size_t warps1 = (size_t)aff_shape(ctx, s1).warps + (size_t)ctx->sm_count * 64;   // the first level has the most warps
     const bool ok = S.aff_a.reserve(s1 * sizeof(Affine)) == GM_OK && S.aff_b.reserve(s2 * sizeof(Affine) + 16) == GM_OK &&
                     S.aff_prefix.reserve(s1 * sizeof(Fq)) == GM_OK && S.aff_meta.reserve(s1 * sizeof(uint2)) == GM_OK &&
                     S.aff_others.reserve(warps1 * 32 * sizeof(Fq)) == GM_OK && S.aff_totals.reserve(warps1 * sizeof(Fq)) == GM_OK &&
@@ -1006,23 +1063,27 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
     LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, oc, os, S.scan_tmp.as<uint32_t>(), M32);
     LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
     LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, os, S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
-    const size_t bound = slot_bound[r + 1];
-    const int G = aff_pick_g(ctx, bound);
-    const size_t warps = (bound + 32 * (size_t)G - 1) / (32 * (size_t)G);
-    const unsigned ctas = (unsigned)((warps * 32 + AFF_THREADS - 1) / AFF_THREADS);
+    const AffShape shp = aff_shape(ctx, slot_bound[r + 1]);
+    const int G = shp.G;
+    const unsigned ctas = shp.warps * 32 / AFF_THREADS;
+    // few inversions: one per single-warp CTA (lane 0 only: the three-way branch of the almost-inverse does not diverge)
+    const int spread = shp.warps <= (uint32_t)ctx->sm_count * 24 ? 32 : 1;
+    const unsigned inv_threads = spread == 32 ? 32u : 128u;
+    const unsigned inv_ctas = (unsigned)(((size_t)shp.warps * spread + inv_threads - 1) / inv_threads);
     Fq* prefix = S.aff_prefix.as<Fq>();
     uint2* smeta = S.aff_meta.as<uint2>();
     Fq* others = S.aff_others.as<Fq>();
     Fq* totals = S.aff_totals.as<Fq>();
+    const uint32_t* refs0 = r == 0 ? S.sorted.as<uint32_t>() : nullptr;
     if (r == 0)
-      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, cur_pts, S.sorted.as<uint32_t>(), cur_counts, cur_starts, oc, os, M32, G, prefix, smeta, others, totals);
+      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, 0u, prefix, smeta, others, totals);
     else
-      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, cur_pts, (const uint32_t*)nullptr, cur_counts, cur_starts, oc, os, M32, G, prefix, smeta, others, totals);
-    LAUNCH(ctx, k_aff_invert, (unsigned)((warps + 63) / 64), 64, 0, oc, os, M32, G, totals);
+      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, 0u, prefix, smeta, others, totals);
+    LAUNCH(ctx, k_aff_invert, inv_ctas, inv_threads, 0, oc, os, M32, G, spread, 0u, shp.warps, totals);
     if (r == 0)
-      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, cur_pts, S.sorted.as<uint32_t>(), oc, os, M32, G, prefix, smeta, others, totals, out);
+      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, 0u, prefix, smeta, others, totals, out);
     else
-      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, cur_pts, (const uint32_t*)nullptr, oc, os, M32, G, prefix, smeta, others, totals, out);
+      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, 0u, prefix, smeta, others, totals, out);
     cur_counts = oc; cur_starts = os; cur_pts = out;
   }
 
