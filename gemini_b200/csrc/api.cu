@@ -1,5 +1,6 @@
 // C ABI of libgemini_b200 (include/gemini_b200.h): argument checking, host<->device staging and
 // handle lifetimes.  All arithmetic happens in the kernels of msm.cu / fr.cu; there is no CPU path.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -87,6 +88,11 @@ int gm_init(int device_id, gm_ctx** out_ctx) {
   cudaDeviceProp prop;
   GM_CUDA(cudaGetDeviceProperties(&prop, device_id));
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    // GM_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity (measured: no effect on the MSM gathers; default untouched)
+    const char* fg = getenv("GM_L2_FETCH");
+    if (fg && atoi(fg) > 0) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)); cudaGetLastError(); }
+  }
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) GM_CUDA(cudaEventCreate(&ev));
@@ -291,14 +297,19 @@ int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len) {
     const MsmPlan P = msm_plan_merged(std::min(expect, prefix), 0);
     GM_ARG((double)P.W * (double)prefix < 2147483648.0, "SRS too large for a precomputed table (W * n must stay below 2^31)");
     void* table = nullptr;
-    const size_t bytes = (size_t)P.W * prefix * sizeof(Affine);
+    // GM_TABLE_PAD=1 pads the records to one 128-byte line each: a third less DRAM traffic in the gathers (ncu:
+    // 45.1 -> 32.3 GB for k_aff_finish<1> at 2^24) but no time gained - the gathers are latency-, not
+    // bandwidth-bound - at 33 % more HBM, so packed 96-byte records stay the default.
+    const char* pad_env = getenv("GM_TABLE_PAD");
+    const int rec_q = (pad_env && atoi(pad_env)) ? 8 : 6;
+    const size_t bytes = (size_t)P.W * prefix * rec_q * 16;
     cudaError_t e = cudaMalloc(&table, bytes);
     if (e != cudaSuccess) {
       set_error("precompute: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
       srs_drop_tables(srs);
       return GM_ERR_OOM;
     }
-    int rc = msm_precompute(ctx, reinterpret_cast<const Affine*>(srs->d_points), prefix, P.c, P.W, reinterpret_cast<Affine*>(table));
+    int rc = msm_precompute(ctx, reinterpret_cast<const Affine*>(srs->d_points), prefix, P.c, P.W, rec_q, reinterpret_cast<Affine*>(table));
     e = cudaStreamSynchronize(ctx->stream);
     if (rc != GM_OK || e != cudaSuccess) {
       if (rc == GM_OK) { set_error("precompute: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
@@ -310,6 +321,7 @@ int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len) {
     srs->pre[k].prefix = prefix;
     srs->pre[k].c = P.c;
     srs->pre[k].W = P.W;
+    srs->pre[k].rec_q = rec_q;
     srs->npre = k + 1;
     prefix >>= 3;
     expect = prefix;
@@ -373,6 +385,7 @@ static MsmBases bases_of_srs(const gm_srs* srs, size_t base_offset, size_t n, bo
       b.n = srs->pre[k].prefix;
       b.c = srs->pre[k].c;
       b.W = srs->pre[k].W;
+      b.rec_q = srs->pre[k].rec_q;
       break;
     }
   }

@@ -117,6 +117,7 @@ struct gm_srs {
     void* d_table = nullptr;
     size_t prefix = 0;
     int c = 0, W = 0;
+    int rec_q = 6;  // 16-byte quads per record (8 = padded to 128 B)
   };
   PreTable pre[3];
   int npre = 0;

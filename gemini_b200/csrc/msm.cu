@@ -71,6 +71,13 @@ __device__ __forceinline__ void store_rw(T* p, const T& v) {
   for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = s[k];
 }
 
+// Record idx of a base table whose records are rec_q 16-byte quads apart: 6 = packed 96-byte points, 8 = points
+// padded to 128 bytes so that a gathered record never straddles two 128-byte lines (DRAM traffic of the gathers
+// is counted in whole lines: profiles/r01_summary.md).
+__device__ __forceinline__ const Affine* rec_at(const Affine* base, size_t idx, int rec_q) {
+  return reinterpret_cast<const Affine*>(reinterpret_cast<const uint4*>(base) + idx * (size_t)rec_q);
+}
+
 // Warp-aggregated atomicAdd: lanes that target the same counter elect a leader which adds the group size
 // once; every lane gets its own slot.  For uniformly random keys this is a no-op in cost terms, for the
 // reference's default all-equal scalars (one hot bucket per window) it removes 31/32 of the contended
@@ -265,12 +272,22 @@ __device__ __forceinline__ uint32_t bucket_of_slot(const uint32_t* __restrict__ 
   }
   return lo;
 }
+// the same search in a window of the scan staged in shared memory: win[i] = starts[b_lo + i], i < span
+static constexpr int AFF_WIN = 480;   // window entries per warp (a warp's slots rarely span more buckets)
+__device__ __forceinline__ uint32_t bucket_of_slot_win(const uint32_t* win, uint32_t span, uint32_t s) {
+  uint32_t lo = 0, hi = span - 1u;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+    if (win[mid] <= s) lo = mid; else hi = mid - 1u;
+  }
+  return lo;
+}
 
 template <bool FIRST>
-__device__ __forceinline__ Affine aff_load_input(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e) {
+__device__ __forceinline__ Affine aff_load_input(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e, int rec_q) {
   if (FIRST) {
     const uint32_t ref = __ldg(refs + e);
-    Affine p = load_ro(in + (ref & 0x7FFFFFFFu));
+    Affine p = load_ro(rec_at(in, ref & 0x7FFFFFFFu, rec_q));
     if (ref >> 31) p.y = p.y.neg();   // -(0,0) = (0,0): the identity stays the identity
     return p;
   }
@@ -286,8 +303,8 @@ __device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, int m) {
 
 // x coordinate only (48 of the 96 bytes): all the classification of a generic pair needs
 template <bool FIRST>
-__device__ __forceinline__ Fq aff_load_x(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e) {
-  const Affine* p = FIRST ? in + (__ldg(refs + e) & 0x7FFFFFFFu) : in + e;
+__device__ __forceinline__ Fq aff_load_x(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e, int rec_q) {
+  const Affine* p = FIRST ? rec_at(in, __ldg(refs + e) & 0x7FFFFFFFu, rec_q) : in + e;
   return load_ro(&p->x);
 }
 
@@ -298,53 +315,65 @@ struct AffSlot {
 };
 
 template <bool FIRST>
-__device__ __forceinline__ void aff_fetch_slot(AffSlot& sl, uint32_t s, uint32_t n_slots, uint32_t b_lo, uint32_t b_hi,
+__device__ __forceinline__ void aff_fetch_slot(AffSlot& sl, uint32_t s, uint32_t n_slots, uint32_t b_lo, uint32_t b_hi, const uint32_t* win,
                                                const Affine* __restrict__ in, const uint32_t* __restrict__ refs,
                                                const uint32_t* __restrict__ in_counts, const uint32_t* __restrict__ in_starts,
-                                               const uint32_t* __restrict__ out_starts) {
+                                               const uint32_t* __restrict__ out_starts, int rec_q) {
   sl.valid = s < n_slots;
   if (!sl.valid) return;
-  const uint32_t gb = bucket_of_slot(out_starts, b_lo, b_hi, s);
-  const uint32_t j = s - __ldg(out_starts + gb);
+  uint32_t gb, start;
+  if (win != nullptr) { const uint32_t w = bucket_of_slot_win(win, b_hi - b_lo + 1u, s); gb = b_lo + w; start = win[w]; }
+  else { gb = bucket_of_slot(out_starts, b_lo, b_hi, s); start = __ldg(out_starts + gb); }
+  const uint32_t j = s - start;
   sl.e0 = __ldg(in_starts + gb) + 2u * j;
   sl.has2 = 2u * j + 1u < __ldg(in_counts + gb);
-  sl.x1 = aff_load_x<FIRST>(in, refs, sl.e0);
-  sl.x2 = sl.has2 ? aff_load_x<FIRST>(in, refs, sl.e0 + 1u) : sl.x1;
+  sl.x1 = aff_load_x<FIRST>(in, refs, sl.e0, rec_q);
+  sl.x2 = sl.has2 ? aff_load_x<FIRST>(in, refs, sl.e0 + 1u, rec_q) : sl.x1;
 }
 
 template <bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS, 4)
 k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ in_counts,
               const uint32_t* __restrict__ in_starts, const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts,
-              uint32_t M, int G, uint32_t warp_base, Fq* __restrict__ prefix, uint2* __restrict__ slot_meta,
+              uint32_t M, int G, int rec_q, Fq* __restrict__ prefix, uint2* __restrict__ slot_meta,
               Fq* __restrict__ others, Fq* __restrict__ warp_totals) {
   const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = warp_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
   if (base64 >= n_slots) return;                      // whole warp out of range
   const uint32_t base = (uint32_t)base64;
   const uint32_t last = (uint32_t)min((uint64_t)n_slots - 1u, base64 + 32u * (uint32_t)G - 1u);
   const uint32_t b_lo = bucket_of_slot(out_starts, 0, M - 1, base);
   const uint32_t b_hi = bucket_of_slot(out_starts, b_lo, M - 1, last);
+  // stage the scan entries of the buckets this warp touches in shared memory: the per-slot search then costs a few
+  // shared loads instead of a chain of dependent global loads
+  __shared__ uint32_t sh_win[AFF_THREADS / 32][AFF_WIN];
+  const uint32_t* win = nullptr;
+  if (b_hi - b_lo < (uint32_t)AFF_WIN) {
+    uint32_t* w = sh_win[threadIdx.x >> 5];
+    for (uint32_t i = lane; i <= b_hi - b_lo; i += 32u) w[i] = __ldg(out_starts + b_lo + i);
+    __syncwarp();
+    win = w;
+  }
   Fq run = Fq::one();
   // the gathers of slot k+1 (bucket search, references, x coordinates) are issued before the product of slot k
   AffSlot cur, nxt;
-  aff_fetch_slot<FIRST>(cur, base + lane, n_slots, b_lo, b_hi, in, refs, in_counts, in_starts, out_starts);
+  aff_fetch_slot<FIRST>(cur, base + lane, n_slots, b_lo, b_hi, win, in, refs, in_counts, in_starts, out_starts, rec_q);
 #pragma unroll 1
   for (int k = 0; k < G; k++) {
     if (!cur.valid) break;
     const uint32_t s = base + (uint32_t)k * 32u + lane;
     nxt.valid = false;
-    if (k + 1 < G) aff_fetch_slot<FIRST>(nxt, s + 32u, n_slots, b_lo, b_hi, in, refs, in_counts, in_starts, out_starts);
+    if (k + 1 < G) aff_fetch_slot<FIRST>(nxt, s + 32u, n_slots, b_lo, b_hi, win, in, refs, in_counts, in_starts, out_starts, rec_q);
     Fq den = cur.x2 - cur.x1;
     uint32_t kind = PK_ADD;
     if (!cur.has2) {
       kind = PK_PASS1;
     } else if (den.is_zero() || cur.x1.is_zero() || cur.x2.is_zero()) {
       // rare: equal x (P + P, P - P) or a possible identity (0, 0): classify with the full points
-      const Affine p1 = aff_load_input<FIRST>(in, refs, cur.e0);
-      const Affine p2 = aff_load_input<FIRST>(in, refs, cur.e0 + 1u);
+      const Affine p1 = aff_load_input<FIRST>(in, refs, cur.e0, rec_q);
+      const Affine p2 = aff_load_input<FIRST>(in, refs, cur.e0 + 1u, rec_q);
       kind = aff_pair_kind(p1, p2, true, den);
     }
     slot_meta[s] = make_uint2(cur.e0, kind);
@@ -371,12 +400,12 @@ k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, 
 // level) it is faster to leave 31 lanes idle.  spread = 1: one inversion per thread (large levels).
 __global__ void __launch_bounds__(128)
 k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts, uint32_t M, int G, int spread,
-             uint32_t warp_base, uint32_t warp_end, Fq* __restrict__ warp_totals) {
+             Fq* __restrict__ warp_totals) {
   const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
-  const uint64_t n_warps = min((uint64_t)warp_end, ((uint64_t)n_slots + 32u * (uint32_t)G - 1u) / (32u * (uint32_t)G));
+  const uint64_t n_warps = ((uint64_t)n_slots + 32u * (uint32_t)G - 1u) / (32u * (uint32_t)G);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t % (uint32_t)spread) return;
-  const uint64_t i = warp_base + t / (uint32_t)spread;
+  const uint64_t i = t / (uint32_t)spread;
   if (i >= n_warps) return;
   store_rw(warp_totals + i, fp_inv(load_rw(warp_totals + i)));
 }
@@ -384,12 +413,12 @@ k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict
 template <bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS, 4)
 k_aff_finish(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ out_counts,
-             const uint32_t* __restrict__ out_starts, uint32_t M, int G, uint32_t warp_base, const Fq* __restrict__ prefix,
+             const uint32_t* __restrict__ out_starts, uint32_t M, int G, int rec_q, const Fq* __restrict__ prefix,
              const uint2* __restrict__ slot_meta, const Fq* __restrict__ others, const Fq* __restrict__ warp_totals,
              Affine* __restrict__ out) {
   const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = warp_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
   if (base64 >= n_slots) return;
   const uint32_t base = (uint32_t)base64;
@@ -403,11 +432,11 @@ k_aff_finish(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, c
     const uint32_t e0 = sm.x, kind = sm.y;
     Affine r;
     if (kind == PK_ZERO) { r.x = Fq::zero(); r.y = Fq::zero(); }
-    else if (kind == PK_PASS1) r = aff_load_input<FIRST>(in, refs, e0);
-    else if (kind == PK_PASS2) r = aff_load_input<FIRST>(in, refs, e0 + 1u);
+    else if (kind == PK_PASS1) r = aff_load_input<FIRST>(in, refs, e0, rec_q);
+    else if (kind == PK_PASS2) r = aff_load_input<FIRST>(in, refs, e0 + 1u, rec_q);
     else {
-      const Affine p1 = aff_load_input<FIRST>(in, refs, e0);
-      const Affine p2 = aff_load_input<FIRST>(in, refs, e0 + 1u);
+      const Affine p1 = aff_load_input<FIRST>(in, refs, e0, rec_q);
+      const Affine p2 = aff_load_input<FIRST>(in, refs, e0 + 1u, rec_q);
       const Fq den = (kind == PK_ADD) ? (p2.x - p1.x) : p1.y.dbl();
       const Fq inv_den = inv * load_rw(prefix + s);
       inv = inv * den;
@@ -493,7 +522,7 @@ template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 3)  // 3 CTAs/SM: at most 168 registers per thread
 k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
              const uint32_t* __restrict__ starts, const uint32_t* __restrict__ poff, const uint2* __restrict__ work,
-             const Meta* __restrict__ meta, uint32_t split, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
+             const Meta* __restrict__ meta, uint32_t split, int rec_q, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
              uint32_t* __restrict__ live) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= meta->n_items) return;
@@ -511,7 +540,7 @@ k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sort
       p = load_ro(bases + first + e);
     } else {
       const uint32_t ref = __ldg(sorted + first + e);
-      p = load_ro(bases + (ref & 0x7FFFFFFFu));
+      p = load_ro(rec_at(bases, ref & 0x7FFFFFFFu, rec_q));
       if (ref >> 31) p.y = p.y.neg();
     }
     xyzz_madd(acc, p);
@@ -845,13 +874,13 @@ k_generate_points(size_t n, uint64_t first, Affine* __restrict__ out) {
 // c doublings per level in XYZZ, then one shared inversion (Montgomery's trick) back to affine.
 static constexpr int PRE_MAX_W = 26;
 __global__ void __launch_bounds__(64)
-k_precompute(const Affine* __restrict__ pts, size_t n, int c, int W, Affine* __restrict__ table) {
+k_precompute(const Affine* __restrict__ pts, size_t n, int c, int W, int rec_q, Affine* __restrict__ table) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Affine p = load_ro(pts + i);
-  store_rw(table + i, p);
+  store_rw(const_cast<Affine*>(rec_at(table, i, rec_q)), p);
   if (p.is_identity()) {
-    for (int w = 1; w < W; w++) store_rw(table + (size_t)w * n + i, p);
+    for (int w = 1; w < W; w++) store_rw(const_cast<Affine*>(rec_at(table, (size_t)w * n + i, rec_q)), p);
     return;
   }
   Fq xs[PRE_MAX_W], ys[PRE_MAX_W], zzs[PRE_MAX_W], zzzs[PRE_MAX_W], pref[PRE_MAX_W];
@@ -871,7 +900,7 @@ k_precompute(const Affine* __restrict__ pts, size_t n, int c, int W, Affine* __r
     Affine a;
     a.x = xs[w] * iz.sqr();
     a.y = ys[w] * izzz;
-    store_rw(table + (size_t)w * n + i, a);
+    store_rw(const_cast<Affine*>(rec_at(table, (size_t)w * n + i, rec_q)), a);
   }
 }
 
@@ -990,6 +1019,7 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   const Affine* d_bases = merged ? B.table : B.points + base_offset;
   const uint32_t ref_offset = merged ? (uint32_t)base_offset : 0u;
   const uint32_t ref_stride = merged ? (uint32_t)B.n : 0u;
+  const int rec_q = merged ? B.rec_q : 6;
   const size_t refs = (size_t)P.W * n;
 
   GM_TRY(S.digits.reserve(refs * 4));
@@ -1076,14 +1106,14 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
     Fq* totals = S.aff_totals.as<Fq>();
     const uint32_t* refs0 = r == 0 ? S.sorted.as<uint32_t>() : nullptr;
     if (r == 0)
-      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, 0u, prefix, smeta, others, totals);
+      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, rec_q, prefix, smeta, others, totals);
     else
-      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, 0u, prefix, smeta, others, totals);
-    LAUNCH(ctx, k_aff_invert, inv_ctas, inv_threads, 0, oc, os, M32, G, spread, 0u, shp.warps, totals);
+      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, rec_q, prefix, smeta, others, totals);
+    LAUNCH(ctx, k_aff_invert, inv_ctas, inv_threads, 0, oc, os, M32, G, spread, totals);
     if (r == 0)
-      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, 0u, prefix, smeta, others, totals, out);
+      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, rec_q, prefix, smeta, others, totals, out);
     else
-      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, 0u, prefix, smeta, others, totals, out);
+      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, rec_q, prefix, smeta, others, totals, out);
     cur_counts = oc; cur_starts = os; cur_pts = out;
   }
 
@@ -1093,10 +1123,10 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   const unsigned acc_ctas = (unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS);
   if (levels > 0)
     LAUNCH(ctx, k_accumulate<true>, acc_ctas, ACC_THREADS, 0, cur_pts, (const uint32_t*)nullptr, cur_counts, cur_starts, S.poff.as<uint32_t>(),
-           S.work.as<uint2>(), meta, split, buckets, S.partials.as<XYZZ>(), live);
+           S.work.as<uint2>(), meta, split, rec_q, buckets, S.partials.as<XYZZ>(), live);
   else
     LAUNCH(ctx, k_accumulate<false>, acc_ctas, ACC_THREADS, 0, d_bases, S.sorted.as<uint32_t>(), cur_counts, cur_starts, S.poff.as<uint32_t>(),
-           S.work.as<uint2>(), meta, split, buckets, S.partials.as<XYZZ>(), live);
+           S.work.as<uint2>(), meta, split, rec_q, buckets, S.partials.as<XYZZ>(), live);
   GM_CUDA(cudaEventRecord(ctx->ev[4], st));
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
@@ -1182,10 +1212,10 @@ int msm_stream_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* d_buckets, cons
   return msm_reduce(ctx, P, d_buckets, d_live, d_acc);
 }
 
-int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, Affine* d_table) {
+int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, int rec_q, Affine* d_table) {
   if (n == 0) return GM_OK;
   if (W > PRE_MAX_W) { set_error("precompute: too many windows (%d)", W); return GM_ERR_ARG; }
-  LAUNCH(ctx, k_precompute, (unsigned)((n + 63) / 64), 64, 0, d_points, n, c, W, d_table);
+  LAUNCH(ctx, k_precompute, (unsigned)((n + 63) / 64), 64, 0, d_points, n, c, W, rec_q, d_table);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

@@ -22,6 +22,7 @@ struct MsmBases {
   const Affine* table = nullptr;
   size_t n = 0;  // points per table level
   int c = 0, W = 0;
+  int rec_q = 6;  // 16-byte quads per table record: 6 = packed 96 B, 8 = padded to one 128-byte line
 };
 
 // *d_acc (XYZZ, device) += sum_i scalars[i] * bases[i]; asynchronous on ctx->stream
@@ -33,7 +34,7 @@ size_t msm_plan_buckets(const MsmPlan& P);
 int msm_stream_push(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint,
                     const MsmPlan& P, XYZZ* d_buckets, uint32_t* d_live);
 int msm_stream_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* d_buckets, const uint32_t* d_live, XYZZ* d_acc);
-int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, Affine* d_table);
+int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, int rec_q, Affine* d_table);
 int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);
 int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out);
