@@ -104,19 +104,25 @@ class ShardedTimeProver:
         self.group, self.device = group, device
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.start, self.B, self.L = sumcheck_block(n_f, n_g, self.rank, self.world)
-        if len(f_block) > self.B or len(g_block) > self.B:
-            raise ValueError("block longer than 2^L / world")
         self.make_local = make_local
         self.twist0 = twist % self.R
         self._round = 0
         self.local_rounds = _ark_log2(self.B)
         self.scales = [pow(self.twist0, r * self.B, self.R) for r in range(self.world)]
-        f_block = list(f_block) + [0] * (self.B - len(f_block))
-        g_block = list(g_block) + [0] * (self.B - len(g_block))
-        self.local = make_local(f_block, g_block, self.twist0)
+        self.local = make_local(self._pad(f_block), self._pad(g_block), self.twist0)
         self.tail = None
         if self.local_rounds == 0:
             self._start_tail()
+
+    def _pad(self, block):
+        """host blocks are zero-padded to B here; device-resident blocks (DeviceFr) must already hold B elements"""
+        if hasattr(block, "ptr") and hasattr(block, "n"):
+            if block.n != self.B:
+                raise ValueError("a device-resident block must hold exactly 2^L / world elements (zero-pad it on the device)")
+            return block
+        if len(block) > self.B:
+            raise ValueError("block longer than 2^L / world")
+        return list(block) + [0] * (self.B - len(block))
 
     # -- the two exchanges ------------------------------------------------------------------------
     def _combine(self, msg: Tuple[int, int]) -> Tuple[int, int]:
