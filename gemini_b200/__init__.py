@@ -13,7 +13,9 @@ from . import field  # noqa: F401
 from .msm import VariableBaseMSM, ChunkedPippenger, HashMapPippenger, msm_chunks  # noqa: F401
 from .kzg import CommitterKey, CommitterKeyStream  # noqa: F401
 from .sumcheck import TimeProver, HerringTimeProver, SpaceProver, ElasticProver, Sumcheck, fold_polynomial  # noqa: F401
-from .tensorcheck import foldings_polynomial  # noqa: F401
+from .tensorcheck import (foldings_polynomial, FoldedPolynomialTree, evaluate_folding, transcribe_foldings,  # noqa: F401
+                          partially_foldtree)
+from . import dist  # noqa: F401
 from .devvec import DeviceFr, DeviceCsr  # noqa: F401
 from .transcript import MerlinTranscript  # noqa: F401
 from . import snark  # noqa: F401
@@ -21,5 +23,6 @@ from . import snark  # noqa: F401
 __all__ = [
     "Context", "Srs", "GeminiError", "VariableBaseMSM", "ChunkedPippenger", "HashMapPippenger", "msm_chunks",
     "CommitterKey", "CommitterKeyStream", "TimeProver", "HerringTimeProver", "SpaceProver", "ElasticProver",
-    "Sumcheck", "fold_polynomial", "foldings_polynomial", "field", "DeviceFr", "DeviceCsr", "MerlinTranscript", "snark",
+    "Sumcheck", "fold_polynomial", "foldings_polynomial", "FoldedPolynomialTree", "evaluate_folding", "transcribe_foldings",
+    "partially_foldtree", "dist", "field", "DeviceFr", "DeviceCsr", "MerlinTranscript", "snark",
 ]

@@ -223,3 +223,49 @@ class CommitterKeyStream:
             st.push_range(len(self) - m, np.ascontiguousarray(lvl[::-1]))
             out.append(st.finalize())
         return out
+
+    def open_folding(self, polynomials, points: Sequence[int], etas: Sequence[int], max_msm_buffer: int = 0):
+        """space.rs:229-285 -> (remainders per level, evaluation proof).  ``polynomials``: tensorcheck.FoldedPolynomialTree.
+
+        The reference streams every level through a division by the vanishing polynomial of ``points`` and feeds
+        eta_i * quotient coefficients into one HashMapPippenger (all levels pair the coefficient of degree d with the
+        same base g^(tau^d), so the map merges them).  Here: k synthetic divisions per level on the device
+        (k = len(points)), the eta-combination of the quotients as one resident vector, ONE MSM."""
+        from .devvec import DeviceFr
+
+        ctx = self.ctx
+        pts = [p % R for p in points]
+        k = len(pts)
+        remainders, batched = [], None
+        for i, lvl in enumerate(polynomials.levels):
+            q, cs = lvl, []
+            for a in pts:
+                if q.n == 0:
+                    cs.append(0)
+                    continue
+                q, c = q.div_linear(a)
+                cs.append(c)
+            # remainder in Newton form c_1 + c_2 (X - a_1) + c_3 (X - a_1)(X - a_2) ... -> monomial coefficients
+            rem = [0] * k
+            basis = [1]
+            for j, c in enumerate(cs):
+                for d, b in enumerate(basis):
+                    rem[d] = (rem[d] + c * b) % R
+                if j + 1 < k:
+                    nb = [0] * (len(basis) + 1)
+                    for d, b in enumerate(basis):
+                        nb[d + 1] = (nb[d + 1] + b) % R
+                        nb[d] = (nb[d] - pts[j] * b) % R
+                    basis = nb
+            remainders.append(rem[::-1])                      # deque order of the reference: highest degree first
+            if q.n:
+                if batched is None:
+                    batched = DeviceFr.zeros(ctx, max(l.n for l in polynomials.levels))
+                batched.axpy(etas[i] % R, q)
+        if batched is None:
+            return remainders, None
+        m = batched.n
+        st = _DeviceStream(ctx, self.srs_be, m)
+        st.push_range(len(self) - m, np.ascontiguousarray(batched.limbs()[::-1]))
+        return remainders, st.finalize()
+

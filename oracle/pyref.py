@@ -835,6 +835,33 @@ def kzg_commit_folding(powers_of_g_be, coeffs_be, challenges, max_msm_buffer: in
     return [p.finalize() for p in pips]
 
 
+def kzg_open_folding(powers_of_g_be, coeffs_be, challenges, points, etas, max_msm_buffer: int):
+    """CommitterKeyStream::open_folding, kzg/space.rs:229-285: one pass over the FoldedPolynomialTree; per fold level a
+    streaming division by the vanishing polynomial of ``points``; every quotient coefficient, scaled by the level's
+    eta, goes into ONE HashMapPippenger.  Returns (remainders per level in deque order, evaluation proof)."""
+    n = len(challenges)
+    pip = HashMapPippenger(max_msm_buffer)
+    zeros = vanishing_polynomial(points)
+    deg = len(zeros) - 1
+    remainders = [deque() for _ in range(n)]
+    folded_bases = []
+    for i in range(1, n + 1):
+        delta = len(powers_of_g_be) - folded_stream_len(len(coeffs_be), i)
+        folded_bases.append(iter(powers_of_g_be[delta:]))
+        for _ in range(len(points)):
+            remainders[i - 1].append(0)
+    for i, coefficient in folded_polynomial_tree(coeffs_be, challenges):
+        if i == 0:
+            continue
+        base = next(folded_bases[i - 1])
+        qc = remainders[i - 1].popleft()
+        remainders[i - 1].append(coefficient % R)
+        for j in range(len(points)):
+            remainders[i - 1][j] = (remainders[i - 1][j] - zeros[deg - j - 1] * qc) % R
+        pip.add(base, etas[i - 1] * qc % R)
+    return [list(r) for r in remainders], pip.finalize()
+
+
 def evaluate_folding(coeffs_be, challenges, x: int) -> List[int]:
     """tensorcheck/mod.rs:73-88."""
     result = [0] * len(challenges)

@@ -56,3 +56,37 @@ def test_fold_large_property(ctx):
     # evaluation identity: sum_i out[i] x^i == f_even(x) + r f_odd(x) at x = 1
     tot = sum(limbs_to_ints(out)) * rinv % R
     assert tot == (sum(f[0::2]) + r * sum(f[1::2])) * rinv % R
+
+
+def test_folded_polynomial_tree_consumers(ctx):
+    """Elastic tensorcheck pieces: the device-resident FoldedPolynomialTree against the stack-machine
+    restatement - stream order, evaluate_folding, transcribe_foldings / partially_foldtree, open_folding."""
+    import random
+
+    from gemini_b200 import kzg, tensorcheck
+    from util import rand_points
+
+    rng = random.Random(5)
+    for n, depth in ((37, 4), (64, 6), (5, 3), (1000, 7)):
+        f_be = [rng.randrange(o.R) for _ in range(n)]
+        ch = [rng.randrange(o.R) for _ in range(depth)]
+        tree = tensorcheck.FoldedPolynomialTree(ctx, f_be, ch)
+        assert tree.depth() == depth and len(tree) == n
+        assert list(tree.iter()) == list(o.folded_polynomial_tree(f_be, ch))
+        x = rng.randrange(o.R)
+        assert tensorcheck.evaluate_folding(tree, x) == o.evaluate_folding(f_be, ch, x)
+        want_levels = o.foldings_polynomial(f_be[::-1], ch + [0])
+        assert tensorcheck.transcribe_foldings(tree, 1) == want_levels[1:]
+        partial, transcribed = tensorcheck.partially_foldtree(ctx, f_be, ch)
+        assert partial.depth() == depth and transcribed == []      # depth <= SPACE_TIME_THRESHOLD: nothing transcribed
+        # open_folding: remainders and the batched evaluation proof
+        srs_le = rand_points(n + 2, 77)
+        cks = kzg.CommitterKeyStream(ctx, srs_le[::-1])
+        points = [rng.randrange(o.R) for _ in range(3)]
+        etas = [rng.randrange(o.R) for _ in range(depth)]
+        rem, proof = cks.open_folding(tree, points, etas, 1 << 10)
+        want_rem, want_proof = o.kzg_open_folding(srs_le[::-1], f_be, ch, points, etas, 1 << 10)
+        assert rem == want_rem
+        assert proof == want_proof
+        # and the commitments of the same tree (commit_folding) for good measure
+        assert cks.commit_folding(f_be, ch, 1 << 10) == o.kzg_commit_folding(srs_le[::-1], f_be, ch, 1 << 10)

@@ -133,3 +133,36 @@ def test_kzg_time_equals_space():
     ch = rs(3, 12)
     folds = o.foldings_polynomial(poly, ch + [0])
     assert o.kzg_commit_folding(srs[::-1], poly[::-1], ch, 20) == [o.kzg_commit(srs, f) for f in folds]
+
+
+def test_open_folding_restatement_matches_time_side_algebra():
+    """kzg/space.rs:229-285 (streaming, HashMapPippenger) against the textbook statement: per fold level the quotient and
+    remainder of f^(i) by the vanishing polynomial; proof = sum_i eta_i * commit(quotient_i)."""
+    import random
+
+    from util import rand_points
+
+    rng = random.Random(99)
+    for n, depth, npts in ((37, 4, 3), (16, 4, 3), (5, 3, 3), (9, 2, 1)):
+        coeffs_le = [rng.randrange(o.R) for _ in range(n)]
+        challenges = [rng.randrange(o.R) for _ in range(depth)]
+        points = [rng.randrange(o.R) for _ in range(npts)]
+        etas = [rng.randrange(o.R) for _ in range(depth)]
+        srs_le = rand_points(n + 3, 123)
+        rem, proof = o.kzg_open_folding(srs_le[::-1], coeffs_le[::-1], challenges, points, etas, 1 << 10)
+        z = o.vanishing_polynomial(points)
+        want_proof = None
+        f = coeffs_le
+        for i in range(depth):
+            f = o.fold_polynomial(f, challenges[i])
+            q = o.poly_div(f, z)
+            # remainder = f - q z
+            qz = [0] * max(len(f), len(q) + len(z) - 1 if q else 0)
+            for a, qa in enumerate(q):
+                for b, zb in enumerate(z):
+                    qz[a + b] = (qz[a + b] + qa * zb) % o.R
+            r = [(f[d] - (qz[d] if d < len(qz) else 0)) % o.R if d < len(f) else 0 for d in range(npts)]
+            assert rem[i] == r[::-1], (n, i)
+            if q:
+                want_proof = o.g1_add(want_proof, o.g1_mul(o.naive_msm(srs_le, q), etas[i]))
+        assert proof == want_proof
