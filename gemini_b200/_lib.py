@@ -45,6 +45,7 @@ SIGNATURES = {
     "gm_l2_flush": (_i, [_vp]),
     "gm_srs_load_g1": (_i, [_vp, _vp, _sz, _sz, _l, _pp]),
     "gm_srs_generate_g1": (_i, [_vp, _sz, _u64, _pp]),
+    "gm_srs_setup_g1": (_i, [_vp, _vp, _vp, _sz, _pp]),
     "gm_srs_fill_g1": (_i, [_vp, _vp, _sz, _pp]),
     "gm_srs_precompute": (_i, [_vp, _vp, _sz]),
     "gm_srs_precompute_info": (_i, [_vp, _pi, _pi]),

@@ -137,6 +137,14 @@ class Context:
         check(lib.gm_srs_generate_g1(self._h, n, first_multiple, C.byref(h)))
         return Srs(self, h.value)
 
+    def srs_setup(self, g, tau: int, n: int) -> Srs:
+        """powers_of_g[i] = tau^i * g, i < n (CommitterKey::new, kzg/time.rs:49-72), computed on the device."""
+        garr = field.g1_to_limbs([g])
+        tarr = field.fr_to_limbs([tau])
+        h = C.c_void_p()
+        check(lib.gm_srs_setup_g1(self._h, _ptr(garr), _ptr(tarr), n, C.byref(h)))
+        return Srs(self, h.value)
+
     def srs_fill(self, point, n: int) -> Srs:
         arr = field.g1_to_limbs([point])
         h = C.c_void_p()

@@ -258,6 +258,32 @@ int gm_srs_generate_g1(gm_ctx* ctx, size_t n, uint64_t first_multiple, gm_srs** 
   return GM_OK;
 }
 
+int gm_srs_setup_g1(gm_ctx* ctx, const uint64_t g_xy[12], const uint64_t tau[4], size_t n, gm_srs** out_srs) {
+  GM_ARG(ctx && out_srs && g_xy && tau, "NULL argument");
+  GM_TRY(set_device(ctx));
+  gm_srs* s = nullptr;
+  GM_TRY(srs_alloc(ctx, n, &s));
+  Affine g;
+  memcpy(&g, g_xy, 96);
+  Fr t;
+  memcpy(t.v, tau, 32);
+  void* d_pow = nullptr;
+  cudaError_t e = cudaMalloc(&d_pow, std::max<size_t>(n, 1) * 32);
+  int rc = GM_OK;
+  if (e != cudaSuccess) { set_error("srs setup: cudaMalloc failed: %s", cudaGetErrorString(e)); rc = GM_ERR_OOM; }
+  if (rc == GM_OK) rc = fr_powers_dev(ctx, t, n, reinterpret_cast<Fr*>(d_pow));          // misc::powers(tau, n)
+  if (rc == GM_OK) rc = srs_fixed_base(ctx, g, reinterpret_cast<const uint32_t*>(d_pow), n, reinterpret_cast<Affine*>(s->d_points));
+  e = cudaStreamSynchronize(ctx->stream);
+  if (d_pow) cudaFree(d_pow);
+  if (rc != GM_OK || e != cudaSuccess) {
+    if (rc == GM_OK) { set_error("srs setup: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+    gm_srs_free(s);
+    return rc;
+  }
+  *out_srs = s;
+  return GM_OK;
+}
+
 int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** out_srs) {
   GM_ARG(ctx && out_srs && point_xy, "NULL argument");
   GM_TRY(set_device(ctx));

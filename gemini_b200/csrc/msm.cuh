@@ -42,5 +42,6 @@ int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out);
 int srs_pack(gm_ctx* ctx, const uint8_t* d_raw, size_t n, size_t stride, long inf_offset, Affine* d_out);
 int srs_fill(gm_ctx* ctx, const Affine& p, size_t n, Affine* d_out);
 int srs_generate(gm_ctx* ctx, size_t n, uint64_t first, Affine* d_out);
+int srs_fixed_base(gm_ctx* ctx, const Affine& g, const uint32_t* d_scalars, size_t n, Affine* d_out);
 
 }  // namespace gm

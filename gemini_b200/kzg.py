@@ -75,6 +75,20 @@ class CommitterKey:
         self.srs = powers_of_g if isinstance(powers_of_g, Srs) else ctx.srs_load(powers_of_g)
         self._msm = VariableBaseMSM(ctx)
 
+    @classmethod
+    def new(cls, ctx: Context, max_degree: int, max_eval_points: int, rng, precompute: bool = False) -> "CommitterKey":
+        """``CommitterKey::new`` (time.rs:49-72), G1 half: tau and g are drawn from ``rng`` (``rng.randrange``), then
+        powers_of_g[i] = tau^i * g for i <= max_degree by the device fixed-base MSM.  powers_of_g2 (``max_eval_points``
+        G2 elements, used by the verifier only) is outside this path; tau and g are kept for tests."""
+        tau = rng.randrange(1, R)
+        k = rng.randrange(1, R)
+        g = ctx.srs_generate(1, first_multiple=k & ((1 << 64) - 1) or 1).points()[0]     # a random-looking G1 element
+        ck = cls(ctx, ctx.srs_setup(g, tau, max_degree + 1))
+        ck.tau, ck.g, ck.max_eval_points = tau, g, max_eval_points
+        if precompute:
+            ck.srs.precompute()
+        return ck
+
     def max_degree(self) -> int:
         return len(self.srs) - 1
 

@@ -67,6 +67,10 @@ int gm_srs_load_g1(gm_ctx* ctx, const void* points, size_t n, size_t stride_byte
                    gm_srs** out_srs);
 /* synthetic bases P_i = [first_multiple + i] * G generated on the device (bench / tests) */
 int gm_srs_generate_g1(gm_ctx* ctx, size_t n, uint64_t first_multiple, gm_srs** out_srs);
+/* CommitterKey::new, src/kzg/time.rs:49-72 (G1 half): powers_of_g[i] = tau^i * g for i < n - misc::powers, the
+ * fixed-base MSM of ark-ec (FixedBase::get_window_table / FixedBase::msm) and normalize_batch, all on the device.
+ * g_xy: affine generator (Montgomery x|y); tau: Montgomery Fr.  powers_of_g2 (G2) is outside this path. */
+int gm_srs_setup_g1(gm_ctx* ctx, const uint64_t g_xy[12], const uint64_t tau[4], size_t n, gm_srs** out_srs);
 /* n copies of one point: DummyStreamer(G1::generator(), n), examples/snark.rs:62-65 */
 int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** out_srs);
 /* Optional, one-time (key setup, like CommitterKey::new): store 2^(c*w) * P_i for every window w next to

@@ -174,3 +174,27 @@ def test_precompute_closed_form_large(ctx, logn):
     m = min(n, 1 << 15)
     tot_m = sum(v * (i + 1) for i, v in enumerate(limbs_to_ints(limbs[:m]))) % R * rinv % R
     assert st.finalize() == o.g1_mul(o.G1_GEN, tot_m)
+
+
+def test_committer_key_new_fixed_base_setup(ctx):
+    """CommitterKey::new (kzg/time.rs:49-72): powers_of_g[i] = tau^i g by the device fixed-base MSM."""
+    import random
+
+    rng = random.Random(31)
+    g = o.g1_mul(o.G1_GEN, rng.randrange(1, R))
+    for tau in (rng.randrange(1, R), 1, R - 1, 2):
+        n = 37
+        pts = ctx.srs_setup(g, tau, n).points()
+        assert pts == [o.g1_mul(g, pow(tau, i, R)) for i in range(n)]
+    assert ctx.srs_setup(g, 0, 3).points() == [g, None, None]
+    # size-independent property at 2^18: commit(f) against the generated key is [f(tau)] g
+    ck = gm.CommitterKey.new(ctx, (1 << 18) - 1, 3, random.Random(5))
+    assert ck.max_degree() == (1 << 18) - 1
+    limbs = fr_random_limbs(1 << 18, seed=9)
+    rinv = pow(1 << 256, -1, R)
+    acc = 0
+    for v in reversed(limbs_to_ints(limbs)):
+        acc = (acc * ck.tau + v * rinv) % R
+    assert field.jacobian_to_affine(ctx.msm(ck.srs, limbs)) == o.g1_mul(ck.g, acc)
+    sample = ck.srs.points(12345, 2)
+    assert sample == [o.g1_mul(ck.g, pow(ck.tau, 12345, R)), o.g1_mul(ck.g, pow(ck.tau, 12346, R))]
