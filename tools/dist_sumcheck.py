@@ -31,6 +31,8 @@ def main():
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    for k, v in (("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29633"), ("RANK", "0"), ("WORLD_SIZE", "1")):
+        os.environ.setdefault(k, v)      # plain `python tools/dist_sumcheck.py` = one rank
     dist.init_process_group("nccl" if world > 1 else "gloo", device_id=torch.device("cuda", local) if world > 1 else None)
     dev = f"cuda:{local}" if world > 1 else None
     ctx = gm.Context(local)
