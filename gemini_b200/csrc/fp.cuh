@@ -245,8 +245,58 @@ struct Fp {
   }
 };
 
+// ---------------------------------------------------------------------------
+// Lazy reduction for sums of products (the inner products of the sumcheck messages, like ark-ff's sum_of_products
+// behind misc::ip_unsafe): acc += a*b keeps the full 2N-limb product and only folds the TOP half back below p (one
+// N-limb conditional subtraction), so a product costs N^2 IMAD.WIDE instead of the 2 N^2 of a Montgomery product;
+// one Montgomery reduction at the very end.  Invariant: acc < p * 2^(32N)  (top half < p).  Needs 2 bits of slack
+// in the top limb of p (a*b < p^2 < p 2^(32N) / 4 ... true for Fr: r < 2^255).
+// ---------------------------------------------------------------------------
+template <class P>
+struct FpAcc {
+  static constexpr int N = P::N;
+  uint32_t v[2 * N];
+
+  GM_HD static FpAcc zero() {
+    FpAcc r;
+#pragma unroll
+    for (int j = 0; j < 2 * N; j++) r.v[j] = 0;
+    return r;
+  }
+  // acc += a * b   (a, b < p)
+  GM_HD void mul_add(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) {
+      // column k: previous limb of the accumulator plus all a[i] * b[k - i]
+      c0 = add_cc(c0, v[k]);
+      c1 = addc_cc(c1, 0);
+      c2 = addc(c2, 0);
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int j = k - i;
+        if (j >= 0 && j < N) mad_acc3(c0, c1, c2, a.v[i], b.v[j]);
+      }
+      v[k] = c0;
+      c0 = c1; c1 = c2; c2 = 0;
+    }
+    // acc < p 2^(32N) + p^2 < 2 p 2^(32N): one conditional subtraction of p from the top half restores the invariant
+    detail::cond_sub_p<P>(v + N, v + N);
+  }
+  // (acc / 2^(32N)) mod p as a field element: top half + REDC(bottom half)
+  GM_HD Fp<P> reduce() const {
+    Fp<P> lo, hi, one;
+#pragma unroll
+    for (int j = 0; j < N; j++) { lo.v[j] = v[j]; hi.v[j] = v[N + j]; one.v[j] = (j == 0) ? 1u : 0u; }
+    Fp<P> t;
+    mont_mul<P>(t.v, one.v, lo.v);   // lo may exceed p: it is the row operand (a < p, b < R is all CIOS needs)
+    return hi + t;
+  }
+};
+
 using Fq = Fp<FqParams>;
 using Fr = Fp<FrParams>;
+using FrAcc = FpAcc<FrParams>;
 
 // ---------------------------------------------------------------------------
 // Inversion.  fp_inv_fermat: a^(p-2), ~570 Montgomery products.  fp_inv: Kaliski's "almost Montgomery

@@ -127,8 +127,31 @@ __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, 
   }
 }
 
+// GM_LAZY_SUMCHECK (off): accumulate the sums with lazy reduction (FrAcc, fp.cuh) - the last product of every term
+// keeps its full 512 bits and the Montgomery reduction is paid once per thread, not once per term.  The accumulator
+// is validated on the host (tests/test_host_field.py::test_lazy_sum_of_products) and compiles to fused IMAD.WIDE, but
+// the GPU budget of round 1 ran out before the parity suite could be run with it, so the shipped kernels keep the
+// plain Montgomery accumulation that the parity tests have seen.
+#ifdef GM_LAZY_SUMCHECK
+using ScAcc = FrAcc;
+__device__ __forceinline__ Fr sc_acc_value(const ScAcc& a) { return a.reduce(); }
 template <bool TW>
-__device__ __forceinline__ void pair_contrib(Fr& a, Fr& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
+__device__ __forceinline__ void pair_contrib(ScAcc& a, ScAcc& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
+                                             const Fr& twist, const Fr& t) {
+  if (TW) {
+    a.mul_add(fe * ge, t);
+    b.mul_add(fe * go + (ge * fo) * twist, t);
+  } else {
+    a.mul_add(fe, ge);
+    b.mul_add(fe, go);
+    b.mul_add(ge, fo);
+  }
+}
+#else
+using ScAcc = Fr;
+__device__ __forceinline__ Fr sc_acc_value(const ScAcc& a) { return a; }
+template <bool TW>
+__device__ __forceinline__ void pair_contrib(ScAcc& a, ScAcc& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
                                              const Fr& twist, const Fr& t) {
   if (TW) {
     a = a + (fe * ge) * t;
@@ -138,6 +161,7 @@ __device__ __forceinline__ void pair_contrib(Fr& a, Fr& b, const Fr& fe, const F
     b = b + (fe * go + ge * fo);
   }
 }
+#endif
 
 template <bool TW>
 __global__ void __launch_bounds__(SC_THREADS)
@@ -145,7 +169,7 @@ k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size
              Fr* partials, unsigned int* ticket, Fr* out) {
   const size_t npairs = min((nf + 1) / 2, (ng + 1) / 2);
   const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
-  Fr a = Fr::zero(), b = Fr::zero();
+  ScAcc a = ScAcc::zero(), b = ScAcc::zero();
   Fr t = Fr::one(), step = Fr::one();
   if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }  // (twist^2)^SC_THREADS
 #pragma unroll 1
@@ -157,7 +181,7 @@ k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size
     pair_contrib<TW>(a, b, fe, fo, ge, go, twist, t);
     if (TW) t = t * step;
   }
-  sc_reduce_and_publish(a, b, partials, ticket, out);
+  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
 }
 
 // fold by (rf, rg) and message of the folded vectors with the squared twist `twist` (already squared
@@ -170,7 +194,7 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
   const size_t npairs = max((nf2 + 1) / 2, (ng2 + 1) / 2);  // every element must be folded
   const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
-  Fr a = Fr::zero(), b = Fr::zero();
+  ScAcc a = ScAcc::zero(), b = ScAcc::zero();
   Fr t = Fr::one(), step = Fr::one();
   if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }
 #pragma unroll 1
@@ -192,7 +216,7 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
     pair_contrib<TW>(a, b, fe, fo, ge, go, twist, t);
     if (TW) t = t * step;
   }
-  sc_reduce_and_publish(a, b, partials, ticket, out);
+  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
 }
 
 // splitmix64 counter stream -> Fr elements (the 255-bit value, minus r if needed, is used directly as

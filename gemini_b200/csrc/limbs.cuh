@@ -78,6 +78,11 @@ GM_D void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint3
 GM_D void madc_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
+// three-word column accumulator (c0, c1, c2) += a*b   (product scanning; IMAD.WIDE + IADD3.X in SASS)
+GM_D void mad_acc3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
+               : "+r"(c0), "+r"(c1), "+r"(c2) : "r"(a), "r"(b));
+}
 
 #else  // host emulation of the PTX carry flag ------------------------------
 
@@ -119,6 +124,12 @@ inline void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uin
 }
 inline void madc_wide_top(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint32_t l = madc_lo_cc(a, b, 0); uint32_t h = madc_hi(a, b, 0); lo = l; hi = h;
+}
+inline void mad_acc3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t a, uint32_t b) {
+  const uint64_t p = (uint64_t)a * b;
+  const uint64_t t0 = (uint64_t)c0 + (uint32_t)p;
+  const uint64_t t1 = (uint64_t)c1 + (uint32_t)(p >> 32) + (t0 >> 32);
+  c0 = (uint32_t)t0; c1 = (uint32_t)t1; c2 += (uint32_t)(t1 >> 32);
 }
 
 #endif

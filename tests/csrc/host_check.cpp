@@ -93,4 +93,14 @@ void hc_aff_batch(const uint32_t* p1, const uint32_t* p2, const int* has2, int n
   }
   delete[] prefix;
 }
+// lazy-reduction accumulator: out = sum_i a_i * b_i (Montgomery form), n pairs of 8 u32
+void hc_fr_sum_of_products(const uint32_t* a, const uint32_t* b, int n, uint32_t* out) {
+  FrAcc acc = FrAcc::zero();
+  for (int i = 0; i < n; i++) {
+    Fr x, y; memcpy(x.v, a + 8 * i, 32); memcpy(y.v, b + 8 * i, 32);
+    acc.mul_add(x, y);
+  }
+  Fr r = acc.reduce();
+  memcpy(out, r.v, 32);
+}
 }

@@ -139,3 +139,28 @@ def test_affine_pair_batch_shared_inversion(hc):
         got = None if (x, y) == (0, 0) else (x, y)
         assert got == want, (i, int(kinds[i]))
     assert set(int(k) for k in kinds) == {0, 1, 2, 3, 4}
+
+
+def test_lazy_sum_of_products(hc):
+    """FpAcc (fp.cuh): full 512-bit products accumulated with a conditional subtraction of the top half and ONE
+    Montgomery reduction at the end - the schedule behind the sumcheck message sums."""
+    rng = random.Random(11)
+    p, n32 = o.R, 8
+    Rm = (1 << 256) % p
+    Ri = pow(Rm, -1, p)
+    for n in (1, 2, 7, 300):
+        A = [rng.randrange(p) for _ in range(n)]
+        B = [rng.randrange(p) for _ in range(n)]
+        if n == 7:
+            A[:4] = [p - 1, p - 1, 0, 1]
+            B[:4] = [p - 1, p - 2, p - 1, p - 1]
+        a, b = pack(A, n32), pack(B, n32)
+        out = np.zeros((1, n32), dtype=np.uint32)
+        hc.hc_fr_sum_of_products(P(a), P(b), n, P(out))
+        assert unpack(out)[0] == sum(x * y for x, y in zip(A, B)) * Ri % p
+    # worst case for the invariant: many maximal products
+    A = [p - 1] * 64
+    a = pack(A, n32)
+    out = np.zeros((1, n32), dtype=np.uint32)
+    hc.hc_fr_sum_of_products(P(a), P(a), 64, P(out))
+    assert unpack(out)[0] == 64 * (p - 1) * (p - 1) * Ri % p
