@@ -5,6 +5,7 @@
 #include "../../gemini_b200/csrc/g1.cuh"
 #include "../../gemini_b200/csrc/g1_affine.cuh"
 #include "../../gemini_b200/csrc/fq_f64.cuh"
+#include "../../gemini_b200/csrc/fp_inv_fast.cuh"
 #include <string.h>
 using namespace gm;
 
@@ -20,6 +21,7 @@ template <class F> static void f_mul(F& z, const F& x, const F& y) { z = x * y; 
 template <class F> static void f_add(F& z, const F& x, const F& y) { z = x + y; }
 template <class F> static void f_sub(F& z, const F& x, const F& y) { z = x - y; }
 template <class F> static void f_inv(F& z, const F& x, const F&) { z = fp_inv(x); }
+template <class F> static void f_inv_fast(F& z, const F& x, const F&) { z = fp_inv_divsteps(x); }
 template <class F> static void f_redc(F& z, const F& x, const F&) { z = x.from_mont(); }
 template <class F> static void f_tom(F& z, const F& x, const F&) { z = x.to_mont(); }
 template <class F> static void f_sqr(F& z, const F& x, const F&) { z = x.sqr(); }
@@ -27,11 +29,11 @@ static void f_mul_f64(Fq& z, const Fq& x, const Fq& y) { f64::fq_mul_f64(z.v, x.
 
 extern "C" {
 void hc_fq(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
-  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64};
+  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64, f_inv_fast<Fq>};
   bin<Fq>(ops[op], a, b, r, n);
 }
 void hc_fr(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
-  void (*ops[])(Fr&, const Fr&, const Fr&) = {f_mul<Fr>, f_add<Fr>, f_sub<Fr>, f_inv<Fr>, f_redc<Fr>, f_tom<Fr>, f_sqr<Fr>};
+  void (*ops[])(Fr&, const Fr&, const Fr&) = {f_mul<Fr>, f_add<Fr>, f_sub<Fr>, f_inv<Fr>, f_redc<Fr>, f_tom<Fr>, f_sqr<Fr>, f_sqr<Fr>, f_inv_fast<Fr>};
   bin<Fr>(ops[op], a, b, r, n);
 }
 // XYZZ accumulator (48 u32) (+)= affine point (24 u32, (0,0) = identity), optionally negated

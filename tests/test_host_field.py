@@ -164,3 +164,22 @@ def test_lazy_sum_of_products(hc):
     out = np.zeros((1, n32), dtype=np.uint32)
     hc.hc_fr_sum_of_products(P(a), P(a), 64, P(out))
     assert unpack(out)[0] == 64 * (p - 1) * (p - 1) * Ri % p
+
+
+@pytest.mark.parametrize("name,p,n", [("hc_fq", o.Q, 12), ("hc_fr", o.R, 8)])
+def test_fast_inverse_divsteps(hc, name, p, n):
+    """fp_inv_fast.cuh (staged for round 2): batched division steps, 30-bit limbs, against Python's pow(x, -1, p) and
+    against the Kaliski inverse that the kernels use today."""
+    fn = getattr(hc, name)
+    rng = random.Random(21)
+    Rm = (1 << (32 * n)) % p
+    Ri = pow(Rm, -1, p)
+    A = [1, 2, 3, p - 1, p - 2, Rm, (p - 1) // 2, (p + 1) // 2, (1 << (32 * n - 3)) % p, 1 << 29, 1 << 30, (1 << 30) - 1, 1 << 31]
+    A += [rng.randrange(1, p) for _ in range(600)] + [rng.randrange(1, 1 << 64) for _ in range(50)] + [p - rng.randrange(1, 1 << 40) for _ in range(50)]
+    a = pack(A, n)
+    fast, slow = np.zeros_like(a), np.zeros_like(a)
+    fn(8, P(a), P(a), P(fast), len(A))
+    fn(3, P(a), P(a), P(slow), len(A))
+    want = [pow(x * Ri % p, -1, p) * Rm % p for x in A]
+    assert unpack(slow) == want
+    assert unpack(fast) == want
