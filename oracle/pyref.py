@@ -871,6 +871,52 @@ def evaluate_folding(coeffs_be, challenges, x: int) -> List[int]:
 
 
 # --------------------------------------------------------------------------
+# Streaming adaptors either side of the streamed MSM: restated so that the device versions of
+# round 2 have an oracle; pinned by the reference's own tests (tests/test_oracle_kats.py)
+# --------------------------------------------------------------------------
+EOL = None  # MatrixElement::EOL; an element is the pair (value, index)
+
+
+def diagonal_matrix_stream(r: int, n: int):
+    """iterable/dummy.rs DiagonalMatrixStreamer: column-major, HIGHEST index first, one EOL per column."""
+    for i in reversed(range(n)):
+        yield (r % R, i)
+        yield EOL
+
+
+def matrix_tensor_stream(matrix_stream, v: Sequence[int]) -> Iterator[int]:
+    """MatrixTensorIter, snark/streams.rs:60-102: per column (up to EOL) sum value * tensor(v)[index]; the reference
+    selects the factors of tensor(v)[index] from 16-bit partial tensors (expand_tensor), which is the same product."""
+    result = 0
+    for e in matrix_stream:
+        if e is EOL:
+            yield result
+            result = 0
+            continue
+        value, index = e
+        if value % R:
+            for j, rho in enumerate(v):
+                if (index >> j) & 1:
+                    value = value * rho % R
+            result = (result + value) % R
+
+
+def lincomb_stream(streams_be: Sequence[Sequence[int]], coeffs: Sequence[int]) -> List[int]:
+    """LinCombStream / LinCombIter, tensorcheck/streams.rs:42-132: big-endian streams of unequal length are aligned at
+    their LOW-degree end (the shorter ones are padded in front), element k = sum_i coeffs[i] * stream_i[k]."""
+    n = max((len(t) for t in streams_be), default=0)
+    out = []
+    for k in range(n):
+        acc = 0
+        for t, c in zip(streams_be, coeffs):
+            pad = n - len(t)
+            if k >= pad:
+                acc = (acc + c * t[k - pad]) % R
+        out.append(acc)
+    return out
+
+
+# --------------------------------------------------------------------------
 # snark::Proof::new_time and TensorcheckProof::new_time (time prover, config 4)
 # --------------------------------------------------------------------------
 def product_matrix_vector(matrix, z: Sequence[int]) -> List[int]:

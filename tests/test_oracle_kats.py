@@ -166,3 +166,39 @@ def test_open_folding_restatement_matches_time_side_algebra():
             if q:
                 want_proof = o.g1_add(want_proof, o.g1_mul(o.naive_msm(srs_le, q), etas[i]))
         assert proof == want_proof
+
+
+def test_linear_combination_kat():
+    """src/misc.rs:402-421"""
+    polys = [[100, 101, 102, 103], [100, 100, 100, 100]]
+    assert o.linear_combination(polys, [1, 10]) == [1100, 1101, 1102, 1103]
+    assert o.linear_combination([], []) == []
+
+
+def test_matrix_tensor_stream_kats():
+    """src/snark/streams.rs:106-133 and :177-222 (random field elements replaced by seeded ones)"""
+    import random
+
+    rng = random.Random(12)
+    r = rng.randrange(o.R)
+    assert list(o.matrix_tensor_stream(o.diagonal_matrix_stream(r, 4), [1, 1])) == [r, r, r, r]
+    t0, t1 = rng.randrange(o.R), rng.randrange(o.R)
+    assert list(o.matrix_tensor_stream(o.diagonal_matrix_stream(r, 4), [t0, t1])) == [r * t0 * t1 % o.R, r * t1 % o.R, r * t0 % o.R, r]
+    E = o.EOL
+    matrix = [(1, 0), (1, 1), (1, 2), (1, 3), E, (1, 1), E, (1, 2), E, E]
+    got = list(o.matrix_tensor_stream(matrix, [r, r * r % o.R]))
+    assert got == [(r * r * r + r * r + r + 1) % o.R, r, r * r % o.R, 0]
+    ch = [rng.randrange(o.R) for _ in range(4)]
+    got = list(o.matrix_tensor_stream(o.diagonal_matrix_stream(1, 16), ch))
+    assert got[::-1] == o.tensor(ch)
+
+
+def test_lincomb_stream():
+    """src/subprotocols/tensorcheck/streams.rs:249-290 plus the alignment rule of LinCombStream::iter (pads)"""
+    ones = [[1] * 100 for _ in range(20)]
+    assert o.lincomb_stream(ones, [0] * 20)[0] == 0
+    # unequal lengths: big-endian streams line up at the low-degree end = linear_combination of the reversed vectors
+    a, b, c = [5, 6, 7, 8], [1, 2], [9]
+    got = o.lincomb_stream([a, b, c], [2, 3, 4])
+    assert got[::-1] == o.linear_combination([a[::-1], b[::-1], c[::-1]], [2, 3, 4])
+    assert got == [10, 12, 14 + 3, 16 + 6 + 36]
