@@ -1145,6 +1145,16 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   slot_bound[0] = refs;
   for (int r = 0; r < levels; r++) slot_bound[r + 1] = (slot_bound[r] + std::min(M, slot_bound[r])) / 2 + 1;
   if (levels > 0) {
+    // the level scratch of a very large pass must not crowd out the buffers the XYZZ path needs anyway: skip the levels
+    // when the part still to be allocated exceeds half of the free HBM (only looked at above 8 GB of scratch)
+    const size_t need = slot_bound[1] * (sizeof(Affine) + sizeof(Fq) + sizeof(uint2)) + (levels > 1 ? slot_bound[2] * sizeof(Affine) : 0);
+    if (need > ((size_t)8 << 30)) {
+      const size_t have = S.aff_a.cap + S.aff_b.cap + S.aff_prefix.cap + S.aff_meta.cap;
+      size_t free_b = 0, total_b = 0;
+      if (need > have && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need - have > free_b / 2) levels = 0;
+    }
+  }
+  if (levels > 0) {
     const size_t s1 = slot_bound[1], s2 = levels > 1 ? slot_bound[2] : 0;
     const size_t warps1 = (size_t)aff_shape(ctx, s1).warps + (size_t)ctx->sm_count * 64;   // the first level has the most warps
     const bool ok = S.aff_a.reserve(s1 * sizeof(Affine)) == GM_OK && S.aff_b.reserve(s2 * sizeof(Affine) + 16) == GM_OK &&
