@@ -37,6 +37,7 @@ SIGNATURES = {
     "gm_shutdown": (_i, [_vp]),
     "gm_last_error": (C.c_char_p, []),
     "gm_abi_version": (_i, []),
+    "gm_msm_describe_plan": (_i, [_sz, _i, _i, _vp]),
     "gm_launch_count": (_u64, [_vp]),
     "gm_last_device_ms": (C.c_float, [_vp, _i]),
     "gm_device_synchronize": (_i, [_vp]),

@@ -72,6 +72,12 @@ extern "C" {
 const char* gm_last_error(void) { return g_err; }
 int gm_abi_version(void) { return 1; }
 
+int gm_msm_describe_plan(size_t n, int with_table, int sm_count, int out[8]) {
+  if (!out || sm_count <= 0) return GM_ERR_ARG;
+  msm_describe_plan(n, with_table != 0, sm_count, out);
+  return GM_OK;
+}
+
 int gm_init(int device_id, gm_ctx** out_ctx) {
   GM_ARG(out_ctx != nullptr, "out_ctx is NULL");
   int count = 0;

@@ -1327,6 +1327,21 @@ int msm_stream_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* d_buckets, cons
   return msm_reduce(ctx, P, d_buckets, d_live, d_acc);
 }
 
+// Planning decisions as plain numbers (host only, no device needed): window bits, windows, buckets per set, affine
+// levels and the (G, warps) shape of the first level - what tests/test_host_logic.py pins.
+void msm_describe_plan(size_t n, bool with_table, int sm_count, int out[8]) {
+  const MsmPlan P = with_table ? msm_plan_merged(n, 0) : msm_plan(n);
+  const size_t M = (size_t)(P.merged ? 1 : P.W) * P.nb;
+  const size_t refs = (size_t)P.W * n;
+  const int levels = affine_levels(refs, M);
+  gm_ctx fake;
+  fake.sm_count = sm_count;
+  const size_t s1 = (refs + std::min(M, refs)) / 2 + 1;
+  const AffShape sh = aff_shape(&fake, s1);
+  out[0] = P.c; out[1] = P.W; out[2] = (int)P.nb; out[3] = P.merged ? 1 : 0; out[4] = levels;
+  out[5] = sh.G; out[6] = (int)sh.warps; out[7] = P.L;
+}
+
 int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, int rec_q, Affine* d_table) {
   if (n == 0) return GM_OK;
   if (W > PRE_MAX_W) { set_error("precompute: too many windows (%d)", W); return GM_ERR_ARG; }

@@ -49,6 +49,10 @@ int gm_init(int device_id, gm_ctx** out_ctx);
 int gm_shutdown(gm_ctx* ctx);
 const char* gm_last_error(void);
 int gm_abi_version(void);
+/* Host-only introspection of the MSM planner (no device needed): out = {window bits c, windows W, buckets per set,
+ * merged bucket set (precomputed table) 0/1, affine levels, slots per thread G and warps of the first level, buckets per
+ * running-sum slice}.  Honours the same GM_MSM_* / GM_AFF_* environment overrides as the MSM itself. */
+int gm_msm_describe_plan(size_t n, int with_table, int sm_count, int out[8]);
 /* number of kernels this library has launched on this ctx since gm_init (bench gpu_launches) */
 uint64_t gm_launch_count(const gm_ctx* ctx);
 /* device elapsed ms of the last gm_msm_* / gm_sumcheck_* call, by CUDA events on the ctx stream;

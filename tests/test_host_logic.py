@@ -168,3 +168,33 @@ def test_sumcheck_block_layout():
         gdist.sumcheck_block(8, 8, 0, 3)
     with pytest.raises(ValueError):
         gdist.sumcheck_block(2, 2, 0, 4)
+
+
+def test_msm_planner_decisions(monkeypatch):
+    """Host-only planner introspection (gm_msm_describe_plan): the decisions the measured numbers of profiles/ rest on."""
+    import ctypes as C
+
+    from gemini_b200._lib import lib
+
+    for k in ("GM_MSM_AFFINE", "GM_MSM_C", "GM_MSM_C_PRE", "GM_AFF_WPS", "GM_AFF_KEEP"):
+        monkeypatch.delenv(k, raising=False)
+
+    def plan(n, table):
+        out = (C.c_int * 8)()
+        assert lib.gm_msm_describe_plan(n, 1 if table else 0, 148, out) == 0
+        return dict(zip(("c", "W", "nb", "merged", "levels", "G", "warps", "L"), list(out)))
+
+    p20 = plan(1 << 20, True)
+    assert (p20["c"], p20["W"], p20["nb"], p20["merged"]) == (20, 13, 1 << 19, 1)
+    assert p20["levels"] == 2 and p20["G"] == 23 and p20["warps"] % 4 == 0     # >= 64 warps per SM in the first level
+    assert p20["warps"] * 32 * p20["G"] >= (13 << 20) // 2
+    p24 = plan(1 << 24, True)
+    assert (p24["c"], p24["W"], p24["merged"], p24["levels"], p24["G"]) == (22, 12, 1, 4, 64)
+    small = plan(1 << 12, True)
+    assert small["levels"] == 0 and small["c"] >= 10                           # small MSMs stay on the XYZZ path
+    plain = plan(1 << 20, False)
+    assert plain["merged"] == 0 and plain["W"] * plain["c"] >= 255 and plain["levels"] >= 1
+    monkeypatch.setenv("GM_MSM_AFFINE", "5")
+    assert plan(1 << 12, True)["levels"] == 5
+    monkeypatch.setenv("GM_MSM_AFFINE", "0")
+    assert plan(1 << 24, True)["levels"] == 0
