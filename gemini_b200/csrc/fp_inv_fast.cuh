@@ -195,4 +195,15 @@ GM_HD Fp<P> fp_inv_divsteps(const Fp<P>& a) {
   return (x * r2) * r2;
 }
 
+// The inversion the latency-critical kernels call (k_aff_invert, k_normalize): Kaliski today; -DGM_FAST_INV switches them
+// to the division-step inverse once it has passed the GPU parity suite.
+template <class P>
+GM_HD Fp<P> fp_inv_serial(const Fp<P>& a) {
+#ifdef GM_FAST_INV
+  return fp_inv_divsteps(a);
+#else
+  return fp_inv(a);
+#endif
+}
+
 }  // namespace gm

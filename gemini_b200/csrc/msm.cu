@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "g1.cuh"
 #include "g1_affine.cuh"
+#include "fp_inv_fast.cuh"
 #include "msm.cuh"
 
 namespace gm {
@@ -407,7 +408,7 @@ k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict
   if (t % (uint32_t)spread) return;
   const uint64_t i = t / (uint32_t)spread;
   if (i >= n_warps) return;
-  store_rw(warp_totals + i, fp_inv(load_rw(warp_totals + i)));
+  store_rw(warp_totals + i, fp_inv_serial(load_rw(warp_totals + i)));
 }
 
 template <bool FIRST>
