@@ -41,7 +41,6 @@ static constexpr uint32_t SKIP = 0xFFFFFFFFu;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
 static constexpr int SPLIT = 1024;         // upper bound of the point references per work item (the runtime value is a kernel argument)
 static constexpr int ACC_THREADS = 128;
-static constexpr int RED_THREADS = 128;    // CTA size of the XYZZ tree reductions
 
 // Warp-aggregated atomicAdd: lanes that target the same counter elect a leader which adds the group size
 // once; every lane gets its own slot.  For uniformly random keys this is a no-op in cost terms, for the
@@ -515,23 +514,6 @@ k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sort
   if (live != nullptr && po == NONE) live[gb] = 1u;
 }
 
-// CTA-wide sum of one XYZZ per thread (shared-memory tree); result valid in thread 0.
-__device__ __forceinline__ XYZZ block_sum_xyzz(XYZZ v, XYZZ* sh) {
-  store_rw(sh + threadIdx.x, v);
-  __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) {
-      XYZZ a = load_rw(sh + threadIdx.x);
-      XYZZ b = load_rw(sh + threadIdx.x + s);
-      xyzz_add(a, b);
-      store_rw(sh + threadIdx.x, a);
-    }
-    __syncthreads();
-  }
-  XYZZ r = load_rw(sh);
-  __syncthreads();
-  return r;
-}
 
 // 6. split buckets: bucket = sum of its partials.  Buckets with at most 32 partials are summed by one warp
 //    (shuffle tree, no CTA barrier); larger ones (a bucket that holds a large share of all points) by a CTA.
@@ -594,164 +576,6 @@ k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restr
   }
 }
 
-// 7. running-sum reduction over slices of L consecutive buckets of one window
-__global__ void __launch_bounds__(128)
-k_bucket_chunks(const XYZZ* __restrict__ buckets, const uint32_t* __restrict__ counts, uint32_t nb, int L, uint32_t nchunks,
-                int W, XYZZ* __restrict__ chunk_s, XYZZ* __restrict__ chunk_w) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int w = blockIdx.y;
-  if (t >= nchunks) return;
-  const size_t g0 = (size_t)w * nb + (size_t)t * L;
-  XYZZ running = XYZZ::identity(), sum = XYZZ::identity();
-  for (int b = L - 1; b >= 0; b--) {
-    if (counts[g0 + b]) {
-      XYZZ v = load_rw(buckets + g0 + b);
-      xyzz_add(running, v);
-    }
-    xyzz_add(sum, running);
-  }
-  store_rw(chunk_s + (size_t)w * nchunks + t, running);
-  store_rw(chunk_w + (size_t)w * nchunks + t, sum);
-}
-
-// 8. The chunk sums S_t (t < T) still carry the weights t*L.  View t = hi*L2 + lo as an H2 x L2 matrix:
-//      sum_t t*S_t = sum_lo lo * C_lo + L2 * sum_hi hi * R_hi,   C_lo / R_hi = plain column / row sums,
-//    so the weighting needs one short double-and-add per ROW and per COLUMN (H2 + L2 of them) instead
-//    of one per chunk.  CTA roles by blockIdx.x: [0,H2) rows of S, [H2,2*H2) rows of W (plain sums of
-//    the locally weighted chunk sums), [2*H2, 2*H2+L2) columns of S.
-__global__ void __launch_bounds__(RED_THREADS)
-k_rowcol(const XYZZ* __restrict__ chunk_s, const XYZZ* __restrict__ chunk_w, uint32_t T, uint32_t H2, uint32_t L2,
-         XYZZ* __restrict__ row_sum, XYZZ* __restrict__ wrow_sum, XYZZ* __restrict__ col_sum) {
-  extern __shared__ uint4 sh_raw[];
-  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
-  const int w = blockIdx.y;
-  const uint32_t bx = blockIdx.x;
-  const XYZZ* src = (bx >= H2 && bx < 2 * H2) ? chunk_w : chunk_s;
-  src += (size_t)w * T;
-  XYZZ acc = XYZZ::identity();
-  if (bx < 2 * H2) {
-    const uint32_t row = bx < H2 ? bx : bx - H2;
-    for (uint32_t lo = threadIdx.x; lo < L2; lo += blockDim.x) {
-      XYZZ v = load_rw(src + (size_t)row * L2 + lo);
-      xyzz_add(acc, v);
-    }
-  } else {
-    const uint32_t col = bx - 2 * H2;
-    for (uint32_t hi = threadIdx.x; hi < H2; hi += blockDim.x) {
-      XYZZ v = load_rw(src + (size_t)hi * L2 + col);
-      xyzz_add(acc, v);
-    }
-  }
-  XYZZ tot = block_sum_xyzz(acc, sh);
-  if (threadIdx.x == 0) {
-    if (bx < H2) store_rw(row_sum + (size_t)w * H2 + bx, tot);
-    else if (bx < 2 * H2) store_rw(wrow_sum + (size_t)w * H2 + (bx - H2), tot);
-    else store_rw(col_sum + (size_t)w * L2 + (bx - 2 * H2), tot);
-  }
-}
-
-__device__ __forceinline__ XYZZ small_scalar_mul(const XYZZ& p, uint32_t k) {
-  XYZZ x = XYZZ::identity();
-  if (k == 0 || p.is_identity()) return x;
-  for (int bit = 31 - __clz(k); bit >= 0; bit--) {
-    xyzz_dbl(x);
-    if ((k >> bit) & 1u) xyzz_add(x, p);
-  }
-  return x;
-}
-
-// 9a. one thread per column / row: lo * C_lo  or  2^log2(L2) * hi * R_hi; CTA tree-sum -> partials.
-//     CTAs [0, ctas_c) handle columns, the rest rows.
-__global__ void __launch_bounds__(RED_THREADS)
-k_weighted(const XYZZ* __restrict__ row_sum, const XYZZ* __restrict__ col_sum, uint32_t H2, uint32_t L2, int log_l2,
-           uint32_t ctas_c, XYZZ* __restrict__ part) {
-  extern __shared__ uint4 sh_raw[];
-  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
-  const int w = blockIdx.y;
-  XYZZ v = XYZZ::identity();
-  if (blockIdx.x < ctas_c) {
-    const uint32_t lo = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lo < L2) v = small_scalar_mul(load_rw(col_sum + (size_t)w * L2 + lo), lo);
-  } else {
-    const uint32_t hi = (blockIdx.x - ctas_c) * blockDim.x + threadIdx.x;
-    if (hi < H2) {
-      v = small_scalar_mul(load_rw(row_sum + (size_t)w * H2 + hi), hi);
-      for (int d = 0; d < log_l2; d++) xyzz_dbl(v);
-    }
-  }
-  XYZZ tot = block_sum_xyzz(v, sh);
-  if (threadIdx.x == 0) store_rw(part + (size_t)w * gridDim.x + blockIdx.x, tot);
-}
-
-// 9b. window total = sum W + L * (sum of weighted partials), times 2^(c*w) when windows keep their own
-//     bucket sets (variable_base.rs:168-175).  Lower half of the CTA tree-sums the weighted partials,
-//     upper half the W row sums, concurrently.
-__global__ void __launch_bounds__(2 * RED_THREADS)
-k_window_total(const XYZZ* __restrict__ part, uint32_t nparts, const XYZZ* __restrict__ wrow_sum, uint32_t H2, int log_l,
-               int c, int merged, XYZZ* __restrict__ win_sum) {
-  extern __shared__ uint4 sh_raw[];
-  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
-  const int w = blockIdx.x;
-  const uint32_t half = blockDim.x >> 1;
-  const uint32_t t = threadIdx.x % half;
-  const bool upper = threadIdx.x >= half;
-  const XYZZ* src = upper ? wrow_sum + (size_t)w * H2 : part + (size_t)w * nparts;
-  const uint32_t cnt = upper ? H2 : nparts;
-  XYZZ acc = XYZZ::identity();
-  for (uint32_t k = t; k < cnt; k += half) {
-    XYZZ v = load_rw(src + k);
-    xyzz_add(acc, v);
-  }
-  store_rw(sh + threadIdx.x, acc);
-  __syncthreads();
-  for (uint32_t s = half >> 1; s > 0; s >>= 1) {
-    if (t < s) {
-      XYZZ a = load_rw(sh + threadIdx.x);
-      XYZZ b2 = load_rw(sh + threadIdx.x + s);
-      xyzz_add(a, b2);
-      store_rw(sh + threadIdx.x, a);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    XYZZ tot = load_rw(sh);
-    for (int d = 0; d < log_l; d++) xyzz_dbl(tot);
-    XYZZ wsum = load_rw(sh + half);
-    xyzz_add(tot, wsum);
-    if (!merged)
-      for (int d = 0; d < c * w; d++) xyzz_dbl(tot);
-    store_rw(win_sum + w, tot);
-  }
-}
-
-// 10. acc += sum of windows
-__global__ void k_final(const XYZZ* __restrict__ win_sum, int W, XYZZ* __restrict__ acc) {
-  if (threadIdx.x || blockIdx.x) return;
-  XYZZ a = load_rw(acc);
-  for (int w = 0; w < W; w++) {
-    XYZZ b = load_rw(win_sum + w);
-    xyzz_add(a, b);
-  }
-  store_rw(acc, a);
-}
-
-__global__ void k_normalize(const XYZZ* __restrict__ acc, Jacobian* __restrict__ out) {
-  if (threadIdx.x || blockIdx.x) return;
-  XYZZ a = load_rw(acc);
-  Jacobian j = xyzz_to_jacobian_normalized(a);
-  store_rw(out, j);
-}
-
-__global__ void k_add_jacobians(const Jacobian* __restrict__ in, uint32_t k, XYZZ* __restrict__ acc) {
-  if (threadIdx.x || blockIdx.x) return;
-  XYZZ a = load_rw(acc);
-  for (uint32_t i = 0; i < k; i++) {
-    Jacobian j = load_rw(in + i);
-    XYZZ b = xyzz_from_jacobian(j);
-    xyzz_add(a, b);
-  }
-  store_rw(acc, a);
-}
 
 // -------------------------------------------------------------------------------------------
 // host side
@@ -994,49 +818,6 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   return GM_OK;
 }
 
-// Phase B: bucket reduction (running sums, weights, windows) and *d_acc += result.  `valid[gb] != 0` marks the
-// buckets that hold a point (per-call counts, or the persistent live flags of a stream).
-static int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_t* valid, XYZZ* d_acc) {
-  MsmScratch& S = ctx->msm;
-  const bool merged = P.merged;
-  const int Weff = merged ? 1 : P.W;
-  // chunk index t = hi * L2 + lo, an H2 x L2 matrix (both powers of two)
-  int log_t = 0;
-  while ((1u << log_t) < P.nchunks) log_t++;
-  const int log_l2 = (log_t + 1) / 2;
-  const uint32_t L2 = 1u << log_l2, H2 = P.nchunks >> log_l2;
-  int log_l = 0;
-  while ((1 << log_l) < P.L) log_l++;
-  const uint32_t ctas_c = (L2 + RED_THREADS - 1) / RED_THREADS, ctas_r = (H2 + RED_THREADS - 1) / RED_THREADS;
-  const uint32_t nparts = ctas_c + ctas_r;
-  // small: chunk_s | chunk_w | row_sum | wrow_sum | col_sum | part | win_sum
-  const size_t off_cs = 0;
-  const size_t off_cw = off_cs + (size_t)Weff * P.nchunks * sizeof(XYZZ);
-  const size_t off_rs = off_cw + (size_t)Weff * P.nchunks * sizeof(XYZZ);
-  const size_t off_wr = off_rs + (size_t)Weff * H2 * sizeof(XYZZ);
-  const size_t off_col = off_wr + (size_t)Weff * H2 * sizeof(XYZZ);
-  const size_t off_bp = off_col + (size_t)Weff * L2 * sizeof(XYZZ);
-  const size_t off_ws = off_bp + (size_t)Weff * nparts * sizeof(XYZZ);
-  const size_t small_bytes = off_ws + (size_t)Weff * sizeof(XYZZ);
-  GM_TRY(S.small.reserve(small_bytes));
-  uint8_t* sm = S.small.as<uint8_t>();
-  XYZZ* chunk_s = reinterpret_cast<XYZZ*>(sm + off_cs);
-  XYZZ* chunk_w = reinterpret_cast<XYZZ*>(sm + off_cw);
-  XYZZ* row_sum = reinterpret_cast<XYZZ*>(sm + off_rs);
-  XYZZ* wrow_sum = reinterpret_cast<XYZZ*>(sm + off_wr);
-  XYZZ* col_sum = reinterpret_cast<XYZZ*>(sm + off_col);
-  XYZZ* part = reinterpret_cast<XYZZ*>(sm + off_bp);
-  XYZZ* win_sum = reinterpret_cast<XYZZ*>(sm + off_ws);
-  const size_t red_sh = RED_THREADS * sizeof(XYZZ);
-  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, buckets, valid, P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
-  LAUNCH(ctx, k_rowcol, dim3(2 * H2 + L2, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
-  LAUNCH(ctx, k_weighted, dim3(nparts, Weff), RED_THREADS, red_sh, row_sum, col_sum, H2, L2, log_l2, ctas_c, part);
-  LAUNCH(ctx, k_window_total, Weff, 2 * RED_THREADS, 2 * red_sh, part, nparts, wrow_sum, H2, log_l, P.c, merged ? 1 : 0, win_sum);
-  LAUNCH(ctx, k_final, 1, 32, 0, win_sum, Weff, d_acc);
-  GM_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
-  GM_CUDA(cudaGetLastError());
-  return GM_OK;
-}
 
 int msm_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
   // W * n references are addressed with 32 bits (31 + sign for table references): run very large inputs as several passes
@@ -1087,22 +868,8 @@ void msm_describe_plan(size_t n, bool with_table, int sm_count, int out[8]) {
 }
 
 
-int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc) {
-  GM_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(XYZZ), ctx->stream));
-  return GM_OK;
-}
 
-int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc) {
-  LAUNCH(ctx, k_add_jacobians, 1, 32, 0, d_in, (uint32_t)k, d_acc);
-  GM_CUDA(cudaGetLastError());
-  return GM_OK;
-}
 
-int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out) {
-  LAUNCH(ctx, k_normalize, 1, 32, 0, d_acc, d_out);
-  GM_CUDA(cudaGetLastError());
-  return GM_OK;
-}
 
 
 

@@ -35,6 +35,8 @@ int msm_stream_push(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, cons
                     const MsmPlan& P, XYZZ* d_buckets, uint32_t* d_live);
 int msm_stream_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* d_buckets, const uint32_t* d_live, XYZZ* d_acc);
 int msm_precompute(gm_ctx* ctx, const Affine* d_points, size_t n, int c, int W, int rec_q, Affine* d_table);
+// bucket reduction (msm_reduce.cu): *d_acc += sum over the buckets flagged by valid[]; shared by the one-shot and streamed MSM
+int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_t* valid, XYZZ* d_acc);
 void msm_describe_plan(size_t n, bool with_table, int sm_count, int out[8]);
 int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);

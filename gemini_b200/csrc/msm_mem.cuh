@@ -38,4 +38,24 @@ __device__ __forceinline__ const Affine* rec_at(const Affine* base, size_t idx, 
   return reinterpret_cast<const Affine*>(reinterpret_cast<const uint4*>(base) + idx * (size_t)rec_q);
 }
 
+static constexpr int RED_THREADS = 128;    // CTA size of the XYZZ tree reductions
+
+// CTA-wide sum of one XYZZ per thread (shared-memory tree); result valid in thread 0.
+__device__ __forceinline__ XYZZ block_sum_xyzz(XYZZ v, XYZZ* sh) {
+  store_rw(sh + threadIdx.x, v);
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      XYZZ a = load_rw(sh + threadIdx.x);
+      XYZZ b = load_rw(sh + threadIdx.x + s);
+      xyzz_add(a, b);
+      store_rw(sh + threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  XYZZ r = load_rw(sh);
+  __syncthreads();
+  return r;
+}
+
 }  // namespace gm
