@@ -9,6 +9,9 @@
 //                       (variable_base.rs:21-61), per-bucket histogram            [HBM: 32 B/term in]
 //   2 scan              exclusive prefix sum of the W * 2^(c-1) bucket counts
 //   3 k_scatter         counting sort: point references grouped by (window, bucket)
+//   3b k_aff_prepare / k_aff_invert / k_aff_finish  (x levels)
+//                       pairwise bucket sums in AFFINE coordinates with shared inversions (g1_affine.cuh):
+//                       6 instead of 10 Fq products per addition; the survivors go on to rows 4-6
 //   4 k_classify / k_worklist_fill
 //                       buckets are cut into work items of <= SPLIT references and the items are
 //                       ordered by size (largest first) so that the 32 lanes of a warp run equally
@@ -22,6 +25,7 @@
 //   9 k_weighted, k_window_total   one short scalar multiplication per row and per column, CTA tree-sums,
 //                       per-window total times 2^(c*w) (variable_base.rs:168-175)
 //  10 k_final           sum of windows, += device-resident accumulator, optional normalisation
+// Rows 1-6 live in this file, rows 7-10 in msm_reduce.cu, the key-setup kernels in srs.cu.
 //
 // The window size c is chosen by a cost model for the GPU (not arkworks' ln(n)+2): the result is a
 // unique group element, so any c gives the bit-identical normalised output.
