@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libgemini_b200.so")
+# GEMINI_B200_LIB selects another in-tree build of the same ABI (experimental kernels built with `make EXP=...`)
+lib_path = os.environ.get("GEMINI_B200_LIB") or os.path.join(_HERE, "libgemini_b200.so")
 
 
 class GeminiError(RuntimeError):
