@@ -1040,3 +1040,91 @@ def snark_new_time(r1cs, powers_of_g, transcript):
             "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
             "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),
             "tensorcheck_proof": tc}
+
+
+# --------------------------------------------------------------------------
+# snark::Proof::new_elastic (config 5) - restated so that the reference's own strongest test, time proof == elastic
+# proof (snark/tests.rs:13-58), pins the streaming restatements above against the time-side ones
+# --------------------------------------------------------------------------
+def matrix_into_colmaj(rows, col_number: int):
+    """circuit.rs:179-205: column-major stream, LAST column first, within a column the LAST row first; one EOL per
+    column.  ``rows[i]`` = [(value, column), ...] sorted by column."""
+    out = []
+    for column in reversed(range(col_number)):
+        for row in reversed(range(len(rows))):
+            for val, col in reversed(rows[row]):
+                if col == column:
+                    out.append((val % R, row))
+                elif col < column:
+                    break
+        out.append(EOL)
+    return out
+
+
+def powers2(x: int, n: int) -> List[int]:
+    """misc.rs:68-77: x, x^2, x^4, ..."""
+    out, cur = [], x % R
+    for _ in range(n):
+        out.append(cur)
+        cur = cur * cur % R
+    return out
+
+
+def elastic_tensorcheck(transcript, powers_of_g_be, witness_be, body_be, challenges, max_msm_buffer: int):
+    """snark/elastic_prover.rs:109-167 (``tensorcheck``)."""
+    chals = list(challenges)[:-1]                                             # strip_last
+    commitments = kzg_commit_folding(powers_of_g_be, body_be, chals, max_msm_buffer)
+    for c in commitments:
+        transcript.append_g1(b"commitment", c)
+    eval_chal = transcript.get_challenge(b"evaluation-chal")
+    points = [eval_chal * eval_chal % R, eval_chal, (-eval_chal) % R]
+    at_pos = evaluate_folding(body_be, chals, points[1])
+    at_neg = evaluate_folding(body_be, chals, points[2])
+    fold_evals = [[x, y] for x, y in zip(at_pos, at_neg)]
+    evaluations_w = [evaluate_be(witness_be, p) for p in points]
+    for e in evaluations_w:
+        transcript.append_serializable(b"eval", e)
+    for row in fold_evals:
+        for e in row:
+            transcript.append_serializable(b"eval", e)
+    open_chal = transcript.get_challenge(b"open-chal")
+    open_chals = powers(open_chal, len(challenges) + 1)
+    _, proof_w = kzg_stream_open_multi_points(powers_of_g_be, witness_be, points, max_msm_buffer)
+    _, proof = kzg_open_folding(powers_of_g_be, body_be, chals, points, open_chals[1:], max_msm_buffer)
+    return {"base_polynomials_evaluations": [evaluations_w], "folded_polynomials_evaluations": fold_evals,
+            "evaluation_proof": g1_add(proof_w, proof), "folded_polynomials_commitments": commitments}
+
+
+def snark_new_elastic(r1cs, powers_of_g, transcript, max_msm_buffer: int):
+    """snark::Proof::new_elastic, snark/elastic_prover.rs:169-267, on the streams the reference's test builds
+    (snark/tests.rs:26-52): everything big-endian (Reverse), matrices column-major."""
+    z, w = r1cs["z"], r1cs["w"]
+    z_a = product_matrix_vector(r1cs["a"], z)
+    z_b = product_matrix_vector(r1cs["b"], z)
+    z_c = product_matrix_vector(r1cs["c"], z)
+    srs_be = list(powers_of_g)[::-1]
+    z_be, w_be = z[::-1], w[::-1]
+    witness_commitment = kzg_stream_commit(srs_be, w_be)
+    transcript.append_g1(b"witness", witness_commitment)
+    alpha = transcript.get_challenge(b"alpha")
+    zc_alpha = evaluate_be(z_c[::-1], alpha)
+    transcript.append_serializable(b"zc(alpha)", zc_alpha)
+    first = sumcheck_prove_transcript(ElasticProver(z_a[::-1], z_b[::-1], alpha), transcript)
+    eta = transcript.get_challenge(b"eta")
+    b_tensors = first["challenges"]
+    c_tensors = powers2(alpha, len(b_tensors))
+    a_tensors = hadamard(b_tensors, c_tensors)
+    n = len(z)
+    a_alpha = list(matrix_tensor_stream(matrix_into_colmaj(r1cs["a"], n), a_tensors))
+    b_alpha = list(matrix_tensor_stream(matrix_into_colmaj(r1cs["b"], n), b_tensors))
+    c_alpha = list(matrix_tensor_stream(matrix_into_colmaj(r1cs["c"], n), c_tensors))
+    lhs = lincomb_stream([a_alpha, b_alpha, c_alpha], powers(eta, 3))
+    second = sumcheck_prove_transcript(ElasticProver(lhs, z_be, 1), transcript)
+    batch_challenge = transcript.get_challenge(b"batch_challenge")
+    body = lincomb_stream([lhs, z_be], powers(batch_challenge, 2))
+    tc = elastic_tensorcheck(transcript, srs_be, w_be, body, second["challenges"], max_msm_buffer)
+    return {"witness_commitment": witness_commitment, "zc_alpha": zc_alpha,
+            "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
+            "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),
+            "tensorcheck_proof": tc}
+

@@ -202,3 +202,49 @@ def test_lincomb_stream():
     got = o.lincomb_stream([a, b, c], [2, 3, 4])
     assert got[::-1] == o.linear_combination([a[::-1], b[::-1], c[::-1]], [2, 3, 4])
     assert got == [10, 12, 14 + 3, 16 + 6 + 36]
+
+
+class _HashTranscript:
+    """Deterministic Fiat-Shamir stand-in (the Merlin restatement lives in the product and has its own vectors)."""
+
+    def __init__(self):
+        import hashlib
+
+        self._hashlib = hashlib
+        self.h = hashlib.sha256(b"test-transcript")
+
+    def append_serializable(self, label, obj):
+        self.h.update(label + repr(obj).encode())
+
+    def append_g1(self, label, point):
+        self.h.update(label + b"G1" + repr(point).encode())
+
+    def get_challenge(self, label):
+        self.h.update(b"challenge" + label)
+        return int.from_bytes(self._hashlib.sha512(self.h.digest()).digest(), "little") % o.R
+
+
+@pytest.mark.parametrize("rows,cols,seed", [(8, 16, 1), (8, 8, 2), (5, 7, 3), (16, 16, 4)])
+def test_snark_time_proof_equals_elastic_proof(rows, cols, seed):
+    """The reference's strongest test, snark/tests.rs:13-58 (`assert_eq!(time_proof, space_proof)`), on random sparse
+    matrices: it ties the streaming restatements (ElasticProver, stream commit, MatrixTensor, LinCombStream,
+    commit_folding, evaluate_folding, open_multi_points, open_folding) to the time-side ones."""
+    import random
+
+    from util import rand_points
+
+    rng = random.Random(seed)
+
+    def matrix():
+        m = []
+        for _ in range(rows):
+            cs = sorted(rng.sample(range(cols), rng.randrange(1, min(4, cols) + 1)))
+            m.append([(rng.randrange(1, o.R), c) for c in cs])
+        return m
+
+    z = [rng.randrange(o.R) for _ in range(cols)]
+    r1cs = {"a": matrix(), "b": matrix(), "c": matrix(), "z": z, "w": z[cols // 2:], "x": z[:cols // 2]}
+    srs = rand_points(rows + cols + 1, 500 + seed)
+    time_proof = o.snark_new_time(r1cs, srs, _HashTranscript())
+    elastic_proof = o.snark_new_elastic(r1cs, srs, _HashTranscript(), 20)
+    assert elastic_proof == time_proof
