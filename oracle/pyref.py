@@ -19,6 +19,9 @@ Every function restates a routine of the reference (arkworks-rs/gemini @
   elastic_prover.rs:44-57, subclaim.rs:77-97}``, herring
   ``src/herring/time_prover.rs:72-137`` and ``src/misc.rs:235-266``.
 * KZG callers: ``src/kzg/time.rs:81-159`` and ``src/kzg/space.rs:95-285``.
+* provers: ``src/snark/time_prover.rs:19-117``, ``src/snark/elastic_prover.rs:109-267`` with the stream adaptors
+  ``src/snark/streams.rs:60-102``, ``src/subprotocols/tensorcheck/streams.rs:42-132``, ``src/circuit.rs:179-205``;
+  the reference's test "time proof == elastic proof" (``src/snark/tests.rs:13-58``) holds between the two.
 
 Parity status: the Fr paths are pinned by the reference's own known-answer
 tests (see tests/test_oracle_kats.py).  For the MSM *value* the reference
