@@ -38,6 +38,7 @@ __device__ __forceinline__ const Affine* rec_at(const Affine* base, size_t idx, 
   return reinterpret_cast<const Affine*>(reinterpret_cast<const uint4*>(base) + idx * (size_t)rec_q);
 }
 
+static constexpr int GEN_RUN = 16;        // consecutive multiples per thread in the point generators (srs.cu, srs_setup.cu)
 static constexpr int RED_THREADS = 128;    // CTA size of the XYZZ tree reductions
 
 // CTA-wide sum of one XYZZ per thread (shared-memory tree); result valid in thread 0.
