@@ -162,3 +162,83 @@ def new_time(ctx: Context, r1cs: R1cs, ck: CommitterKey, transcript, timers: Opt
             "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
             "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),
             "tensorcheck_proof": tc}
+
+
+# ---------------------------------------------------------------------------------------------------
+# Elastic prover (config 5) - STAGED: assembled from GPU-validated parts (stream commit, ElasticProver, commit_folding,
+# evaluate_folding, open_multi_points, open_folding) and checked on the CPU only through its oracle twin
+# (the CPU restatement of new_elastic equals the one of new_time, tests/test_oracle_kats.py); the composition itself has not run on a GPU yet - its parity
+# test waits in tests/staged_gpu_elastic.py (not collected) for the first GPU minutes of round 2.
+# ---------------------------------------------------------------------------------------------------
+def elastic_tensorcheck(transcript, cks, witness_be: Sequence[int], body_le: DeviceFr, challenges: Sequence[int], max_msm_buffer: int) -> Dict:
+    """``tensorcheck`` of snark/elastic_prover.rs:109-167.  ``body_le``: the batched body polynomial, resident and
+    little-endian (the stream the reference re-reads is its reverse); ``witness_be``: big-endian host coefficients."""
+    from .msm import _DeviceStream
+    from .tensorcheck import FoldedPolynomialTree, evaluate_folding
+
+    ctx = cks.ctx
+    chals = list(challenges)[:-1]                                              # strip_last
+    tree = FoldedPolynomialTree.from_le_device(ctx, body_le, chals)
+    # CommitterKeyStream::commit_folding (kzg/space.rs:192-223) against the resident levels
+    commitments = []
+    for lvl in tree.levels:
+        m = lvl.n
+        st = _DeviceStream(ctx, cks.srs_be, max(m, 1))
+        st.push_range(len(cks) - m, np.ascontiguousarray(lvl.limbs()[::-1]))
+        commitments.append(st.finalize())
+    for c in commitments:
+        transcript.append_g1(b"commitment", c)
+    eval_chal = transcript.get_challenge(b"evaluation-chal")
+    points = [eval_chal * eval_chal % R, eval_chal, (-eval_chal) % R]
+    at_pos, at_neg = evaluate_folding(tree, points[1]), evaluate_folding(tree, points[2])
+    fold_evals = [[x, y] for x, y in zip(at_pos, at_neg)]
+    w_le = DeviceFr.from_host(ctx, list(witness_be)[::-1])
+    evaluations_w = [w_le.evaluate(p) for p in points]
+    for e in evaluations_w:
+        transcript.append_serializable(b"eval", e)
+    for row in fold_evals:
+        for e in row:
+            transcript.append_serializable(b"eval", e)
+    open_chal = transcript.get_challenge(b"open-chal")
+    open_chals = [pow(open_chal, k, R) for k in range(len(challenges) + 1)]
+    _, proof_w = cks.open_multi_points(witness_be, points, max_msm_buffer)
+    _, proof = cks.open_folding(tree, points, open_chals[1:], max_msm_buffer)
+    total = field.jacobian_to_affine(ctx.g1_sum(np.stack([field.affine_to_jacobian_limbs(proof_w), field.affine_to_jacobian_limbs(proof)])))
+    return {"base_polynomials_evaluations": [evaluations_w], "folded_polynomials_evaluations": fold_evals,
+            "evaluation_proof": total, "folded_polynomials_commitments": commitments}
+
+
+def new_elastic(ctx: Context, r1cs: R1cs, cks, transcript, max_msm_buffer: int = 1 << 20) -> Dict:
+    """snark::Proof::new_elastic (snark/elastic_prover.rs:169-267).  ``cks``: kzg.CommitterKeyStream (big-endian SRS).
+    The streams of the reference (Reverse(z), column-major matrices, MatrixTensor, LinCombStream) are the resident
+    little-endian vectors of the time prover read backwards, so the vector algebra is shared with ``new_time``; what
+    differs is the prover flavour (ElasticProver: rounds from the MIN length, Space -> Time hand-off) and the KZG side
+    (stream commit, commit_folding, open_multi_points + open_folding instead of one batched opening)."""
+    from .sumcheck import ElasticProver
+
+    z_a, z_b, z_c = r1cs.a.matvec(r1cs.z), r1cs.b.matvec(r1cs.z), r1cs.c.matvec(r1cs.z)
+    w_be = r1cs.w.to_ints()[::-1]
+    witness_commitment = cks.commit(w_be)
+    transcript.append_g1(b"witness", witness_commitment)
+    alpha = transcript.get_challenge(b"alpha")
+    zc_alpha = z_c.evaluate(alpha)
+    transcript.append_serializable(b"zc(alpha)", zc_alpha)
+    first = _prove_sumcheck(transcript, ElasticProver(ctx, z_a.to_ints()[::-1], z_b.to_ints()[::-1], alpha))
+    eta = transcript.get_challenge(b"eta")
+    # MatrixTensor(a_colmaj, hadamard(b, powers2(alpha))) etc. = transposed SpMV with the expanded tensors
+    b_ch = tensor(ctx, first["challenges"])
+    c_ch = powers(ctx, alpha, b_ch.n)
+    a_ch = b_ch.hadamard(c_ch)
+    lhs = r1cs.at.matvec(a_ch)
+    lhs.axpy(eta, r1cs.bt.matvec(b_ch))
+    lhs.axpy(eta * eta % R, r1cs.ct.matvec(c_ch))
+    second = _prove_sumcheck(transcript, ElasticProver(ctx, lhs.to_ints()[::-1], r1cs.z.to_ints()[::-1], 1))
+    batch_challenge = transcript.get_challenge(b"batch_challenge")
+    body = DeviceFr.zeros(ctx, max(lhs.n, r1cs.z.n))
+    body.axpy(1, lhs)
+    body.axpy(batch_challenge, r1cs.z)
+    tc = elastic_tensorcheck(transcript, cks, w_be, body, second["challenges"], max_msm_buffer)
+    return {"witness_commitment": witness_commitment, "zc_alpha": zc_alpha,
+            "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
+            "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),
+            "tensorcheck_proof": tc}
