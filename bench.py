@@ -3,12 +3,16 @@
 
 Metric (BASELINE.json): G1 MSM throughput in scalar-mults/s.  One "step" = one kzg::commit-equivalent
 MSM (VariableBaseMSM::msm_unchecked, /root/reference/src/kzg/time.rs:81-83) over n = 2^logn synthetic
-BLS12-381 G1 bases resident on the device and n uniformly random Fr scalars.
+BLS12-381 G1 bases resident on the device and n uniformly random Fr scalars (default logn = 24, the size
+the north star is quoted on).
 
-  own arm       python bench.py --gpus N --steps K --warmup W [--logn 20]
-                (N > 1: launched under torchrun, one rank per GPU; each rank owns a contiguous range
-                 of n points = weak scaling; partial G1 sums are exchanged with one NCCL all-gather
-                 of 144-byte Jacobian points and added on every rank)
+  own arm       python bench.py --gpus N --steps K --warmup W [--logn 24]
+                N > 1: launched under torchrun, one rank per GPU.  Each rank owns a contiguous range of n points
+                (weak scaling); the exchange of the partial G1 sums is ONE ncclAllGather of 192-byte accumulators
+                on the library's own stream (gm_msm_g1_sharded) - torch.distributed only carries the 128-byte
+                NCCL id at start-up.  The other BASELINE configs ride along under "extra": configs[1] (2^20),
+                config 3 (sumcheck + fold, 2^24 Fr), config 4 (snark time prover, logsize 24), config 5 (streamed
+                MSM in 2^20 chunks) and, at N > 1, ONE MSM of fixed total size sharded by point range (strong scaling).
   reference arm python bench.py --impl reference ...   the CPU restatement of arkworks' Pippenger
                 (oracle/gemini_oracle.c, one thread per window like ark-ec's rayon tasks) on the host
                 cores; the reference itself is Rust and cannot be built in this image (no cargo).
@@ -34,10 +38,17 @@ METRIC = "g1_msm_throughput"
 UNIT = "scalar-mults/s"
 ALGO_BYTES_PER_TERM = 128  # 32 B Fr scalar + 96 B packed affine base, each read once
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of the bucket-accumulation phase of ONE MSM (precomputed
-# table, uniform scalars), summed from the ncu launch lists profiles/r01_launches_n20_affine2_dram.csv and
-# profiles/r01_launches_n24_affine4_dram.csv (same bench.py command under ncu); the phase's serialised ncu time
-# (4.68 ms / 55.5 ms) agrees with the live CUDA-event time below
+# table, uniform scalars), summed from the committed ncu launch lists of the same bench.py command (profiles/):
+#   r01: profiles/r01_launches_n20_affine2_dram.csv, profiles/r01_launches_n24_affine4_dram.csv
 NCU_PHASE_TRAFFIC = {20: 8.77e9, 24: 148.9e9}
+NCU_PHASE_TRAFFIC_SRC = "profiles/r01_launches_n{logn}_affine*_dram.csv"
+try:  # refreshed by tools/summarize_launches.py from this round's ncu pass
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as _fh:
+        _t = json.load(_fh)
+        NCU_PHASE_TRAFFIC.update({int(k): float(v) for k, v in _t.get("phase_traffic_bytes", {}).items()})
+        NCU_PHASE_TRAFFIC_SRC = _t.get("source", NCU_PHASE_TRAFFIC_SRC)
+except (OSError, ValueError):
+    pass
 
 
 def measured_peaks():
@@ -51,14 +62,29 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------
 # CPU baseline (oracle/gemini_oracle.c) - the ONLY place bench.py touches oracle/
 # ---------------------------------------------------------------------------------------------
-def load_oracle():
-    so = os.path.join(ROOT, "oracle", "libgemini_oracle.so")
+def load_oracle(native: bool = True):
+    """The C port, rebuilt for THIS host (-march=native: mulx / adx as arkworks' `asm` feature uses) when possible;
+    the portable build (x86-64-v3) that travels with the repo otherwise."""
+    odir = os.path.join(ROOT, "oracle")
+    so = os.path.join(odir, "libgemini_oracle.so")
+    kind = "x86-64-v3"
+    if native:
+        try:
+            subprocess.run(["make", "-C", odir, "native"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+            cand = os.path.join(odir, "_build", "libgemini_oracle_native.so")
+            if os.path.exists(cand):
+                so, kind = cand, "march=native"
+        except Exception:
+            pass
     if not os.path.exists(so):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run(["make", "-C", odir], check=True, stdout=subprocess.DEVNULL)
     lib = C.CDLL(so)
     lib.go_msm_g1.restype = C.c_int
     lib.go_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
     lib.go_generate_bases.argtypes = [C.c_size_t, C.c_uint64, C.c_void_p]
+    lib.go_sumcheck_time.restype = C.c_size_t
+    lib.go_sumcheck_time.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.build_kind = kind
     return lib
 
 
@@ -88,9 +114,20 @@ def splitmix_scalars(n: int, seed: int):
         ge |= eq & (w[:, j] > rl[j])
         eq &= w[:, j] == rl[j]
     ge |= eq
-    for i in np.nonzero(ge)[0]:
-        v = sum(int(w[i, j]) << (64 * j) for j in range(4)) - R
-        w[i] = [(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
+    # values >= r: subtract r limb by limb (borrow chain) on the selected rows
+    sel = np.nonzero(ge)[0]
+    if sel.size:
+        sub = w[sel]
+        borrow = np.zeros(sel.size, dtype=np.uint64)
+        for j in range(4):
+            a = sub[:, j]
+            t = a - rl[j]
+            b1 = (a < rl[j]).astype(np.uint64)
+            t2 = t - borrow
+            b2 = (t < borrow).astype(np.uint64)
+            sub[:, j] = t2
+            borrow = b1 | b2
+        w[sel] = sub
     return w
 
 
@@ -112,6 +149,11 @@ def pick_sample(lib, bases, scalars, n, threads, target_s):
     while m * 2 <= n and per_term * m * 2 * 0.8 <= target_s:  # larger windows make big instances a bit cheaper per term
         m *= 2
     return m
+
+
+def workload_name(logn: int) -> str:
+    tag = {20: " (BASELINE.json configs[1])", 24: " (the size BASELINE.json's north star is quoted on)"}.get(logn, "")
+    return f"kzg::commit n=2^{logn} BLS12-381 G1{tag}"
 
 
 def run_reference(args):
@@ -139,13 +181,13 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     value = m / (ms / 1e3)
     sample = (f"first 2^{m.bit_length() - 1} terms of the 2^{args.logn} workload per step; signed-digit Pippenger c={c_used}, "
-              f"one thread per window (<= {(255 + c_used - 1) // c_used} usable threads)")
+              f"one thread per window (<= {(255 + c_used - 1) // c_used} usable threads); C port built {lib.build_kind}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"kzg::commit n=2^{args.logn} BLS12-381 G1 (CPU restatement of ark-ec msm_unchecked; "
-                               "the Rust reference cannot be built: no cargo in the image)",
+        "config": {"workload": workload_name(args.logn) + " - CPU restatement of ark-ec msm_unchecked (the Rust reference cannot be built: "
+                               "no cargo in the image)",
                    "bases": "P_i=[i+1]G", "scalars": "uniform Fr (splitmix64)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -207,27 +249,105 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
+class Job:
+    """rank / world / context of this process and the rank-synchronised helpers of the timed loops"""
+
+    def __init__(self):
+        import torch
+
+        import gemini_b200 as gm
+
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device - gemini_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.torch = torch
+        self.dist = None
+        self.ctx = gm.Context(self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # the only use of torch.distributed on the data path's behalf: carry the 128-byte NCCL id to every rank
+            self.ctx.comm_init_torch(device=f"cuda:{self.local_rank}")
+
+    def barrier(self):
+        """all ranks aligned and every queue drained: the library's own collective on its own stream + device sync"""
+        self.ctx.comm_barrier()
+        self.torch.cuda.synchronize()
+        self.ctx.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        import numpy as np
+
+        if self.world == 1:
+            return x
+        rows = self.ctx.comm_allgather(np.array([x], dtype=np.float64).view(np.uint64))
+        return float(rows.view(np.float64).max())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+        self.ctx.close()
+
+
+def pinned_copy(torch, ctx, d_ptr, n):
+    import numpy as np
+
+    t = torch.empty(n * 4, dtype=torch.int64).pin_memory()
+    t.copy_(torch.from_numpy(ctx.dev_download(d_ptr, n * 32).view(np.int64)))
+    return t
+
+
+def time_msm(job: Job, srs, d_scal, h_scal, n, steps, warmup, mode):
+    """K timed steps of one (sharded) MSM.  mode: "resident" (scalars in HBM, CUDA events on the library stream),
+    "pinned" / "pageable" (host scalars through the C ABI, wall clock around the blocking call).
+    Returns (sum of step ms - max over ranks, per-phase ms lists, launches, last result)."""
+    import numpy as np
+
+    ctx, nbuf = job.ctx, len(d_scal)
+
+    def step(k):
+        if mode == "resident":
+            return ctx.msm_sharded_dev(srs, d_scal[k % nbuf], n)
+        return ctx.msm_sharded(srs, h_scal[k % nbuf], n=n)
+
+    ref = {}
+    for k in range(max(warmup, 3)):   # rank-independent count: every rank issues the same collectives
+        ref[k % nbuf] = step(k)
+    ev_ms, phases = [], ([], [], [])
+    launches0 = ctx.launch_count
+    for k in range(steps):
+        ctx.l2_flush()  # between timed iterations: 256 MB write > 126 MB L2 (untimed)
+        job.barrier()
+        t0 = time.perf_counter()
+        if mode == "resident":
+            ctx.timer_start()
+            out = step(k)
+            ev_ms.append(ctx.timer_stop())
+        else:
+            out = step(k)
+            ev_ms.append(1e3 * (time.perf_counter() - t0))
+        for j in range(3):
+            phases[j].append(ctx.last_device_ms(j + 1))
+        assert np.array_equal(out, ref.setdefault(k % nbuf, out)), "non-deterministic result"
+    launches = ctx.launch_count - launches0
+    return job.max_over_ranks(sum(ev_ms)), phases, launches, ref
+
+
 def run_own(args):
     import numpy as np
-    import torch
 
-    import gemini_b200 as gm
     from gemini_b200 import field
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - gemini_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = gm.Context(local_rank)
+    job = Job()
+    ctx, rank, world, torch = job.ctx, job.rank, job.world, job.torch
     n = 1 << args.logn
+    sampler = ClockSampler(job.local_rank)
 
     # workload: rank k owns points [k*n, (k+1)*n) of the global SRS P_i = [i+1]G and its n scalars
     srs = ctx.srs_generate(n, first_multiple=1 + rank * n)
@@ -242,120 +362,60 @@ def run_own(args):
         if args.scalars == "equal":  # dummy_r1cs (src/circuit.rs:349-365): every scalar identical
             one = ctx.dev_download(d_scal[k], 32).reshape(1, 4)
             ctx.dev_upload(d_scal[k], np.ascontiguousarray(np.broadcast_to(one, (n, 4))))
-        t = torch.empty(n * 4, dtype=torch.int64).pin_memory()
-        arr = ctx.dev_download(d_scal[k], n * 32)
-        t.copy_(torch.from_numpy(arr.view(np.int64)))
-        h_scal.append(t)
-    part_dev = torch.zeros(18, dtype=torch.int64, device="cuda")
-    gather = [torch.zeros(18, dtype=torch.int64, device="cuda") for _ in range(world)]
+        h_scal.append(pinned_copy(torch, ctx, d_scal[k], n))
 
-    def exchange(partial: np.ndarray) -> np.ndarray:
-        """all-reduce of partial G1 accumulators = all-gather of 144-byte points + device adds"""
-        if world == 1:
-            return partial
-        part_dev.copy_(torch.from_numpy(partial.view(np.int64)))
-        dist.all_gather(gather, part_dev)
-        allp = torch.stack(gather).cpu().numpy().view(np.uint64)
-        return ctx.g1_sum(allp)
-
-    def step_resident(k):
-        return exchange(ctx.msm_dev(srs, d_scal[k % nbuf], n))
-
-    def step_e2e(k):
-        return exchange(ctx.msm(srs, h_scal[k % nbuf]))  # pinned host scalars: H2D inside the call, 144 B D2H
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctx.synchronize()
-
-    results = {}
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()  # nvidia-smi needs ~1 s to produce its first line: started before the warm-up steps
-    t_warm = time.perf_counter()
-    k = 0
-    while k < max(args.warmup, 3) or time.perf_counter() - t_warm < 1.5:
-        results[("r", k % nbuf)] = step_resident(k)
-        k += 1
+        sampler.start()  # nvidia-smi needs ~1 s to produce its first line; no collective depends on it
     # ---- timed: inputs resident in HBM --------------------------------------------------------
-    ev_ms, wall_ms, acc_ms, sort_ms, red_ms = [], [], [], [], []
-    launches0 = ctx.launch_count
-    for k in range(args.steps):
-        ctx.l2_flush()  # between timed iterations: 256 MB write > 126 MB L2 (untimed)
-        barrier()
-        t0 = time.perf_counter()
-        ctx.timer_start()
-        out = step_resident(k)
-        ms = ctx.timer_stop()
-        torch.cuda.synchronize()
-        wall_ms.append(1e3 * (time.perf_counter() - t0))
-        ev_ms.append(ms)
-        sort_ms.append(ctx.last_device_ms(1)); acc_ms.append(ctx.last_device_ms(2)); red_ms.append(ctx.last_device_ms(3))
-        assert np.array_equal(out, results.setdefault(("r", k % nbuf), out)), "non-deterministic result"
-    launches = ctx.launch_count - launches0
+    tot_ms, (sort_ms, acc_ms, red_ms), launches, res_r = time_msm(job, srs, d_scal, h_scal, n, args.steps, args.warmup, "resident")
     clocks = sampler.stop() if rank == 0 else None
-    # N=1: CUDA events on the library's stream.  N>1: the exchange runs on NCCL's stream, so the step is the
-    # synchronised wall time; either way the slowest rank defines the step.
-    mine = sum(ev_ms) if world == 1 else sum(wall_ms)
-    tot = torch.tensor([mine], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tot.item()) / args.steps
+    ms_per_step = tot_ms / args.steps
     value = world * n / (ms_per_step / 1e3)
+    # ---- timed: end to end through the C ABI with host buffers (pinned, then plain pageable memory) ----
+    e2e_tot, _, _, res_e = time_msm(job, srs, d_scal, h_scal, n, args.steps, 2, "pinned")
+    e2e_ms = e2e_tot / args.steps
+    assert np.array_equal(res_e[0], res_r[0]), "host and resident paths disagree"
+    h_page = [np.array(t.numpy().view(np.uint64).reshape(n, 4)) for t in h_scal]   # ordinary (pageable) numpy memory, like a Rust Vec<Fr>
+    page_tot, _, _, res_p = time_msm(job, srs, d_scal, h_page, n, max(2, args.steps // 2), 1, "pageable")
+    page_ms = page_tot / max(2, args.steps // 2)
+    assert np.array_equal(res_p[0], res_r[0]), "pageable and resident paths disagree"
+    del h_page
 
-    # ---- timed: end to end through the C ABI with host buffers -------------------------------
-    for k in range(2):
-        results[("e", k % nbuf)] = step_e2e(k)
-    e2e_ms = []
-    for k in range(args.steps):
-        ctx.l2_flush()
-        barrier()
-        t0 = time.perf_counter()
-        out = step_e2e(k)
-        torch.cuda.synchronize()
-        e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        assert np.array_equal(out, results[("e", k % nbuf)])
-    tot = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    e2e_value = world * n / (float(tot.item()) / args.steps / 1e3)
-    # resident and host paths must agree bit for bit
-    assert np.array_equal(results[("e", 0)], results[("r", 0)])
-
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-        return
-    peak, peak_src = measured_peaks()
-    acc = sum(acc_ms) / len(acc_ms)
-    achieved = n * ALGO_BYTES_PER_TERM / (acc / 1e3) / 1e9
-    plan_c = os.environ.get("GM_MSM_C", "auto")
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"kzg::commit n=2^{args.logn} BLS12-381 G1 per GPU (BASELINE.json configs[1] at logn=20)",
-                   "bases": "P_i=[i+1]G generated on device, resident in HBM", "scalars": "uniform Fr (splitmix64), 2 alternating sets" if args.scalars == "uniform" else "all scalars equal (dummy_r1cs)",
-                   "window_bits": plan_c, "affine_levels": os.environ.get("GM_MSM_AFFINE", "auto"), "srs_precompute": {"window_bits": pre_c, "levels": pre_levels, "hbm_bytes": pre_levels * n * 96},
-                   "l2": "256 MB flush between timed iterations",
-                   "timing": "CUDA events on the library stream" if world == 1 else "synchronised wall clock incl. NCCL all-gather, max over ranks",
-                   "sharding": "contiguous point ranges, all-gather of 144 B partial sums + device adds" if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 144 * world,
-                "ms_per_step": float(tot.item()) / args.steps},
-        "gpu_launches": launches,
-        "phases_ms": {"digits_sort": sum(sort_ms) / len(sort_ms), "bucket_accumulation": acc, "reduce_finish": sum(red_ms) / len(red_ms)},
-        "roofline": {"bound": "hbm", "kernel": "bucket accumulation phase: affine levels (k_aff_prepare, k_aff_invert, k_aff_finish) + work list + k_accumulate, "
-                                                 "timed as one region by CUDA events on the library stream",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_PHASE_TRAFFIC.get(args.logn) if (args.scalars == "uniform" and not args.no_precompute) else None,
-                     "peak_source": peak_src,
-                     "note": "MSM is integer-multiplier bound (SURVEY.md 8d): 6-10 Fq products (276 IMAD.WIDE each) per bucket addition, W additions per term; "
-                             "ncu: k_aff_finish 78-87 %, k_accumulate 89 % sm throughput (FMA-heavy pipe). The HBM fraction is reported as the contract asks; "
-                             "traffic >> algorithmic bytes because every term gathers one 96-B table point PER WINDOW and the affine levels stream their intermediate points"},
-        "clocks": clocks,
-    }
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        acc = sum(acc_ms) / len(acc_ms)
+        achieved = n * ALGO_BYTES_PER_TERM / (acc / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args.logn) + (" per GPU" if world > 1 else ""),
+                       "bases": "P_i=[i+1]G generated on device, resident in HBM",
+                       "scalars": "uniform Fr (splitmix64), 2 alternating sets" if args.scalars == "uniform" else "all scalars equal (dummy_r1cs)",
+                       "window_bits": os.environ.get("GM_MSM_C", "auto"), "affine_levels": os.environ.get("GM_MSM_AFFINE", "auto"),
+                       "srs_precompute": {"window_bits": pre_c, "levels": pre_levels, "hbm_bytes": pre_levels * n * 96},
+                       "l2": "256 MB flush between timed iterations",
+                       "timing": "CUDA events on the library stream (the NCCL all-gather of the partial sums is queued on that stream), max over ranks",
+                       "sharding": f"{world} contiguous point ranges, one ncclAllGather of 192-B partial accumulators + {world - 1} device adds per MSM"
+                                   if world > 1 else "single GPU"},
+            "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 144 * world,
+                    "ms_per_step": e2e_ms, "host_memory": "pinned",
+                    "pageable": {"value": world * n / (page_ms / 1e3), "ms_per_step": page_ms,
+                                 "note": "same call from ordinary pageable host memory (what an arkworks &[Fr] is)"}},
+            "gpu_launches": launches,
+            "phases_ms": {"digits_sort": sum(sort_ms) / len(sort_ms), "bucket_accumulation": acc, "reduce_finish": sum(red_ms) / len(red_ms)},
+            "roofline": {"bound": "hbm", "kernel": "bucket accumulation phase: affine levels (k_aff_prepare, k_aff_invert, k_aff_finish) + work list + k_accumulate, "
+                                                     "timed as one region by CUDA events on the library stream",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_PHASE_TRAFFIC.get(args.logn) if (args.scalars == "uniform" and not args.no_precompute) else None,
+                         "traffic_source": NCU_PHASE_TRAFFIC_SRC.format(logn=args.logn),
+                         "peak_source": peak_src,
+                         "note": "MSM is integer-multiplier bound (SURVEY.md 8d): 6-10 Fq products (276 IMAD.WIDE each) per bucket addition, W additions per term. "
+                                 "The HBM fraction is reported as the contract asks; traffic >> algorithmic bytes because every term gathers one 96-B table point "
+                                 "PER WINDOW and the affine levels stream their intermediate points"},
+            "clocks": clocks,
+        }
     if world == 1 and not args.no_cpu:
         lib = load_oracle()
         threads = host_threads()
@@ -368,27 +428,35 @@ def run_own(args):
         cpu_pt = field.g1_from_limbs(cpu_out.reshape(1, 12))[0]
         line["cpu_baseline"] = {"value": m / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"first 2^{m.bit_length() - 1} terms of the same workload, one MSM, arkworks window c={c_used}, "
-                                          f"one thread per window; CPU and GPU results equal: {cpu_pt == gpu_out}"}
+                                          f"one thread per window, C port built {lib.build_kind}; CPU and GPU results equal: {cpu_pt == gpu_out}"}
         assert cpu_pt == gpu_out, "GPU result differs from the CPU restatement"
-    if world == 1 and args.extras:
-        # the other BASELINE configs on the same box, as extra keys (never allowed to break the headline line)
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_snark
-            import bench_sumcheck
+        if lib.build_kind != "x86-64-v3":   # round 1's portable build next to it, so that the ratio is honest
+            old = load_oracle(native=False)
+            dt_old, _, _ = cpu_msm_timed(old, bases, scal, m, threads)
+            line["cpu_baseline"]["portable_build_value"] = m / dt_old
 
-            srs.free()
-            for p in d_scal:
-                ctx.dev_free(p)
-            rows = []
-            bench_sumcheck.run(ctx, 24, 3, rows.append)
-            line["extra"] = {"sumcheck_2^24": rows, "snark_time_prover": bench_snark.run(ctx, args.extras_logn, 2)}
-        except Exception as exc:  # pragma: no cover
-            line["extra"] = {"error": repr(exc)}
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    srs.free()
+    for p in d_scal:
+        ctx.dev_free(p)
+    del h_scal
+    if not args.no_extras:
+        extra = {}
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extras
+
+        for name, fn in bench_extras.plan(job, args):
+            try:   # an extra must never break the headline line
+                job.barrier()
+                extra[name] = fn()
+            except Exception as exc:  # pragma: no cover
+                extra[name] = {"error": repr(exc)}
+                if world > 1:
+                    raise          # a rank that skips collectives would hang the others: fail loudly instead
+        if rank == 0:
+            line["extra"] = extra
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    job.close()
 
 
 def main():
@@ -396,10 +464,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--logn", type=int, default=20, help="log2 of the number of MSM terms per GPU")
+    ap.add_argument("--logn", type=int, default=24, help="log2 of the number of MSM terms per GPU")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--scalars", default="uniform", choices=["uniform", "equal"])
-    ap.add_argument("--extras", action="store_true", help="also time config 3 (sumcheck 2^24) and config 4 (snark time prover) into an `extra` key")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (skip configs[1], 3, 4, 5 and the strong-scaling MSM)")
     ap.add_argument("--extras-logn", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the table of 2^(c*w) multiples of the SRS")

@@ -63,6 +63,16 @@ SIGNATURES = {
     "gm_msm_stream_finalize": (_i, [_vp, _vp]),
     "gm_msm_stream_free": (_i, [_vp]),
     "gm_g1_sum": (_i, [_vp, _vp, _sz, _vp]),
+    "gm_comm_unique_id": (_i, [_vp]),
+    "gm_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "gm_comm_rank": (_i, [_vp]),
+    "gm_comm_world": (_i, [_vp]),
+    "gm_comm_nccl_version": (_i, []),
+    "gm_comm_barrier": (_i, [_vp]),
+    "gm_comm_allgather": (_i, [_vp, _vp, _sz, _vp]),
+    "gm_msm_g1_sharded": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
+    "gm_msm_g1_sharded_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
+    "gm_msm_stream_finalize_sharded": (_i, [_vp, _vp]),
     "gm_fr_fold": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "gm_fr_fold_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "gm_fr_fold_chain": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
@@ -75,6 +85,10 @@ SIGNATURES = {
     "gm_sumcheck_round": (_sz, [_vp]),
     "gm_sumcheck_set_rounds": (_i, [_vp, _sz, _sz]),
     "gm_sumcheck_final_foldings": (_i, [_vp, _vp, _pi]),
+    "gm_sumcheck_last_device_ms": (C.c_float, [_vp]),
+    "gm_sumcheck_timer_start": (_i, [_vp]),
+    "gm_sumcheck_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
+    "gm_sumcheck_state_dev": (_i, [_vp, _pp, _psz, _pp, _psz]),
     "gm_sumcheck_read_state": (_i, [_vp, _vp, _psz, _vp, _psz, _vp]),
     "gm_sumcheck_free": (_i, [_vp]),
     "gm_dev_alloc": (_i, [_vp, _sz, _pp]),

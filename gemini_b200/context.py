@@ -64,6 +64,7 @@ class Srs:
         return field.g1_from_limbs(self.read(offset, n))
 
     def free(self) -> None:
+        """Safe before or after ``Context.close()``: the handle keeps the C context alive (gm_srs_free)."""
         if self._h:
             lib.gm_srs_free(self._h)
             self._h = C.c_void_p(None)
@@ -86,9 +87,73 @@ class Context:
 
     # -- lifetime ----------------------------------------------------------------------------
     def close(self) -> None:
+        """gm_shutdown: drops this reference.  Handles made from the context (Srs, provers, streams) stay valid and
+        may be freed afterwards in any order; calls that need the context itself raise GM_ERR_STATE."""
         if self._h:
             lib.gm_shutdown(self._h)
             self._h = C.c_void_p(None)
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """gm_comm_init: join the NCCL communicator described by ``unique_id`` (128 bytes from ``comm_unique_id()`` on
+        rank 0, shared out of band)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib.gm_comm_init(self._h, buf, rank, world))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(lib.gm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_torch(self, group=None, device=None) -> None:
+        """Bootstrap through an initialised torch.distributed group: rank 0 draws the id, a broadcast shares it."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        raw = self.comm_unique_id() if rank == 0 else bytes(128)
+        t = torch.tensor(list(raw), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=0, group=group)
+        self.comm_init(bytes(t.cpu().tolist()), rank, world)
+
+    @property
+    def comm_rank(self) -> int:
+        return int(lib.gm_comm_rank(self._h))
+
+    @property
+    def comm_world(self) -> int:
+        return int(lib.gm_comm_world(self._h))
+
+    def comm_barrier(self) -> None:
+        check(lib.gm_comm_barrier(self._h))
+
+    def comm_allgather(self, row: np.ndarray) -> np.ndarray:
+        """one small uint64 row per rank -> (world, len) uint64, identical on every rank (gm_comm_allgather)"""
+        a = np.ascontiguousarray(row, dtype=np.uint64).reshape(-1)
+        out = np.empty((self.comm_world, a.shape[0]), dtype=np.uint64)
+        check(lib.gm_comm_allgather(self._h, _ptr(a), a.nbytes, _ptr(out)))
+        return out
+
+    def msm_sharded(self, srs: "Srs", scalars, base_offset: int = 0, bigint: bool = False, n: Optional[int] = None) -> np.ndarray:
+        """This rank's shard of a multi-GPU msm_unchecked; returns the total over all ranks (gm_msm_g1_sharded)."""
+        out = np.empty(18, dtype=np.uint64)
+        if hasattr(scalars, "data_ptr"):
+            cnt = scalars.numel() * scalars.element_size() // 32 if n is None else n
+            fn = lib.gm_msm_g1_sharded_dev if scalars.is_cuda else lib.gm_msm_g1_sharded
+            check(fn(self._h, srs._h, base_offset, _ptr(scalars), cnt, int(bigint), _ptr(out)))
+            return out
+        arr = as_fr_array(scalars, montgomery=not bigint)
+        cnt = arr.shape[0] if n is None else n
+        check(lib.gm_msm_g1_sharded(self._h, srs._h, base_offset, _ptr(arr), cnt, int(bigint), _ptr(out)))
+        return out
+
+    def msm_sharded_dev(self, srs: "Srs", scalars_dev_ptr: int, n: int, base_offset: int = 0, bigint: bool = False) -> np.ndarray:
+        out = np.empty(18, dtype=np.uint64)
+        check(lib.gm_msm_g1_sharded_dev(self._h, srs._h, base_offset, C.c_void_p(scalars_dev_ptr), n, int(bigint), _ptr(out)))
+        return out
 
     def __del__(self):
         try:

@@ -21,6 +21,21 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace gm
 
+namespace gm {
+void ctx_retain(gm_ctx* ctx) { ctx->refs.fetch_add(1); }
+void ctx_release(gm_ctx* ctx) {
+  if (ctx->refs.fetch_sub(1) != 1) return;
+  // last reference: the scratch went at gm_shutdown, what is left are the streams, events and the pinned block
+  cudaSetDevice(ctx->device);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  delete ctx;
+}
+}  // namespace gm
+
 using namespace gm;
 
 struct ResultSlot {  // device-side result area of a context
@@ -46,6 +61,11 @@ struct gm_msm_stream {
 
 struct gm_sumcheck {
   gm_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;        // private: distinct provers run concurrently (proof.rs:85 drives them from rayon)
+  cudaEvent_t ev[2] = {nullptr, nullptr};  // per-call device time
+  cudaEvent_t tm[2] = {nullptr, nullptr};  // gm_sumcheck_timer_start / _stop
+  float last_ms = 0.f;
+  int slot = -1;                        // pinned 64-byte message slot of the context (-1: own allocation)
   Fr* f[2] = {nullptr, nullptr};
   Fr* g[2] = {nullptr, nullptr};
   int cur = 0;
@@ -102,8 +122,10 @@ int gm_init(int device_id, gm_ctx** out_ctx) {
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) GM_CUDA(cudaEventCreate(&ev));
-  ctx->pinned_bytes = 65536;  // slot 0 (first 4 KB): call results; 64-byte slots after it: sumcheck round messages
+  GM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  ctx->pinned_bytes = 65536;  // first 4 KB: call results; 64-byte slots after it: sumcheck round messages
   GM_CUDA(cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault));
+  for (uint32_t k = (uint32_t)((ctx->pinned_bytes - 4096) / 64); k-- > 0;) ctx->free_slots.push_back(k);
   // short-lived vectors (prover state, DeviceFr temporaries) come from the stream-ordered pool: keep freed
   // blocks cached instead of returning them to the driver at every synchronisation
   cudaMemPool_t pool;
@@ -114,41 +136,47 @@ int gm_init(int device_id, gm_ctx** out_ctx) {
   return GM_OK;
 }
 
+// Drops the caller's reference.  Handles created from this context stay valid (their *_free works in any order
+// relative to gm_shutdown); calls that need the context itself fail with GM_ERR_STATE from here on.  The context
+// pointer must not be passed to gm_shutdown twice.
 int gm_shutdown(gm_ctx* ctx) {
   if (!ctx) return GM_OK;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  ctx->msm.release();
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  if (ctx->d_result) cudaFree(ctx->d_result);
-  if (ctx->d_flush) cudaFree(ctx->d_flush);
-  ctx->fr_red.release();
-  ctx->fr_div.release();
-  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->copy_stream);
-  delete ctx;
+  {
+    std::lock_guard<std::recursive_mutex> guard(ctx->mu);
+    if (ctx->closed.exchange(true)) return GM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    comm_destroy(ctx);
+    ctx->msm.release();
+    if (ctx->d_result) cudaFree(ctx->d_result);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
+    ctx->d_result = ctx->d_flush = nullptr;
+    ctx->fr_red.release();
+    ctx->fr_div.release();
+  }
+  ctx_release(ctx);
   return GM_OK;
 }
 
-uint64_t gm_launch_count(const gm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t gm_launch_count(const gm_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 float gm_last_device_ms(const gm_ctx* ctx, int phase) { return (ctx && phase >= 0 && phase < 4) ? ctx->last_ms[phase] : -1.f; }
 int gm_device_synchronize(gm_ctx* ctx) {
   GM_ARG(ctx, "ctx is NULL");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GM_OK;
 }
 
 int gm_timer_start(gm_ctx* ctx) {
   GM_ARG(ctx, "ctx is NULL");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
   return GM_OK;
 }
 int gm_timer_stop(gm_ctx* ctx, float* out_ms) {
   GM_ARG(ctx && out_ms, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
   GM_CUDA(cudaEventSynchronize(ctx->ev[7]));
   GM_CUDA(cudaEventElapsedTime(out_ms, ctx->ev[6], ctx->ev[7]));
@@ -156,7 +184,7 @@ int gm_timer_stop(gm_ctx* ctx, float* out_ms) {
 }
 int gm_l2_flush(gm_ctx* ctx) {
   GM_ARG(ctx, "ctx is NULL");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
   if (!ctx->d_flush) GM_CUDA(cudaMalloc(&ctx->d_flush, bytes));
   GM_CUDA(cudaMemsetAsync(ctx->d_flush, 0x5a, bytes, ctx->stream));
@@ -166,33 +194,33 @@ int gm_l2_flush(gm_ctx* ctx) {
 // ---- raw buffers -------------------------------------------------------------------------
 int gm_dev_alloc(gm_ctx* ctx, size_t bytes, void** out_dev) {
   GM_ARG(ctx && out_dev, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaMallocAsync(out_dev, bytes ? bytes : 16, ctx->stream));
   return GM_OK;
 }
 int gm_dev_free(gm_ctx* ctx, void* dev) {
   GM_ARG(ctx, "ctx is NULL");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   if (dev) GM_CUDA(cudaFreeAsync(dev, ctx->stream));  // stream ordered: queued work that uses it finishes first
   return GM_OK;
 }
 int gm_dev_upload(gm_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
   GM_ARG(ctx, "ctx is NULL");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GM_OK;
 }
 int gm_dev_download(gm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
   GM_ARG(ctx, "ctx is NULL");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GM_OK;
 }
 int gm_fr_random_dev(gm_ctx* ctx, void* out_dev, size_t n, uint64_t seed) {
   GM_ARG(ctx && (out_dev || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_TRY(fr_random_dev(ctx, reinterpret_cast<Fr*>(out_dev), n, seed));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GM_OK;
@@ -210,6 +238,7 @@ static int srs_alloc(gm_ctx* ctx, size_t n, gm_srs** out) {
     set_error("cudaMalloc of %zu SRS points failed: %s", n, cudaGetErrorString(e));
     return GM_ERR_OOM;
   }
+  ctx_retain(ctx);
   *out = s;
   return GM_OK;
 }
@@ -231,7 +260,7 @@ static int upload_points(gm_ctx* ctx, const void* points, size_t n, size_t strid
 
 int gm_srs_load_g1(gm_ctx* ctx, const void* points, size_t n, size_t stride_bytes, long inf_offset, gm_srs** out_srs) {
   GM_ARG(ctx && out_srs && (points || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   gm_srs* s = nullptr;
   GM_TRY(srs_alloc(ctx, n, &s));
   DevBuf raw;
@@ -250,7 +279,7 @@ int gm_srs_load_g1(gm_ctx* ctx, const void* points, size_t n, size_t stride_byte
 
 int gm_srs_generate_g1(gm_ctx* ctx, size_t n, uint64_t first_multiple, gm_srs** out_srs) {
   GM_ARG(ctx && out_srs, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   gm_srs* s = nullptr;
   GM_TRY(srs_alloc(ctx, n, &s));
   int rc = srs_generate(ctx, n, first_multiple, reinterpret_cast<Affine*>(s->d_points));
@@ -266,7 +295,7 @@ int gm_srs_generate_g1(gm_ctx* ctx, size_t n, uint64_t first_multiple, gm_srs** 
 
 int gm_srs_setup_g1(gm_ctx* ctx, const uint64_t g_xy[12], const uint64_t tau[4], size_t n, gm_srs** out_srs) {
   GM_ARG(ctx && out_srs && g_xy && tau, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   gm_srs* s = nullptr;
   GM_TRY(srs_alloc(ctx, n, &s));
   Affine g;
@@ -292,7 +321,7 @@ int gm_srs_setup_g1(gm_ctx* ctx, const uint64_t g_xy[12], const uint64_t tau[4],
 
 int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** out_srs) {
   GM_ARG(ctx && out_srs && point_xy, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   gm_srs* s = nullptr;
   GM_TRY(srs_alloc(ctx, n, &s));
   Affine p;
@@ -318,7 +347,7 @@ static void srs_drop_tables(gm_srs* srs) {
 
 int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len) {
   GM_ARG(ctx && srs, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   if (srs->n == 0) return GM_OK;
   srs_drop_tables(srs);
   // table 0 covers the whole SRS; tables 1, 2 cover prefixes 8x and 64x shorter (kept while >= 2^12 points)
@@ -373,22 +402,26 @@ size_t gm_srs_len(const gm_srs* srs) { return srs ? srs->n : 0; }
 int gm_srs_read(gm_ctx* ctx, const gm_srs* srs, size_t offset, size_t n, uint64_t* out_xy) {
   GM_ARG(ctx && srs && out_xy, "NULL argument");
   GM_ARG(offset <= srs->n && n <= srs->n - offset, "range outside the SRS");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaMemcpyAsync(out_xy, reinterpret_cast<const Affine*>(srs->d_points) + offset, n * sizeof(Affine),
                           cudaMemcpyDeviceToHost, ctx->stream));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
   return GM_OK;
 }
 
+// Valid before or after gm_shutdown of the context the SRS came from (the handle keeps the context alive).
 int gm_srs_free(gm_srs* srs) {
   if (!srs) return GM_OK;
-  if (srs->ctx) {
-    cudaSetDevice(srs->ctx->device);
-    cudaStreamSynchronize(srs->ctx->stream);
+  gm_ctx* ctx = srs->ctx;
+  {
+    std::lock_guard<std::recursive_mutex> guard(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);   // queued MSMs that read these points finish first
+    if (srs->owned && srs->d_points) cudaFree(srs->d_points);
+    srs_drop_tables(srs);
   }
-  if (srs->owned && srs->d_points) cudaFree(srs->d_points);
-  srs_drop_tables(srs);
   delete srs;
+  ctx_release(ctx);
   return GM_OK;
 }
 
@@ -430,11 +463,22 @@ static MsmBases bases_of_points(const Affine* pts, size_t n) {
   return b;
 }
 
-static int msm_common(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, uint64_t out[18]) {
+// `sharded`: this rank's partial sum is exchanged with the other ranks of the context's communicator (one
+// ncclAllGather of 192-byte XYZZ points on the library stream) and every rank returns the same total.
+static int exchange_partials(gm_ctx* ctx, XYZZ* d_acc) {
+  if (comm_world(ctx) <= 1) return GM_OK;
+  void* d_all = nullptr;
+  GM_TRY(comm_allgather_dev(ctx, d_acc, sizeof(XYZZ), &d_all));
+  return msm_acc_set_sum_xyzz(ctx, d_all, (size_t)comm_world(ctx), sizeof(XYZZ), d_acc);
+}
+
+static int msm_common(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, uint64_t out[18],
+                      bool sharded = false) {
   ResultSlot* slot;
   GM_TRY(ensure_result(ctx, &slot));
   GM_TRY(msm_acc_reset(ctx, &slot->acc));
   GM_TRY(msm_accumulate(ctx, bases, base_offset, d_scalars, n, bigint, &slot->acc));
+  if (sharded) GM_TRY(exchange_partials(ctx, &slot->acc));
   GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
   GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
   GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -448,7 +492,7 @@ int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void
                   int scalars_are_bigint, uint64_t out_jacobian[18]) {
   GM_ARG(ctx && srs && out_jacobian && (scalars_dev || n == 0), "NULL argument");
   GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   n = std::min(n, srs->n - base_offset);  // msm_unchecked truncates to the shorter input
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0,
@@ -459,12 +503,38 @@ int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t
               int scalars_are_bigint, uint64_t out_jacobian[18]) {
   GM_ARG(ctx && srs && out_jacobian && (scalars || n == 0), "NULL argument");
   GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   n = std::min(n, srs->n - base_offset);
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
   if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
+}
+
+// Multi-GPU MSM: `srs` holds THIS rank's contiguous range of the points and `scalars` the matching
+// range of the scalars; every rank calls with its own shard and gets the sum over all ranks.
+int gm_msm_g1_sharded_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
+                          int scalars_are_bigint, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && srs && out_jacobian && (scalars_dev || n == 0), "NULL argument");
+  GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
+  GM_ENTER(ctx);
+  n = std::min(n, srs->n - base_offset);
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), n, scalars_are_bigint != 0,
+                    out_jacobian, /*sharded=*/true);
+}
+
+int gm_msm_g1_sharded(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+                      int scalars_are_bigint, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && srs && out_jacobian && (scalars || n == 0), "NULL argument");
+  GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
+  GM_ENTER(ctx);
+  n = std::min(n, srs->n - base_offset);
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
+  if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian,
+                    /*sharded=*/true);
 }
 
 int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t bases_len, const uint64_t* scalars,
@@ -482,7 +552,7 @@ int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t
 int gm_msm_g1_hostbases(gm_ctx* ctx, const void* points, size_t stride_bytes, long inf_offset, const uint64_t* scalars,
                         size_t n, int scalars_are_bigint, uint64_t out_jacobian[18]) {
   GM_ARG(ctx && out_jacobian && ((points && scalars) || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   MsmScratch& S = ctx->msm;
   GM_TRY(S.bases_tmp.reserve(std::max<size_t>(n, 1) * sizeof(Affine)));
@@ -502,7 +572,7 @@ int gm_msm_g1_hostbases(gm_ctx* ctx, const void* points, size_t stride_bytes, lo
 
 int gm_g1_sum(gm_ctx* ctx, const uint64_t* jacobians, size_t k, uint64_t out_jacobian[18]) {
   GM_ARG(ctx && out_jacobian && (jacobians || k == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   ResultSlot* slot;
   GM_TRY(ensure_result(ctx, &slot));
   GM_TRY(ctx->msm.bases_tmp.reserve(std::max<size_t>(k, 1) * sizeof(Jacobian)));
@@ -529,10 +599,11 @@ static int stream_flush(gm_msm_stream* s) {
 
 int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, gm_msm_stream** out) {
   GM_ARG(ctx && out, "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   gm_msm_stream* s = new (std::nothrow) gm_msm_stream();
   if (!s) return GM_ERR_OOM;
   s->ctx = ctx;
+  ctx_retain(ctx);
   s->srs = srs_or_null;
   s->chunk_cap = chunk_cap;
   cudaError_t e = cudaMalloc(&s->d_acc, sizeof(XYZZ));
@@ -554,7 +625,7 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
                        const uint64_t* scalars, size_t m, int scalars_are_bigint) {
   GM_ARG(s && (scalars || m == 0), "NULL argument");
   gm_ctx* ctx = s->ctx;
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   if (m == 0) return GM_OK;
   MsmBases bases;
   size_t boff = 0;
@@ -604,13 +675,19 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
   return GM_OK;
 }
 
-int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]) {
+static int stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18], bool sharded);
+int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]) { return stream_finalize(s, out_jacobian, false); }
+// streamed MSM of a multi-GPU job (config 5): every rank streamed its own range; the totals are exchanged once, here
+int gm_msm_stream_finalize_sharded(gm_msm_stream* s, uint64_t out_jacobian[18]) { return stream_finalize(s, out_jacobian, true); }
+
+static int stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18], bool sharded) {
   GM_ARG(s && out_jacobian, "NULL argument");
   gm_ctx* ctx = s->ctx;
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   ResultSlot* slot;
   GM_TRY(ensure_result(ctx, &slot));
   GM_TRY(stream_flush(s));
+  if (sharded) GM_TRY(exchange_partials(ctx, s->d_acc));
   GM_TRY(msm_acc_normalize(ctx, s->d_acc, &slot->out));
   GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
   GM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -620,26 +697,29 @@ int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]) {
 
 int gm_msm_stream_free(gm_msm_stream* s) {
   if (!s) return GM_OK;
-  if (s->ctx) {
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    cudaStreamSynchronize(s->ctx->copy_stream);
-  }
-  if (s->d_acc) cudaFree(s->d_acc);
-  for (int k = 0; k < 2; k++) {
-    s->scal[k].release(); s->pts_raw[k].release(); s->pts[k].release();
-    if (k == 0) { s->buckets.release(); s->live.release(); }
-    if (s->copied[k]) cudaEventDestroy(s->copied[k]);
-    if (s->consumed[k]) cudaEventDestroy(s->consumed[k]);
+  gm_ctx* ctx = s->ctx;
+  {
+    std::lock_guard<std::recursive_mutex> guard(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (s->d_acc) cudaFree(s->d_acc);
+    for (int k = 0; k < 2; k++) {
+      s->scal[k].release(); s->pts_raw[k].release(); s->pts[k].release();
+      if (k == 0) { s->buckets.release(); s->live.release(); }
+      if (s->copied[k]) cudaEventDestroy(s->copied[k]);
+      if (s->consumed[k]) cudaEventDestroy(s->consumed[k]);
+    }
   }
   delete s;
+  ctx_release(ctx);
   return GM_OK;
 }
 
 // ---- Fr folds ----------------------------------------------------------------------------
 int gm_fr_fold_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t r[4], void* out_dev) {
   GM_ARG(ctx && r && ((f_dev && out_dev) || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   Fr rr;
   fr_from_u64(rr, r);
   GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -652,7 +732,7 @@ int gm_fr_fold_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t r[4]
 
 int gm_fr_fold(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t r[4], uint64_t* out) {
   GM_ARG(ctx && r && ((f && out) || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   if (n == 0) return GM_OK;
   const size_t half = (n + 1) / 2;
   DevBuf& in = ctx->msm.scalars;
@@ -679,7 +759,7 @@ size_t gm_fr_fold_chain_len(size_t n, size_t k) {
 
 int gm_fr_fold_chain(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t* challenges, size_t k, uint64_t* out_levels) {
   GM_ARG(ctx && ((f && out_levels) || n == 0 || k == 0) && (challenges || k == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   if (n == 0 || k == 0) return GM_OK;
   const size_t tot = gm_fr_fold_chain_len(n, k);
   DevBuf& in = ctx->msm.scalars;
@@ -707,11 +787,16 @@ int gm_fr_fold_chain(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t* c
 }
 
 // ---- sumcheck ----------------------------------------------------------------------------
+// A prover handle owns its stream, events, vectors and pinned message slot: its calls never take the context lock, so
+// several provers can be driven from different host threads at once (Sumcheck::prove_batch, proof.rs:85).
+static Lane lane_of(gm_sumcheck* p) { return Lane{p->stream, &p->ctx->launches}; }
+
 static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_t twist[4], int flavour, gm_sumcheck** out) {
   GM_ARG(flavour == GM_SUMCHECK_GEMINI_TIME || flavour == GM_SUMCHECK_HERRING_F, "unknown flavour");
   gm_sumcheck* p = new (std::nothrow) gm_sumcheck();
   if (!p) return GM_ERR_OOM;
   p->ctx = ctx;
+  ctx_retain(ctx);
   p->nf = f_len;
   p->ng = g_len;
   p->flavour = flavour;
@@ -719,8 +804,12 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
   // time_prover.rs:35-38 (max) vs herring/time_prover.rs:36-39 (min)
   p->tot_rounds = flavour == GM_SUMCHECK_GEMINI_TIME ? ceil_log2(std::max(f_len, g_len)) : ceil_log2(std::min(f_len, g_len));
   const size_t ctas = sc_max_ctas(f_len, g_len);
-  cudaError_t e = cudaSuccess;
-  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMallocAsync(ptr, std::max<size_t>(bytes, 32), ctx->stream); };
+  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+    e = cudaEventCreate(&p->ev[k]);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->tm[k]);
+  }
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMallocAsync(ptr, std::max<size_t>(bytes, 32), p->stream); };
   alloc((void**)&p->f[0], f_len * 32);
   alloc((void**)&p->f[1], ((f_len + 1) / 2) * 32);
   alloc((void**)&p->g[0], g_len * 32);
@@ -728,11 +817,16 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
   alloc((void**)&p->d_partials, ctas * 64);
   alloc((void**)&p->d_ticket, 16);
   alloc((void**)&p->d_out, 64);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ticket, 0, 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ticket, 0, 16, p->stream);
   if (e == cudaSuccess) {
-    const size_t slots = (ctx->pinned_bytes - 4096) / 64;
-    p->h_out = reinterpret_cast<Fr*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 4096 + 64 * (ctx->next_slot++ % slots));
+    std::lock_guard<std::recursive_mutex> guard(ctx->mu);
+    if (!ctx->free_slots.empty()) {
+      p->slot = (int)ctx->free_slots.back();
+      ctx->free_slots.pop_back();
+      p->h_out = reinterpret_cast<Fr*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 4096 + 64 * (size_t)p->slot);
+    }
   }
+  if (e == cudaSuccess && p->slot < 0) e = cudaHostAlloc((void**)&p->h_out, 64, cudaHostAllocDefault);
   if (e != cudaSuccess) {
     set_error("sumcheck alloc: %s", cudaGetErrorString(e));
     gm_sumcheck_free(p);
@@ -742,35 +836,29 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
   return GM_OK;
 }
 
-int gm_sumcheck_new(gm_ctx* ctx, const uint64_t* f, size_t f_len, const uint64_t* g, size_t g_len, const uint64_t twist[4],
-                    int flavour, gm_sumcheck** out) {
-  GM_ARG(ctx && out && twist && (f || f_len == 0) && (g || g_len == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+static int sumcheck_load(gm_ctx* ctx, const void* f, size_t f_len, const void* g, size_t g_len, const uint64_t twist[4], int flavour,
+                         cudaMemcpyKind kind, gm_sumcheck** out) {
   gm_sumcheck* p = nullptr;
-  GM_TRY(sumcheck_alloc(ctx, f_len, g_len, twist, flavour, &p));
-  cudaError_t e = cudaSuccess;
-  if (f_len) e = cudaMemcpyAsync(p->f[0], f, f_len * 32, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && g_len) e = cudaMemcpyAsync(p->g[0], g, g_len * 32, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) {
-    set_error("sumcheck upload: %s", cudaGetErrorString(e));
-    gm_sumcheck_free(p);
-    return GM_ERR_CUDA;
+  {
+    // the only part that touches the context: device selection, the closed check and - for device-resident inputs -
+    // an event that orders this prover's stream after the work already queued on the context's stream
+    GM_ENTER(ctx);
+    GM_TRY(sumcheck_alloc(ctx, f_len, g_len, twist, flavour, &p));
+    cudaError_t e = cudaSuccess;
+    if (kind == cudaMemcpyDeviceToDevice) {
+      e = cudaEventRecord(ctx->ev_join, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(p->stream, ctx->ev_join, 0);
+    }
+    if (e != cudaSuccess) {
+      set_error("sumcheck join: %s", cudaGetErrorString(e));
+      gm_sumcheck_free(p);
+      return GM_ERR_CUDA;
+    }
   }
-  *out = p;
-  return GM_OK;
-}
-
-int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void* g_dev, size_t g_len, const uint64_t twist[4],
-                        int flavour, gm_sumcheck** out) {
-  GM_ARG(ctx && out && twist && (f_dev || f_len == 0) && (g_dev || g_len == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
-  gm_sumcheck* p = nullptr;
-  GM_TRY(sumcheck_alloc(ctx, f_len, g_len, twist, flavour, &p));
   cudaError_t e = cudaSuccess;
-  if (f_len) e = cudaMemcpyAsync(p->f[0], f_dev, f_len * 32, cudaMemcpyDeviceToDevice, ctx->stream);
-  if (e == cudaSuccess && g_len) e = cudaMemcpyAsync(p->g[0], g_dev, g_len * 32, cudaMemcpyDeviceToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (f_len) e = cudaMemcpyAsync(p->f[0], f, f_len * 32, kind, p->stream);
+  if (e == cudaSuccess && g_len) e = cudaMemcpyAsync(p->g[0], g, g_len * 32, kind, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);   // inputs are copied at construction: no aliasing afterwards
   if (e != cudaSuccess) {
     set_error("sumcheck copy: %s", cudaGetErrorString(e));
     gm_sumcheck_free(p);
@@ -780,20 +868,32 @@ int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void
   return GM_OK;
 }
 
+int gm_sumcheck_new(gm_ctx* ctx, const uint64_t* f, size_t f_len, const uint64_t* g, size_t g_len, const uint64_t twist[4],
+                    int flavour, gm_sumcheck** out) {
+  GM_ARG(ctx && out && twist && (f || f_len == 0) && (g || g_len == 0), "NULL argument");
+  return sumcheck_load(ctx, f, f_len, g, g_len, twist, flavour, cudaMemcpyHostToDevice, out);
+}
+
+int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void* g_dev, size_t g_len, const uint64_t twist[4],
+                        int flavour, gm_sumcheck** out) {
+  GM_ARG(ctx && out && twist && (f_dev || f_len == 0) && (g_dev || g_len == 0), "NULL argument");
+  return sumcheck_load(ctx, f_dev, f_len, g_dev, g_len, twist, flavour, cudaMemcpyDeviceToDevice, out);
+}
+
 static bool sc_use_twist(const gm_sumcheck* p, const Fr& tw) {
   return p->flavour == GM_SUMCHECK_GEMINI_TIME && tw != Fr::one();
 }
 
 int gm_sumcheck_fold(gm_sumcheck* p, const uint64_t r[4]) {
   GM_ARG(p && r, "NULL argument");
-  gm_ctx* ctx = p->ctx;
-  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaSetDevice(p->ctx->device));
   Fr rg;
   fr_from_u64(rg, r);
   const Fr rf = rg * p->twist;  // time_prover.rs:77 / herring/time_prover.rs:85
   const int nxt = p->cur ^ 1;
-  GM_TRY(fr_fold_dev(ctx, p->f[p->cur], p->nf, rf, p->f[nxt]));
-  GM_TRY(fr_fold_dev(ctx, p->g[p->cur], p->ng, rg, p->g[nxt]));
+  const Lane ln = lane_of(p);
+  GM_TRY(fr_fold_dev(ln, p->ctx->sm_count, p->f[p->cur], p->nf, rf, p->f[nxt]));
+  GM_TRY(fr_fold_dev(ln, p->ctx->sm_count, p->g[p->cur], p->ng, rg, p->g[nxt]));
   p->cur = nxt;
   p->nf = (p->nf + 1) / 2;
   p->ng = (p->ng + 1) / 2;
@@ -803,42 +903,42 @@ int gm_sumcheck_fold(gm_sumcheck* p, const uint64_t r[4]) {
 
 int gm_sumcheck_next_message(gm_sumcheck* p, const uint64_t* challenge_or_null, uint64_t out_ab[8], int* out_has_msg) {
   GM_ARG(p && out_ab && out_has_msg, "NULL argument");
-  gm_ctx* ctx = p->ctx;
-  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaSetDevice(p->ctx->device));
   if (p->round > p->tot_rounds) {  // time_prover.rs:84 assert
     set_error("next_message: more rounds than needed");
     return GM_ERR_STATE;
   }
-  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   const bool last = p->round == p->tot_rounds;
   if (challenge_or_null && last) {
     GM_TRY(gm_sumcheck_fold(p, challenge_or_null));
   }
   if (last) {
     *out_has_msg = 0;
-    GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     return GM_OK;
   }
+  const Lane ln = lane_of(p);
+  GM_CUDA(cudaEventRecord(p->ev[0], p->stream));
   if (challenge_or_null) {
     Fr rg;
     fr_from_u64(rg, challenge_or_null);
     const Fr rf = rg * p->twist;
     const Fr new_twist = p->twist.sqr();
     const int nxt = p->cur ^ 1;
-    GM_TRY(sc_fold_message_dev(ctx, p->f[p->cur], p->nf, p->g[p->cur], p->ng, rf, rg, p->f[nxt], p->g[nxt], new_twist,
+    GM_TRY(sc_fold_message_dev(ln, p->f[p->cur], p->nf, p->g[p->cur], p->ng, rf, rg, p->f[nxt], p->g[nxt], new_twist,
                                sc_use_twist(p, new_twist), p->d_partials, p->d_ticket, p->d_out));
     p->cur = nxt;
     p->nf = (p->nf + 1) / 2;
     p->ng = (p->ng + 1) / 2;
     p->twist = new_twist;
   } else {
-    GM_TRY(sc_message_dev(ctx, p->f[p->cur], p->nf, p->g[p->cur], p->ng, p->twist, sc_use_twist(p, p->twist), p->d_partials,
+    GM_TRY(sc_message_dev(ln, p->f[p->cur], p->nf, p->g[p->cur], p->ng, p->twist, sc_use_twist(p, p->twist), p->d_partials,
                           p->d_ticket, p->d_out));
   }
-  GM_CUDA(cudaMemcpyAsync(p->h_out, p->d_out, 64, cudaMemcpyDeviceToHost, ctx->stream));
-  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(p->h_out, p->d_out, 64, cudaMemcpyDeviceToHost, p->stream));
+  GM_CUDA(cudaEventRecord(p->ev[1], p->stream));
+  GM_CUDA(cudaStreamSynchronize(p->stream));
   memcpy(out_ab, p->h_out, 64);
+  cudaEventElapsedTime(&p->last_ms, p->ev[0], p->ev[1]);
   p->round++;
   *out_has_msg = 1;
   return GM_OK;
@@ -852,19 +952,33 @@ int gm_sumcheck_set_rounds(gm_sumcheck* p, size_t round, size_t tot_rounds) {
   p->tot_rounds = tot_rounds;
   return GM_OK;
 }
+float gm_sumcheck_last_device_ms(const gm_sumcheck* p) { return p ? p->last_ms : -1.f; }
+int gm_sumcheck_timer_start(gm_sumcheck* p) {
+  GM_ARG(p, "NULL argument");
+  GM_CUDA(cudaSetDevice(p->ctx->device));
+  GM_CUDA(cudaEventRecord(p->tm[0], p->stream));
+  return GM_OK;
+}
+int gm_sumcheck_timer_stop(gm_sumcheck* p, float* out_ms) {
+  GM_ARG(p && out_ms, "NULL argument");
+  GM_CUDA(cudaSetDevice(p->ctx->device));
+  GM_CUDA(cudaEventRecord(p->tm[1], p->stream));
+  GM_CUDA(cudaEventSynchronize(p->tm[1]));
+  GM_CUDA(cudaEventElapsedTime(out_ms, p->tm[0], p->tm[1]));
+  return GM_OK;
+}
 
 int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has) {
   GM_ARG(p && out_fg && out_has, "NULL argument");
-  gm_ctx* ctx = p->ctx;
-  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaSetDevice(p->ctx->device));
   if (p->round != p->tot_rounds) { *out_has = 0; return GM_OK; }
   if (p->nf == 0 || p->ng == 0) {
     set_error("final_foldings on an empty vector");
     return GM_ERR_STATE;
   }
-  GM_CUDA(cudaMemcpyAsync(p->h_out, p->f[p->cur], 32, cudaMemcpyDeviceToHost, ctx->stream));
-  GM_CUDA(cudaMemcpyAsync(p->h_out + 1, p->g[p->cur], 32, cudaMemcpyDeviceToHost, ctx->stream));
-  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  GM_CUDA(cudaMemcpyAsync(p->h_out, p->f[p->cur], 32, cudaMemcpyDeviceToHost, p->stream));
+  GM_CUDA(cudaMemcpyAsync(p->h_out + 1, p->g[p->cur], 32, cudaMemcpyDeviceToHost, p->stream));
+  GM_CUDA(cudaStreamSynchronize(p->stream));
   memcpy(out_fg, p->h_out, 64);
   *out_has = 1;
   return GM_OK;
@@ -872,26 +986,50 @@ int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has)
 
 int gm_sumcheck_read_state(gm_sumcheck* p, uint64_t* out_f, size_t* f_len, uint64_t* out_g, size_t* g_len, uint64_t out_twist[4]) {
   GM_ARG(p, "NULL argument");
-  gm_ctx* ctx = p->ctx;
-  GM_TRY(set_device(ctx));
+  GM_CUDA(cudaSetDevice(p->ctx->device));
   if (f_len) *f_len = p->nf;
   if (g_len) *g_len = p->ng;
   if (out_twist) memcpy(out_twist, p->twist.v, 32);
-  if (out_f && p->nf) GM_CUDA(cudaMemcpyAsync(out_f, p->f[p->cur], p->nf * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_g && p->ng) GM_CUDA(cudaMemcpyAsync(out_g, p->g[p->cur], p->ng * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (out_f && p->nf) GM_CUDA(cudaMemcpyAsync(out_f, p->f[p->cur], p->nf * 32, cudaMemcpyDeviceToHost, p->stream));
+  if (out_g && p->ng) GM_CUDA(cudaMemcpyAsync(out_g, p->g[p->cur], p->ng * 32, cudaMemcpyDeviceToHost, p->stream));
+  GM_CUDA(cudaStreamSynchronize(p->stream));
   return GM_OK;
 }
 
+// device pointers of the current (folded) vectors: hand-off to callers that keep working on the device
+int gm_sumcheck_state_dev(gm_sumcheck* p, const void** out_f_dev, size_t* f_len, const void** out_g_dev, size_t* g_len) {
+  GM_ARG(p, "NULL argument");
+  GM_CUDA(cudaSetDevice(p->ctx->device));
+  GM_CUDA(cudaStreamSynchronize(p->stream));
+  if (out_f_dev) *out_f_dev = p->f[p->cur];
+  if (out_g_dev) *out_g_dev = p->g[p->cur];
+  if (f_len) *f_len = p->nf;
+  if (g_len) *g_len = p->ng;
+  return GM_OK;
+}
+
+// Valid before or after gm_shutdown of the context (the handle keeps it alive).
 int gm_sumcheck_free(gm_sumcheck* p) {
   if (!p) return GM_OK;
-  if (p->ctx) cudaSetDevice(p->ctx->device);
-  cudaStream_t st = p->ctx ? p->ctx->stream : nullptr;
-  for (int k = 0; k < 2; k++) { if (p->f[k]) cudaFreeAsync(p->f[k], st); if (p->g[k]) cudaFreeAsync(p->g[k], st); }
-  if (p->d_partials) cudaFreeAsync(p->d_partials, st);
-  if (p->d_ticket) cudaFreeAsync(p->d_ticket, st);
-  if (p->d_out) cudaFreeAsync(p->d_out, st);
+  gm_ctx* ctx = p->ctx;
+  cudaSetDevice(ctx->device);
+  if (p->stream) {
+    for (int k = 0; k < 2; k++) { if (p->f[k]) cudaFreeAsync(p->f[k], p->stream); if (p->g[k]) cudaFreeAsync(p->g[k], p->stream); }
+    if (p->d_partials) cudaFreeAsync(p->d_partials, p->stream);
+    if (p->d_ticket) cudaFreeAsync(p->d_ticket, p->stream);
+    if (p->d_out) cudaFreeAsync(p->d_out, p->stream);
+    cudaStreamSynchronize(p->stream);
+    cudaStreamDestroy(p->stream);
+  }
+  for (int k = 0; k < 2; k++) { if (p->ev[k]) cudaEventDestroy(p->ev[k]); if (p->tm[k]) cudaEventDestroy(p->tm[k]); }
+  if (p->slot >= 0) {
+    std::lock_guard<std::recursive_mutex> guard(ctx->mu);
+    ctx->free_slots.push_back((uint32_t)p->slot);
+  } else if (p->h_out) {
+    cudaFreeHost(p->h_out);
+  }
   delete p;
+  ctx_release(ctx);
   return GM_OK;
 }
 

@@ -14,21 +14,21 @@ extern "C" {
 
 int gm_dev_memset(gm_ctx* ctx, void* dev, int byte, size_t bytes) {
   GM_ARG(ctx && (dev || bytes == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaMemsetAsync(dev, byte, bytes, ctx->stream));
   return GM_OK;
 }
 
 int gm_dev_copy(gm_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
   GM_ARG(ctx && ((dst_dev && src_dev) || bytes == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   GM_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return GM_OK;
 }
 
 int gm_fr_powers_dev(gm_ctx* ctx, const uint64_t x[4], size_t n, void* out_dev) {
   GM_ARG(ctx && x && (out_dev || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   Fr xx;
   fr_from_u64(xx, x);
   return fr_powers_dev(ctx, xx, n, reinterpret_cast<Fr*>(out_dev));
@@ -36,7 +36,7 @@ int gm_fr_powers_dev(gm_ctx* ctx, const uint64_t x[4], size_t n, void* out_dev) 
 
 int gm_fr_eval_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t x[4], uint64_t out_even_odd[8]) {
   GM_ARG(ctx && x && out_even_odd && (f_dev || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   Fr xx;
   fr_from_u64(xx, x);
   const size_t ctas = sc_max_ctas(n, n);
@@ -57,7 +57,7 @@ int gm_fr_eval_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t x[4]
 int gm_fr_tensor_dev(gm_ctx* ctx, const uint64_t* rho, size_t k, void* out_dev) {
   GM_ARG(ctx && out_dev && (rho || k == 0), "NULL argument");
   GM_ARG(k <= 32, "at most 32 tensor factors");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   Fr r[32];
   for (size_t j = 0; j < k; j++) fr_from_u64(r[j], rho + 4 * j);
   return fr_tensor_dev(ctx, r, (int)k, reinterpret_cast<Fr*>(out_dev));
@@ -65,13 +65,13 @@ int gm_fr_tensor_dev(gm_ctx* ctx, const uint64_t* rho, size_t k, void* out_dev) 
 
 int gm_fr_hadamard_dev(gm_ctx* ctx, const void* a_dev, const void* b_dev, size_t n, void* out_dev) {
   GM_ARG(ctx && ((a_dev && b_dev && out_dev) || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   return fr_hadamard_dev(ctx, reinterpret_cast<const Fr*>(a_dev), reinterpret_cast<const Fr*>(b_dev), n, reinterpret_cast<Fr*>(out_dev));
 }
 
 int gm_fr_axpy_dev(gm_ctx* ctx, void* acc_dev, const void* x_dev, size_t n, const uint64_t c[4]) {
   GM_ARG(ctx && c && ((acc_dev && x_dev) || n == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   Fr cc;
   fr_from_u64(cc, c);
   return fr_axpy_dev(ctx, reinterpret_cast<Fr*>(acc_dev), reinterpret_cast<const Fr*>(x_dev), n, cc);
@@ -80,14 +80,14 @@ int gm_fr_axpy_dev(gm_ctx* ctx, void* acc_dev, const void* x_dev, size_t n, cons
 int gm_fr_spmv_dev(gm_ctx* ctx, const void* rowptr_dev, const void* col_dev, const void* vals_dev, size_t nrows,
                    const void* x_dev, void* y_dev) {
   GM_ARG(ctx && ((rowptr_dev && y_dev) || nrows == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   return fr_spmv_dev(ctx, reinterpret_cast<const uint32_t*>(rowptr_dev), reinterpret_cast<const uint32_t*>(col_dev),
                      reinterpret_cast<const Fr*>(vals_dev), nrows, reinterpret_cast<const Fr*>(x_dev), reinterpret_cast<Fr*>(y_dev));
 }
 
 int gm_fr_div_linear_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t a[4], void* q_dev, uint64_t out_rem[4]) {
   GM_ARG(ctx && a && out_rem && (f_dev || n == 0) && (q_dev || n <= 1), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   Fr aa;
   fr_from_u64(aa, a);
   GM_TRY(ctx->fr_div.reserve((fr_div_scratch_elems(n) + 1) * 32));
@@ -101,7 +101,7 @@ int gm_fr_div_linear_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_
 
 int gm_fr_fold_chain_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t* challenges, size_t k, void* out_levels_dev) {
   GM_ARG(ctx && ((f_dev && out_levels_dev) || n == 0 || k == 0) && (challenges || k == 0), "NULL argument");
-  GM_TRY(set_device(ctx));
+  GM_ENTER(ctx);
   const Fr* src = reinterpret_cast<const Fr*>(f_dev);
   Fr* dst = reinterpret_cast<Fr*>(out_levels_dev);
   size_t len = n;

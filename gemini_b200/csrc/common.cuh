@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -87,22 +89,36 @@ struct MsmScratch {
 
 }  // namespace gm
 
+struct gm_comm;  // NCCL communicator of a multi-GPU job (comm.cu)
+
+// Lifetime: the context is reference counted.  gm_init returns it with one reference (the caller's, dropped by
+// gm_shutdown); every SRS / sumcheck / msm-stream handle holds another.  gm_shutdown marks the context closed and
+// gives its scratch back, but the struct, its streams and events stay valid until the last handle is freed - so a
+// handle may outlive its context (Rust Drop order, Python __del__ order) and its *_free is always safe.
+// Threads: entry points that take a gm_ctx* (MSM, folds, Fr vector helpers, timers) share the context's stream,
+// scratch arena, result slot and events and are serialised by `mu`.  A gm_sumcheck handle owns its stream, events,
+// device buffers and pinned message slot: distinct provers run concurrently from different host threads.
 struct gm_ctx {
+  std::atomic<int> refs{1};
+  std::atomic<bool> closed{false};
+  std::recursive_mutex mu;
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_join = nullptr;   // orders a handle's stream after the work queued on `stream` (disable-timing)
   float last_ms[4] = {0, 0, 0, 0};
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
   int sm_count = 148;
   gm::MsmScratch msm;
-  void* pinned = nullptr;  // small pinned staging block (results, challenges)
+  void* pinned = nullptr;  // pinned staging block: first 4 KB call results, then 64-byte message slots of sumcheck handles
   size_t pinned_bytes = 0;
-  unsigned next_slot = 0;    // round-robin 64-byte pinned slots for sumcheck handles
+  std::vector<uint32_t> free_slots;  // free 64-byte pinned slots (guarded by mu)
   void* d_result = nullptr;  // device result slot (accumulator + normalised output)
   void* d_flush = nullptr;   // 256 MB scratch written by gm_l2_flush
   gm::DevBuf fr_red;         // reduction partials + ticket + result of the Fr vector helpers
   gm::DevBuf fr_div;         // level arrays of the synthetic-division scan
+  gm_comm* comm = nullptr;   // set by gm_comm_init (multi-GPU jobs)
 };
 
 struct gm_srs {
@@ -128,4 +144,25 @@ inline int set_device(const gm_ctx* ctx) {
   GM_CUDA(cudaSetDevice(ctx->device));
   return GM_OK;
 }
+void ctx_retain(gm_ctx* ctx);
+void ctx_release(gm_ctx* ctx);   // destroys the context when the last reference goes
+
+// Where a kernel is queued: the context's shared stream, or the private stream of a sumcheck handle.
+struct Lane {
+  cudaStream_t stream;
+  std::atomic<uint64_t>* launches;
+};
+inline Lane lane_of(gm_ctx* ctx) { return Lane{ctx->stream, &ctx->launches}; }
 }  // namespace gm
+
+// First statement of every entry point that works on the context's shared stream / scratch: takes the context
+// lock for the rest of the call, rejects a context that was shut down, selects its device.
+#define GM_ENTER(ctx)                                                         \
+  std::lock_guard<std::recursive_mutex> _gm_guard((ctx)->mu);                 \
+  do {                                                                        \
+    if ((ctx)->closed.load()) {                                               \
+      ::gm::set_error("the context was shut down");                           \
+      return GM_ERR_STATE;                                                    \
+    }                                                                         \
+    GM_CUDA(cudaSetDevice((ctx)->device));                                    \
+  } while (0)

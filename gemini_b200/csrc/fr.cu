@@ -388,15 +388,22 @@ k_fr_div_down(const Fr* __restrict__ cur, size_t n, Fr a_l, const Fr* __restrict
     (ctx)->launches++;                                              \
   } while (0)
 
-static inline unsigned fold_grid(const gm_ctx* ctx, size_t outputs) {
+#define LAUNCH_LN(ln, kernel, grid, block, shmem, ...)             \
+  do {                                                              \
+    kernel<<<grid, block, shmem, (ln).stream>>>(__VA_ARGS__);       \
+    (*(ln).launches)++;                                             \
+  } while (0)
+
+static inline unsigned fold_grid_sm(int sm_count, size_t outputs) {
   size_t blocks = (outputs + 255) / 256;
-  size_t cap = (size_t)ctx->sm_count * 16;
+  size_t cap = (size_t)sm_count * 16;
   return (unsigned)std::max<size_t>(1, std::min(blocks, cap));
 }
+static inline unsigned fold_grid(const gm_ctx* ctx, size_t outputs) { return fold_grid_sm(ctx->sm_count, outputs); }
 
-int fr_fold_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& r, Fr* d_out) {
+int fr_fold_dev(const Lane& ln, int sm_count, const Fr* d_f, size_t n, const Fr& r, Fr* d_out) {
   if (n == 0) return GM_OK;
-  LAUNCH(ctx, k_fr_fold, fold_grid(ctx, (n + 1) / 2), 256, 0, d_f, n, r, d_out);
+  LAUNCH_LN(ln, k_fr_fold, fold_grid_sm(sm_count, (n + 1) / 2), 256, 0, d_f, n, r, d_out);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
@@ -434,23 +441,23 @@ size_t sc_max_ctas(size_t nf, size_t ng) {
   return std::max<size_t>(1024, (npairs + SC_TILE - 1) / SC_TILE);  // >= the largest grid of any later round
 }
 
-int sc_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
+int sc_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
                    Fr* d_partials, unsigned int* d_ticket, Fr* d_out) {
   const size_t npairs = std::min((nf + 1) / 2, (ng + 1) / 2);
   const int kpt = sc_pairs_per_thread(npairs);
   const unsigned grid = sc_grid(npairs, kpt);
   if (use_twist) {
     PowTable tab = make_pow_table(twist, npairs);
-    LAUNCH(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
+    LAUNCH_LN(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
   } else {
     PowTable tab;  // unused
-    LAUNCH(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
+    LAUNCH_LN(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
   }
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
 
-int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
+int sc_fold_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
                         Fr* d_f_out, Fr* d_g_out, const Fr& new_twist, bool use_twist, Fr* d_partials,
                         unsigned int* d_ticket, Fr* d_out) {
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
@@ -459,11 +466,11 @@ int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, si
   const unsigned grid = sc_grid(npairs, kpt);
   if (use_twist) {
     PowTable tab = make_pow_table(new_twist, npairs);
-    LAUNCH(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
+    LAUNCH_LN(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out);
   } else {
     PowTable tab;
-    LAUNCH(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
+    LAUNCH_LN(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out);
   }
   GM_CUDA(cudaGetLastError());

@@ -6,17 +6,20 @@
 
 namespace gm {
 
-// d_out[i] = d_f[2i] + r * d_f[2i+1]   (asynchronous on ctx->stream)
-int fr_fold_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& r, Fr* d_out);
+// d_out[i] = d_f[2i] + r * d_f[2i+1]   (asynchronous on the lane's stream)
+int fr_fold_dev(const Lane& ln, int sm_count, const Fr* d_f, size_t n, const Fr& r, Fr* d_out);
+inline int fr_fold_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& r, Fr* d_out) {
+  return fr_fold_dev(lane_of(ctx), ctx->sm_count, d_f, n, r, d_out);
+}
 int fr_random_dev(gm_ctx* ctx, Fr* d_out, size_t n, uint64_t seed);
 
 // number of CTA partial slots a prover over vectors of these lengths can ever need
 size_t sc_max_ctas(size_t nf, size_t ng);
 // (a, b) of the current vectors -> d_out[0..1]
-int sc_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
+int sc_message_dev(const Lane& ln, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
                    Fr* d_partials, unsigned int* d_ticket, Fr* d_out);
 // fold f by rf, g by rg into the out buffers and compute the message of the folded vectors
-int sc_fold_message_dev(gm_ctx* ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
+int sc_fold_message_dev(const Lane& ln, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
                         Fr* d_f_out, Fr* d_g_out, const Fr& new_twist, bool use_twist, Fr* d_partials,
                         unsigned int* d_ticket, Fr* d_out);
 

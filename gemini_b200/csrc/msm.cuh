@@ -41,6 +41,14 @@ void msm_describe_plan(size_t n, bool with_table, int sm_count, int out[8]);
 int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);
 int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out);
+// *d_acc = sum of k XYZZ points laid out `stride_bytes` apart (the gathered per-rank partials)
+int msm_acc_set_sum_xyzz(gm_ctx* ctx, const void* d_in, size_t k, size_t stride_bytes, XYZZ* d_acc);
+
+// comm.cu: NCCL communicator of the context (multi-GPU jobs)
+void comm_destroy(gm_ctx* ctx);
+int comm_world(const gm_ctx* ctx);
+int comm_rank(const gm_ctx* ctx);
+int comm_allgather_dev(gm_ctx* ctx, const void* d_send, size_t bytes, void** out_d_all);
 
 int srs_pack(gm_ctx* ctx, const uint8_t* d_raw, size_t n, size_t stride, long inf_offset, Affine* d_out);
 int srs_fill(gm_ctx* ctx, const Affine& p, size_t n, Affine* d_out);

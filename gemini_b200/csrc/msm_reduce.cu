@@ -177,6 +177,16 @@ __global__ void k_add_jacobians(const Jacobian* __restrict__ in, uint32_t k, XYZ
   store_rw(acc, a);
 }
 
+__global__ void k_sum_xyzz(const uint8_t* __restrict__ in, uint32_t k, uint32_t stride, XYZZ* __restrict__ acc) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ a = XYZZ::identity();
+  for (uint32_t i = 0; i < k; i++) {
+    XYZZ b = load_rw(reinterpret_cast<const XYZZ*>(in + (size_t)i * stride));
+    xyzz_add(a, b);
+  }
+  store_rw(acc, a);
+}
+
 // Phase B: bucket reduction (running sums, weights, windows) and *d_acc += result.  `valid[gb] != 0` marks the
 // buckets that hold a point (per-call counts, or the persistent live flags of a stream).
 int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_t* valid, XYZZ* d_acc) {
@@ -228,6 +238,12 @@ int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc) {
 
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc) {
   LAUNCH(ctx, k_add_jacobians, 1, 32, 0, d_in, (uint32_t)k, d_acc);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int msm_acc_set_sum_xyzz(gm_ctx* ctx, const void* d_in, size_t k, size_t stride_bytes, XYZZ* d_acc) {
+  LAUNCH(ctx, k_sum_xyzz, 1, 32, 0, reinterpret_cast<const uint8_t*>(d_in), (uint32_t)k, (uint32_t)stride_bytes, d_acc);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

@@ -61,6 +61,7 @@ k_fb_table(const Affine* __restrict__ bases, Affine* __restrict__ table) {
   }
   Fq xs[GEN_RUN], ys[GEN_RUN], zzs[GEN_RUN], zzzs[GEN_RUN], pref[GEN_RUN];
   Fq run = Fq::one();
+#pragma unroll 1   // compile time: the unrolled run is 16 inlined mixed additions (minutes of ptxas for setup-only code)
   for (int r = 0; r < GEN_RUN; r++) {
     xs[r] = p.x; ys[r] = p.y; zzs[r] = p.zz; zzzs[r] = p.zzz;
     pref[r] = run;
@@ -68,6 +69,7 @@ k_fb_table(const Affine* __restrict__ bases, Affine* __restrict__ table) {
     xyzz_madd(p, b);
   }
   Fq inv = fp_inv(run);
+#pragma unroll 1
   for (int r = GEN_RUN - 1; r >= 0; r--) {
     Affine a;
     if (zzs[r].is_zero()) { a.x = Fq::zero(); a.y = Fq::zero(); }
@@ -90,6 +92,7 @@ k_fb_msm(const Affine* __restrict__ table, const uint32_t* __restrict__ scalars,
   const int cnt = (int)min((size_t)FB_RUN, n - i0);
   Fq xs[FB_RUN], ys[FB_RUN], zzs[FB_RUN], zzzs[FB_RUN], pref[FB_RUN];
   Fq run = Fq::one();
+#pragma unroll 1
   for (int r = 0; r < cnt; r++) {
     Fr s;
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + (i0 + r) * 8);
@@ -108,6 +111,7 @@ k_fb_msm(const Affine* __restrict__ table, const uint32_t* __restrict__ scalars,
     if (!acc.is_identity()) run = run * acc.zzz;
   }
   Fq inv = fp_inv(run);
+#pragma unroll 1
   for (int r = cnt - 1; r >= 0; r--) {
     Affine a;
     if (zzs[r].is_zero()) { a.x = Fq::zero(); a.y = Fq::zero(); }

@@ -1,10 +1,15 @@
-"""Multi-GPU sharding of the MSM: one process per GPU, contiguous point ranges, one exchange.
+"""Multi-GPU sharding: one process per GPU, contiguous point ranges, one exchange.
 
 The reference is single-process; this is the new K7 step.  sum_i s_i P_i over disjoint
 index ranges is independent per rank; the only exchange is the "all-reduce" of the per-rank partial G1
 accumulators.  NCCL has no curve-addition reduction operator, so the all-reduce is realised as an
-all-gather of the 144-byte normalised Jacobian partials followed by world_size - 1 additions done
-identically on every rank (``combine`` = Context.g1_sum on the device).
+all-gather of the partial accumulators followed by world_size - 1 additions done identically on every rank.
+
+The production exchange lives INSIDE the library (``gm_comm_init`` + ``gm_msm_g1_sharded`` /
+``gm_comm_allgather``, gemini_b200/csrc/comm.cu): one ncclAllGather on the library's own stream, no torch and
+no host staging (:class:`LibComm`, ``Context.msm_sharded``).  :class:`TorchComm` runs the same host logic over
+a torch.distributed group - the ``gloo`` CPU tests of this module, and ``allreduce_g1`` for callers that
+already hold normalised partials on the host.
 """
 from __future__ import annotations
 
@@ -66,17 +71,37 @@ def sumcheck_block(n_f: int, n_g: int, rank: int, world: int) -> Tuple[int, int,
     return rank * B, B, L
 
 
-def _gather_rows(row: np.ndarray, group, device) -> np.ndarray:
-    """all-gather one small uint64 row per rank -> (world, len) uint64 (same on every rank)."""
-    import torch
-    import torch.distributed as dist
+class TorchComm:
+    """all-gather of small rows over a torch.distributed group (gloo on CPU, NCCL through torch)"""
 
-    t = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint64).view(np.int64).copy())
-    if device is not None:
-        t = t.to(device)
-    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
-    dist.all_gather(out, t, group=group)
-    return torch.stack(out).cpu().numpy().view(np.uint64)
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allgather(self, row: np.ndarray) -> np.ndarray:
+        """one small uint64 row per rank -> (world, len) uint64 (same on every rank)"""
+        import torch
+        import torch.distributed as dist
+
+        t = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint64).view(np.int64).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return torch.stack(out).cpu().numpy().view(np.uint64)
+
+
+class LibComm:
+    """the library's own NCCL communicator (gm_comm_init): all-gather on the context's stream, no torch"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.rank, self.world = ctx.comm_rank, ctx.comm_world
+
+    def allgather(self, row: np.ndarray) -> np.ndarray:
+        return self.ctx.comm_allgather(row)
 
 
 class ShardedTimeProver:
@@ -94,15 +119,13 @@ class ShardedTimeProver:
     """
 
     def __init__(self, make_local: Callable, f_block: Sequence, g_block: Sequence, twist: int, n_f: int, n_g: int,
-                 group=None, device=None, modulus: int = None):
-        import torch.distributed as dist
-
+                 group=None, device=None, modulus: int = None, comm=None):
         from . import field
 
         self._field = field
         self.R = modulus or field.R
-        self.group, self.device = group, device
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm = comm if comm is not None else TorchComm(group, device)
+        self.rank, self.world = self.comm.rank, self.comm.world
         self.start, self.B, self.L = sumcheck_block(n_f, n_g, self.rank, self.world)
         self.make_local = make_local
         self.twist0 = twist % self.R
@@ -126,7 +149,7 @@ class ShardedTimeProver:
 
     # -- the two exchanges ------------------------------------------------------------------------
     def _combine(self, msg: Tuple[int, int]) -> Tuple[int, int]:
-        rows = _gather_rows(self._field.fr_to_limbs(list(msg), montgomery=False).reshape(-1), self.group, self.device)
+        rows = self.comm.allgather(self._field.fr_to_limbs(list(msg), montgomery=False).reshape(-1))
         a = b = 0
         for r in range(self.world):
             ar, br = self._field.fr_from_limbs(rows[r].reshape(2, 4), montgomery=False)
@@ -137,7 +160,7 @@ class ShardedTimeProver:
     def _start_tail(self) -> None:
         f, g, tw = self.local.state()
         assert len(f) == 1 and len(g) == 1
-        rows = _gather_rows(self._field.fr_to_limbs([f[0], g[0]], montgomery=False).reshape(-1), self.group, self.device)
+        rows = self.comm.allgather(self._field.fr_to_limbs([f[0], g[0]], montgomery=False).reshape(-1))
         vals = [self._field.fr_from_limbs(rows[r].reshape(2, 4), montgomery=False) for r in range(self.world)]
         self.tail = self.make_local([v[0] for v in vals], [v[1] for v in vals], tw)
 

@@ -90,6 +90,12 @@ class _DeviceStream:
     def finalize(self) -> field.Point:
         return field.jacobian_to_affine(self.finalize_raw())
 
+    def finalize_sharded_raw(self) -> np.ndarray:
+        """multi-GPU msm_chunks: every rank streamed its own range, the totals are exchanged once (one all-gather)"""
+        out = np.empty(18, dtype=np.uint64)
+        check(lib.gm_msm_stream_finalize_sharded(self._h, _ptr(out)))
+        return out
+
     def free(self) -> None:
         if self._h:
             lib.gm_msm_stream_free(self._h)

@@ -94,6 +94,18 @@ class _DeviceProver:
         a, b = field.fr_from_limbs(out)
         return (a, b)
 
+    # -- timing (CUDA events on the handle's own stream) ----------------------------------------
+    def timer_start(self) -> None:
+        check(lib.gm_sumcheck_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        check(lib.gm_sumcheck_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def last_device_ms(self) -> float:
+        return float(lib.gm_sumcheck_last_device_ms(self._h))
+
     # -- inspection --------------------------------------------------------------------------
     def lengths(self) -> Tuple[int, int]:
         nf, ng = C.c_size_t(0), C.c_size_t(0)

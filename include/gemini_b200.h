@@ -18,9 +18,15 @@
  *    short_weierstrass::Projective.  Results are returned NORMALISED (Z = 1, identity
  *    = (1,1,0)), so equal group elements are equal byte strings.
  *  - host pointers unless the name ends in _dev (device pointers of the ctx's GPU).
- *  - handles are opaque; distinct handles may be used concurrently from different
- *    host threads (sumcheck provers are driven from rayon workers in
- *    src/subprotocols/sumcheck/proof.rs:85); one handle is never shared mutably.
+ *  - threads: a gm_sumcheck handle owns its CUDA stream, events, vectors and pinned message slot,
+ *    so DISTINCT provers may be driven concurrently from different host threads (the reference
+ *    drives them from rayon workers, src/subprotocols/sumcheck/proof.rs:85); one handle is never
+ *    shared mutably.  Entry points that take a gm_ctx* (MSM, folds, Fr vector helpers, streamed
+ *    MSM pushes) share the context's stream and scratch arena: they are thread-safe but
+ *    serialised by a per-context lock - use one context per thread for concurrent MSMs.
+ *  - lifetime: the context is reference counted; every gm_srs / gm_sumcheck / gm_msm_stream
+ *    handle keeps it alive, so handles may be freed before OR after gm_shutdown (Rust Drop
+ *    order is arbitrary).  After gm_shutdown, calls that need the context return GM_ERR_STATE.
  *  - there is no CPU fallback: without a CUDA device gm_init fails with GM_ERR_CUDA.
  */
 #ifndef GEMINI_B200_H
@@ -46,6 +52,7 @@ typedef struct gm_sumcheck gm_sumcheck;
 
 /* ---- context ---------------------------------------------------------------------- */
 int gm_init(int device_id, gm_ctx** out_ctx);
+/* drops the caller's reference (call once per gm_init); live handles stay valid and freeable */
 int gm_shutdown(gm_ctx* ctx);
 const char* gm_last_error(void);
 int gm_abi_version(void);
@@ -115,8 +122,32 @@ int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes
 int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]);
 int gm_msm_stream_free(gm_msm_stream* s);
 
-/* sum of k Jacobian points (combine of per-GPU partial accumulators after the all-gather) */
+/* sum of k Jacobian points (Commitment / EvaluationProof `Add`, `Sum`: src/kzg/mod.rs:114-126) */
 int gm_g1_sum(gm_ctx* ctx, const uint64_t* jacobians /* k*18 */, size_t k, uint64_t out_jacobian[18]);
+
+/* ---- multi-GPU (the reference is single-process): one process per GPU, one gm_ctx per process, the
+ *      SRS split by contiguous point range.  Rank 0 draws an id (ncclGetUniqueId) and hands the 128 bytes to the
+ *      other ranks out of band (MPI, a TCP store, torch.distributed ...); every rank then calls gm_comm_init.  The
+ *      exchange of an MSM is ONE ncclAllGather of the 192-byte partial accumulators queued on the library's stream
+ *      between the bucket reduction and the normalisation, followed by world-1 curve additions on every rank. ---- */
+#define GM_COMM_ID_BYTES 128
+int gm_comm_unique_id(uint8_t out_id[GM_COMM_ID_BYTES]);
+int gm_comm_init(gm_ctx* ctx, const uint8_t id[GM_COMM_ID_BYTES], int rank, int world);
+int gm_comm_rank(const gm_ctx* ctx);
+int gm_comm_world(const gm_ctx* ctx);
+int gm_comm_nccl_version(void);
+int gm_comm_barrier(gm_ctx* ctx);
+/* every rank contributes `bytes` (<= 256) host bytes; recv_all receives world * bytes in rank order (the 64-byte round
+ * messages and the per-rank last coefficients of the sharded sumcheck) */
+int gm_comm_allgather(gm_ctx* ctx, const void* send, size_t bytes, void* recv_all);
+/* msm_unchecked over ALL ranks' shards: `srs` / `scalars` are this rank's contiguous range; every rank gets the total */
+int gm_msm_g1_sharded(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+                      int scalars_are_bigint, uint64_t out_jacobian[18]);
+int gm_msm_g1_sharded_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
+                          int scalars_are_bigint, uint64_t out_jacobian[18]);
+/* msm_chunks across ranks (config 5): every rank streams its own range; the exchange happens once, here.  The handle
+ * must not be pushed to afterwards. */
+int gm_msm_stream_finalize_sharded(gm_msm_stream* s, uint64_t out_jacobian[18]);
 
 /* ---- Fr folds: misc::fold_polynomial (src/misc.rs:52-56), herring split_fold
  *      (src/herring/time_prover.rs:72-76), tensorcheck::foldings_polynomial
@@ -147,6 +178,12 @@ size_t gm_sumcheck_round(const gm_sumcheck* p);
 /* override the round counters (From<&SpaceProver> for TimeProver, space_prover.rs:269-307) */
 int gm_sumcheck_set_rounds(gm_sumcheck* p, size_t round, size_t tot_rounds);
 int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has);
+/* device time of the last next_message call of THIS handle, and a CUDA-event stopwatch on the handle's stream */
+float gm_sumcheck_last_device_ms(const gm_sumcheck* p);
+int gm_sumcheck_timer_start(gm_sumcheck* p);
+int gm_sumcheck_timer_stop(gm_sumcheck* p, float* out_ms);
+/* device pointers of the current (folded) vectors, valid until the next call on the handle */
+int gm_sumcheck_state_dev(gm_sumcheck* p, const void** out_f_dev, size_t* f_len, const void** out_g_dev, size_t* g_len);
 /* copy out the current (folded) vectors - used by tests and by the elastic hand-off */
 int gm_sumcheck_read_state(gm_sumcheck* p, uint64_t* out_f, size_t* f_len, uint64_t* out_g, size_t* g_len,
                            uint64_t out_twist[4]);

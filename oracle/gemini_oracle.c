@@ -105,6 +105,90 @@ typedef unsigned __int128 u128;
 DEFINE_FIELD(fq, 6, FQ_MOD, 0x89f3fffcfffcfffdULL, FQ_ONE)
 DEFINE_FIELD(fr, 4, FR_MOD, 0xfffffffeffffffffULL, FR_ONE)
 
+/* ---------------------------------------------------------------- mulx / adcx / adox products
+ * arkworks' `asm` feature (ark-ff-asm, Cargo.lock:83-85) emits the Montgomery products of fields up to 6 limbs as
+ * mulx / adcx / adox code; the reference's README runs its benchmarks with `--features asm`.  When this file is
+ * compiled for a host that has BMI2 + ADX (`make native`: -march=native) the same instruction mix is used here: one row
+ * primitive  acc[0..N] += v[0..N-1] * x  with the low halves on the CF chain and the high halves on the OF chain,
+ * interleaved CIOS (row of a * b_i, row of p * m) with the accumulator kept in registers.  The portable build
+ * (x86-64-v3, no ADX) keeps the unsigned __int128 code above. */
+#if defined(__ADX__) && defined(__BMI2__) && !defined(GO_NO_ADX)
+#define GO_HAVE_ADX 1
+#define MAC_ROW6(v, x, a0, a1, a2, a3, a4, a5, a6)                                                                    \
+  do {                                                                                                                \
+    uint64_t lo_, hi_;                                                                                                \
+    __asm__("xorl %k[lo], %k[lo]\n\t"                                                                                 \
+            "mulx 0(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r0]\n\tadox %[hi], %[r1]\n\t"                                \
+            "mulx 8(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r1]\n\tadox %[hi], %[r2]\n\t"                                \
+            "mulx 16(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r2]\n\tadox %[hi], %[r3]\n\t"                               \
+            "mulx 24(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r3]\n\tadox %[hi], %[r4]\n\t"                               \
+            "mulx 32(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r4]\n\tadox %[hi], %[r5]\n\t"                               \
+            "mulx 40(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r5]\n\tadox %[hi], %[r6]\n\t"                               \
+            "movl $0, %k[lo]\n\tadcx %[lo], %[r6]\n\t"                                                               \
+            : [lo] "=&r"(lo_), [hi] "=&r"(hi_), [r0] "+r"(a0), [r1] "+r"(a1), [r2] "+r"(a2), [r3] "+r"(a3), [r4] "+r"(a4), \
+              [r5] "+r"(a5), [r6] "+r"(a6)                                                                            \
+            : [vp] "r"(v), "d"(x), "m"(*(const uint64_t(*)[6])(v))                                                    \
+            : "cc");                                                                                                  \
+  } while (0)
+#define MAC_ROW4(v, x, a0, a1, a2, a3, a4)                                                                            \
+  do {                                                                                                                \
+    uint64_t lo_, hi_;                                                                                                \
+    __asm__("xorl %k[lo], %k[lo]\n\t"                                                                                 \
+            "mulx 0(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r0]\n\tadox %[hi], %[r1]\n\t"                                \
+            "mulx 8(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r1]\n\tadox %[hi], %[r2]\n\t"                                \
+            "mulx 16(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r2]\n\tadox %[hi], %[r3]\n\t"                               \
+            "mulx 24(%[vp]), %[lo], %[hi]\n\tadcx %[lo], %[r3]\n\tadox %[hi], %[r4]\n\t"                               \
+            "movl $0, %k[lo]\n\tadcx %[lo], %[r4]\n\t"                                                               \
+            : [lo] "=&r"(lo_), [hi] "=&r"(hi_), [r0] "+r"(a0), [r1] "+r"(a1), [r2] "+r"(a2), [r3] "+r"(a3), [r4] "+r"(a4) \
+            : [vp] "r"(v), "d"(x), "m"(*(const uint64_t(*)[4])(v))                                                    \
+            : "cc");                                                                                                  \
+  } while (0)
+
+static inline void fq_mul_adx(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
+  uint64_t m;
+#define FQ_STEP(i, c0, c1, c2, c3, c4, c5, c6)           \
+  MAC_ROW6(a, b[i], c0, c1, c2, c3, c4, c5, c6);         \
+  m = c0 * 0x89f3fffcfffcfffdULL;                        \
+  MAC_ROW6(fq_mod, m, c0, c1, c2, c3, c4, c5, c6);       \
+  c0 = 0; /* column done: it becomes the top word of the next step */
+  FQ_STEP(0, t0, t1, t2, t3, t4, t5, t6)
+  FQ_STEP(1, t1, t2, t3, t4, t5, t6, t0)
+  FQ_STEP(2, t2, t3, t4, t5, t6, t0, t1)
+  FQ_STEP(3, t3, t4, t5, t6, t0, t1, t2)
+  FQ_STEP(4, t4, t5, t6, t0, t1, t2, t3)
+  FQ_STEP(5, t5, t6, t0, t1, t2, t3, t4)
+#undef FQ_STEP
+  const uint64_t t[6] = {t6, t0, t1, t2, t3, t4};
+  fq_csub(r, t, 0);
+}
+static inline void fr_mul_adx(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+  uint64_t m;
+#define FR_STEP(i, c0, c1, c2, c3, c4)                   \
+  MAC_ROW4(a, b[i], c0, c1, c2, c3, c4);                 \
+  m = c0 * 0xfffffffeffffffffULL;                        \
+  MAC_ROW4(fr_mod, m, c0, c1, c2, c3, c4);               \
+  c0 = 0;
+  FR_STEP(0, t0, t1, t2, t3, t4)
+  FR_STEP(1, t1, t2, t3, t4, t0)
+  FR_STEP(2, t2, t3, t4, t0, t1)
+  FR_STEP(3, t3, t4, t0, t1, t2)
+#undef FR_STEP
+  const uint64_t t[4] = {t4, t0, t1, t2};
+  fr_csub(r, t, 0);
+}
+#define fq_mul fq_mul_adx
+#define fr_mul fr_mul_adx
+#endif
+const char* go_build_kind(void) {
+#ifdef GO_HAVE_ADX
+  return "mulx/adcx/adox";
+#else
+  return "portable u128";
+#endif
+}
+
 static void fq_inv(uint64_t* r, const uint64_t* a) { /* a^(q-2) */
   uint64_t e[6];
   memcpy(e, fq_mod, sizeof(e));

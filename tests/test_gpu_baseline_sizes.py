@@ -1,0 +1,175 @@
+"""Parity at the sizes BASELINE.json quotes (n = 2^24 MSM, 2^24-element sumcheck) and on the reference's DEFAULT,
+degenerate inputs at 2^20 (all-equal scalars: dummy_r1cs, src/circuit.rs:349-365; all-identical bases: DummyStreamer,
+examples/snark.rs:62-65).  At these sizes the naive oracle is out of reach, so the checks are
+
+  * closed forms: bases P_i = [i+1]G generated on the device make sum_i s_i P_i = [sum_i s_i (i+1) mod r] G, one scalar
+    multiplication of the big-integer oracle (the weighted sum is evaluated exactly with numpy on 16-bit sub-limbs);
+  * the single-threaded C restatement of TimeProver (oracle/gemini_oracle.c::go_sumcheck_time, itself held to
+    oracle/pyref.py and the golden vectors by tests/test_oracle_c.py / test_golden_cpu.py): EVERY round message and
+    the final foldings, fixed challenge list, twist in {1, random}."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import gemini_b200 as gm
+import pyref as o
+from gemini_b200 import field
+from gemini_b200._lib import check, lib
+from test_oracle_c import clib  # noqa: F401  (fixture)
+from util import R, fr_random_limbs
+
+pytestmark = pytest.mark.gpu
+
+RINV = pow(1 << 256, -1, R)
+
+
+def weighted_sum(limbs: np.ndarray, first_weight: int = 1) -> int:
+    """sum_i value_i * (first_weight + i) over (n,4) uint64 limb rows, exact (16-bit sub-limbs, chunks of 2^20 rows:
+    16 + 25 + 20 bits < 64)."""
+    n = limbs.shape[0]
+    total = 0
+    step = 1 << 20
+    for s0 in range(0, n, step):
+        blk = limbs[s0:s0 + step]
+        w = np.arange(first_weight + s0, first_weight + s0 + blk.shape[0], dtype=np.uint64)
+        for j in range(4):
+            for h in range(4):
+                sub = (blk[:, j] >> np.uint64(16 * h)) & np.uint64(0xFFFF)
+                total += int((sub * w).sum(dtype=np.uint64)) << (64 * j + 16 * h)
+    return total
+
+
+def plain_sum(limbs: np.ndarray) -> int:
+    total = 0
+    for j in range(4):
+        for h in range(2):
+            sub = (limbs[:, j] >> np.uint64(32 * h)) & np.uint64(0xFFFFFFFF)
+            total += int(sub.sum(dtype=np.uint64)) << (64 * j + 32 * h)
+    return total
+
+
+def test_weighted_sum_helper():
+    limbs = fr_random_limbs(3000, 77)
+    vals = [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in limbs]
+    assert weighted_sum(limbs, 5) == sum(v * (5 + i) for i, v in enumerate(vals))
+    assert plain_sum(limbs) == sum(vals)
+
+
+@pytest.mark.parametrize("with_table", [True, False])
+def test_msm_2_24_closed_form(ctx, with_table):
+    """north-star size: one MSM over 2^24 distinct bases, with and without the precomputed table"""
+    n = 1 << 24
+    srs = ctx.srs_generate(n, first_multiple=1)
+    if with_table:
+        srs.precompute()
+    d = ctx.dev_alloc(n * 32)
+    ctx.fr_random_dev(d, n, 2024)
+    limbs = fr_random_limbs(n, 2024)
+    # the device generator and its numpy restatement agree on the (sampled) scalars
+    assert np.array_equal(ctx.dev_download(d + 32 * (n - 4096), 4096 * 32).reshape(4096, 4), limbs[n - 4096:])
+    tot = weighted_sum(limbs) % R * RINV % R
+    got = ctx.msm_dev(srs, d, n)
+    assert field.jacobian_to_affine(got) == o.g1_mul(o.G1_GEN, tot)
+    # the host entry point (H2D inside the call) returns the same bytes
+    assert np.array_equal(ctx.msm(srs, limbs), got)
+    # a prefix that is not a power of two, against the same key
+    m = (1 << 23) + 12345
+    tot_m = weighted_sum(limbs[:m]) % R * RINV % R
+    assert field.jacobian_to_affine(ctx.msm_dev(srs, d, m)) == o.g1_mul(o.G1_GEN, tot_m)
+    ctx.dev_free(d)
+    srs.free()
+
+
+@pytest.mark.parametrize("with_table", [True, False])
+def test_msm_2_20_all_equal_scalars(ctx, with_table):
+    """dummy_r1cs: every scalar identical -> every window has ONE bucket holding all 2^20 points"""
+    n = 1 << 20
+    srs = ctx.srs_generate(n, first_multiple=1)
+    if with_table:
+        srs.precompute()
+    s = fr_random_limbs(1, 4711)
+    sv = (int(s[0, 0]) | int(s[0, 1]) << 64 | int(s[0, 2]) << 128 | int(s[0, 3]) << 192) * RINV % R
+    scal = np.ascontiguousarray(np.broadcast_to(s, (n, 4)))
+    want = o.g1_mul(o.G1_GEN, sv * (n * (n + 1) // 2) % R)
+    assert field.jacobian_to_affine(ctx.msm(srs, scal)) == want
+    srs.free()
+
+
+@pytest.mark.parametrize("with_table", [True, False])
+def test_msm_2_20_all_identical_bases(ctx, with_table):
+    """elastic example: DummyStreamer(G1::generator(), n) -> every bucket addition is P + P or kP + P"""
+    n = 1 << 20
+    srs = ctx.srs_fill(o.G1_GEN, n)
+    if with_table:
+        srs.precompute()
+    limbs = fr_random_limbs(n, 815)
+    want = o.g1_mul(o.G1_GEN, plain_sum(limbs) % R * RINV % R)
+    assert field.jacobian_to_affine(ctx.msm(srs, limbs)) == want
+    # and both degeneracies at once (the elastic example's actual input: equal bases AND equal scalars)
+    s = limbs[:1]
+    sv = (int(s[0, 0]) | int(s[0, 1]) << 64 | int(s[0, 2]) << 128 | int(s[0, 3]) << 192) * RINV % R
+    scal = np.ascontiguousarray(np.broadcast_to(s, (n, 4)))
+    assert field.jacobian_to_affine(ctx.msm(srs, scal)) == o.g1_mul(o.G1_GEN, sv * n % R)
+    srs.free()
+
+
+def _device_transcript(ctx, d_f, nf, d_g, ng, twist_limbs, chal, flavour=0):
+    h = C.c_void_p()
+    check(lib.gm_sumcheck_new_dev(ctx._h, C.c_void_p(d_f), nf, C.c_void_p(d_g), ng, C.c_void_p(twist_limbs.ctypes.data), flavour, C.byref(h)))
+    out = np.empty(8, dtype=np.uint64)
+    has = C.c_int(0)
+    msgs = []
+    check(lib.gm_sumcheck_next_message(h, None, C.c_void_p(out.ctypes.data), C.byref(has)))
+    k = 0
+    while has.value:
+        msgs.append(out.copy())
+        check(lib.gm_sumcheck_next_message(h, C.c_void_p(chal[k].ctypes.data), C.c_void_p(out.ctypes.data), C.byref(has)))
+        k += 1
+    fin = np.empty(8, dtype=np.uint64)
+    check(lib.gm_sumcheck_final_foldings(h, C.c_void_p(fin.ctypes.data), C.byref(has)))
+    assert has.value == 1
+    lib.gm_sumcheck_free(h)
+    return np.stack(msgs), fin
+
+
+@pytest.mark.parametrize("nf,ng", [(1 << 24, 1 << 24), ((1 << 24) + 1, (1 << 24) + 1), (1 << 24, 1 << 20)])
+@pytest.mark.parametrize("twist_seed", [None, 5])
+def test_time_prover_2_24_every_round(ctx, clib, nf, ng, twist_seed):  # noqa: F811
+    """BASELINE config 3 size (and the ragged shapes SURVEY.md 8d names): the whole transcript of TimeProver,
+    message by message, against the C restatement on the same device-generated inputs"""
+    d_f, d_g = ctx.dev_alloc(nf * 32), ctx.dev_alloc(ng * 32)
+    ctx.fr_random_dev(d_f, nf, 101)
+    ctx.fr_random_dev(d_g, ng, 202)
+    f = ctx.dev_download(d_f, nf * 32).reshape(nf, 4)
+    g = ctx.dev_download(d_g, ng * 32).reshape(ng, 4)
+    twist = field.fr_to_limbs([1]) if twist_seed is None else fr_random_limbs(1, twist_seed)
+    rounds = 25
+    chal = fr_random_limbs(rounds + 1, 303)
+    msgs, fin = _device_transcript(ctx, d_f, nf, d_g, ng, twist, [chal[k:k + 1] for k in range(rounds + 1)])
+    ctx.dev_free(d_f)
+    ctx.dev_free(d_g)
+    want_msgs = np.zeros((rounds + 1, 8), dtype=np.uint64)
+    want_fin = np.zeros(8, dtype=np.uint64)
+    k = clib.go_sumcheck_time(f.ctypes.data, nf, g.ctypes.data, ng, twist.ctypes.data, chal.ctypes.data, rounds + 1, want_msgs.ctypes.data,
+                              want_fin.ctypes.data)
+    assert k == msgs.shape[0] == o.ark_log2(max(nf, ng))
+    for r in range(k):
+        assert np.array_equal(msgs[r], want_msgs[r]), f"round {r} message differs"
+    assert np.array_equal(fin, want_fin)
+
+
+def test_fold_2_24_against_c_port(ctx, clib):  # noqa: F811
+    n = (1 << 24) + 3
+    d_f, d_o = ctx.dev_alloc(n * 32), ctx.dev_alloc(((n + 1) // 2) * 32)
+    ctx.fr_random_dev(d_f, n, 9)
+    f = ctx.dev_download(d_f, n * 32).reshape(n, 4)
+    r = fr_random_limbs(1, 10)
+    check(lib.gm_fr_fold_dev(ctx._h, C.c_void_p(d_f), n, C.c_void_p(r.ctypes.data), C.c_void_p(d_o)))
+    got = ctx.dev_download(d_o, ((n + 1) // 2) * 32).reshape(-1, 4)
+    want = np.zeros(((n + 1) // 2, 4), dtype=np.uint64)
+    clib.go_fr_fold.restype = None
+    clib.go_fr_fold(f.ctypes.data, n, r.ctypes.data, want.ctypes.data)
+    assert np.array_equal(got, want)
+    ctx.dev_free(d_f)
+    ctx.dev_free(d_o)

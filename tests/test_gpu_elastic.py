@@ -1,9 +1,5 @@
-"""STAGED (not collected: the file name does not start with test_): parity of the device elastic prover composition
-(gemini_b200.snark.new_elastic) against the oracle, to be renamed to test_gpu_elastic.py once it has passed on a GPU.
-
-    python -m pytest tests/staged_gpu_elastic.py -q        # on a GPU box
-
-Mirrors the reference's strongest test (src/snark/tests.rs:13-58): elastic proof == time proof."""
+"""Parity of the device elastic prover composition (gemini_b200.snark.new_elastic, BASELINE config 5's prover) against
+the oracle.  Mirrors the reference's strongest test (src/snark/tests.rs:13-58): elastic proof == time proof."""
 import random
 
 import pytest

@@ -99,3 +99,32 @@ def test_c_sumcheck(clib, nf, ng):
     got = fr_i(out[:rounds])
     assert [(got[2 * i], got[2 * i + 1]) for i in range(rounds)] == msgs
     assert tuple(fr_i(fin)) == final
+
+
+def test_native_adx_build_agrees_with_portable(clib):
+    """`make -C oracle native` (mulx / adcx / adox products when the host has BMI2 + ADX - the build bench.py times as the
+    CPU baseline) must return exactly what the portable build returns."""
+    import subprocess
+
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["make", "-C", odir, "native"], check=True, stdout=subprocess.DEVNULL)
+    nat = C.CDLL(os.path.join(odir, "_build", "libgemini_oracle_native.so"))
+    nat.go_build_kind.restype = C.c_char_p
+    nat.go_msm_g1.restype = C.c_int
+    nat.go_msm_g1.argtypes = clib.go_msm_g1.argtypes
+    nat.go_sumcheck_time.restype = C.c_size_t
+    nat.go_sumcheck_time.argtypes = clib.go_sumcheck_time.argtypes
+    n = 3000
+    bases, scalars = g1_l(rand_points(n, 70)), fr_l(rand_scalars(n, 71))
+    a, b = np.zeros(12, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+    clib.go_msm_g1(bases.ctypes.data, scalars.ctypes.data, n, 0, 4, a.ctypes.data)
+    nat.go_msm_g1(bases.ctypes.data, scalars.ctypes.data, n, 0, 4, b.ctypes.data)
+    assert np.array_equal(a, b), nat.go_build_kind()
+    f, g = fr_l(rand_scalars(1000, 72)), fr_l(rand_scalars(777, 73))
+    tw, ch = fr_l(rand_scalars(1, 74)), fr_l(rand_scalars(12, 75))
+    outs = []
+    for lib in (clib, nat):
+        msgs, fin = np.zeros((12, 8), dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+        k = lib.go_sumcheck_time(f.ctypes.data, 1000, g.ctypes.data, 777, tw.ctypes.data, ch.ctypes.data, 12, msgs.ctypes.data, fin.ctypes.data)
+        outs.append((k, msgs.copy(), fin.copy()))
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])

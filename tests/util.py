@@ -47,6 +47,7 @@ def fr_random_limbs(n: int, seed: int) -> np.ndarray:
         idx = np.arange(4 * n, dtype=np.uint64) + np.uint64(seed)
         w = splitmix64(idx).reshape(n, 4)
     w[:, 3] &= np.uint64(0x7FFFFFFFFFFFFFFF)
+    w = np.ascontiguousarray(w)
     r_l = [np.uint64((R >> (64 * j)) & M64) for j in range(4)]
     # lexicographic compare (most significant limb first) to find values >= r
     ge = np.zeros(n, dtype=bool)
@@ -55,9 +56,20 @@ def fr_random_limbs(n: int, seed: int) -> np.ndarray:
         ge |= eq & (w[:, j] > r_l[j])
         eq &= w[:, j] == r_l[j]
     ge |= eq
-    for i in np.nonzero(ge)[0]:
-        v = sum(int(w[i, j]) << (64 * j) for j in range(4)) - R
-        w[i] = [(v >> (64 * j)) & M64 for j in range(4)]
+    # values >= r: subtract r limb by limb (borrow chain) on the selected rows
+    sel = np.nonzero(ge)[0]
+    if sel.size:
+        sub = w[sel]
+        borrow = np.zeros(sel.size, dtype=np.uint64)
+        for j in range(4):
+            a = sub[:, j]
+            t = a - r_l[j]
+            b1 = (a < r_l[j]).astype(np.uint64)
+            t2 = t - borrow
+            b2 = (t < borrow).astype(np.uint64)
+            sub[:, j] = t2
+            borrow = b1 | b2
+        w[sel] = sub
     return w
 
 
