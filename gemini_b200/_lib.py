@@ -60,6 +60,7 @@ SIGNATURES = {
     "gm_msm_g1_hostbases": (_i, [_vp, _vp, _sz, _l, _vp, _sz, _i, _vp]),
     "gm_msm_stream_new": (_i, [_vp, _vp, _sz, _pp]),
     "gm_msm_stream_push": (_i, [_vp, _vp, _sz, _l, _sz, _vp, _sz, _i]),
+    "gm_msm_stream_push_dev": (_i, [_vp, _sz, _vp, _sz, _i]),
     "gm_msm_stream_finalize": (_i, [_vp, _vp]),
     "gm_msm_stream_free": (_i, [_vp]),
     "gm_g1_sum": (_i, [_vp, _vp, _sz, _vp]),
@@ -79,6 +80,8 @@ SIGNATURES = {
     "gm_fr_fold_chain_len": (_sz, [_sz, _sz]),
     "gm_sumcheck_new": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _i, _pp]),
     "gm_sumcheck_new_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _i, _pp]),
+    "gm_sumcheck_new_ex": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _i, _i, _pp]),
+    "gm_sumcheck_set_flavour": (_i, [_vp, _i]),
     "gm_sumcheck_next_message": (_i, [_vp, _vp, _vp, _pi]),
     "gm_sumcheck_fold": (_i, [_vp, _vp]),
     "gm_sumcheck_rounds": (_sz, [_vp]),
@@ -98,6 +101,7 @@ SIGNATURES = {
     "gm_fr_random_dev": (_i, [_vp, _vp, _sz, _u64]),
     "gm_dev_memset": (_i, [_vp, _vp, _i, _sz]),
     "gm_dev_copy": (_i, [_vp, _vp, _vp, _sz]),
+    "gm_fr_reverse_dev": (_i, [_vp, _vp, _sz, _vp]),
     "gm_fr_powers_dev": (_i, [_vp, _vp, _sz, _vp]),
     "gm_fr_eval_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "gm_fr_tensor_dev": (_i, [_vp, _vp, _sz, _vp]),

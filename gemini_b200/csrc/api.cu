@@ -621,6 +621,33 @@ int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, 
   return GM_OK;
 }
 
+// scalars already resident on the device (the quotients and fold levels of the elastic prover never leave HBM):
+// bases are the SRS range [base_offset, base_offset + m); no staging copy, the chunk is consumed in place
+int gm_msm_stream_push_dev(gm_msm_stream* s, size_t base_offset, const void* scalars_dev, size_t m, int scalars_are_bigint) {
+  GM_ARG(s && (scalars_dev || m == 0), "NULL argument");
+  gm_ctx* ctx = s->ctx;
+  GM_ENTER(ctx);
+  if (m == 0) return GM_OK;
+  GM_ARG(s->srs != nullptr, "stream has no SRS");
+  GM_ARG(base_offset <= s->srs->n && m <= s->srs->n - base_offset, "base range outside the SRS");
+  const MsmBases bases = bases_of_srs(s->srs, base_offset, m, /*full_table_only=*/true);
+  if (s->plan_set && (!s->plan_srs || m > std::max<size_t>(s->chunk_cap, 1))) GM_TRY(stream_flush(s));
+  if (!s->plan_set) {
+    s->plan = msm_stream_plan(bases, std::max(s->chunk_cap, m));
+    s->chunk_cap = std::max(s->chunk_cap, m);
+    s->plan_srs = true;
+    s->plan_set = true;
+    const size_t M = msm_plan_buckets(s->plan);
+    GM_TRY(s->buckets.reserve(M * sizeof(XYZZ)));
+    GM_TRY(s->live.reserve(M * 4));
+    GM_CUDA(cudaMemsetAsync(s->live.p, 0, M * 4, ctx->stream));
+  }
+  GM_TRY(msm_stream_push(ctx, bases, base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), m, scalars_are_bigint != 0, s->plan,
+                         s->buckets.as<XYZZ>(), s->live.as<uint32_t>()));
+  s->dirty = true;
+  return GM_OK;
+}
+
 int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes, long inf_offset, size_t base_offset,
                        const uint64_t* scalars, size_t m, int scalars_are_bigint) {
   GM_ARG(s && (scalars || m == 0), "NULL argument");
@@ -792,7 +819,7 @@ int gm_fr_fold_chain(gm_ctx* ctx, const uint64_t* f, size_t n, const uint64_t* c
 static Lane lane_of(gm_sumcheck* p) { return Lane{p->stream, &p->ctx->launches}; }
 
 static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_t twist[4], int flavour, gm_sumcheck** out) {
-  GM_ARG(flavour == GM_SUMCHECK_GEMINI_TIME || flavour == GM_SUMCHECK_HERRING_F, "unknown flavour");
+  GM_ARG(flavour == GM_SUMCHECK_GEMINI_TIME || flavour == GM_SUMCHECK_HERRING_F || flavour == GM_SUMCHECK_GEMINI_SPACE, "unknown flavour");
   gm_sumcheck* p = new (std::nothrow) gm_sumcheck();
   if (!p) return GM_ERR_OOM;
   p->ctx = ctx;
@@ -801,7 +828,7 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
   p->ng = g_len;
   p->flavour = flavour;
   fr_from_u64(p->twist, twist);
-  // time_prover.rs:35-38 (max) vs herring/time_prover.rs:36-39 (min)
+  // time_prover.rs:35-38 (max) vs herring/time_prover.rs:36-39 and space_prover.rs:76-79 (min)
   p->tot_rounds = flavour == GM_SUMCHECK_GEMINI_TIME ? ceil_log2(std::max(f_len, g_len)) : ceil_log2(std::min(f_len, g_len));
   const size_t ctas = sc_max_ctas(f_len, g_len);
   cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
@@ -837,7 +864,7 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
 }
 
 static int sumcheck_load(gm_ctx* ctx, const void* f, size_t f_len, const void* g, size_t g_len, const uint64_t twist[4], int flavour,
-                         cudaMemcpyKind kind, gm_sumcheck** out) {
+                         cudaMemcpyKind kind, gm_sumcheck** out, bool big_endian = false) {
   gm_sumcheck* p = nullptr;
   {
     // the only part that touches the context: device selection, the closed check and - for device-resident inputs -
@@ -858,6 +885,13 @@ static int sumcheck_load(gm_ctx* ctx, const void* f, size_t f_len, const void* g
   cudaError_t e = cudaSuccess;
   if (f_len) e = cudaMemcpyAsync(p->f[0], f, f_len * 32, kind, p->stream);
   if (e == cudaSuccess && g_len) e = cudaMemcpyAsync(p->g[0], g, g_len * 32, kind, p->stream);
+  if (e == cudaSuccess && big_endian) {
+    // streams arrive highest-degree first (space_prover.rs:38-58): the prover's own copies are reversed in place
+    const Lane ln = lane_of(p);
+    int rc = fr_reverse_dev(ln, ctx->sm_count, p->f[0], f_len, p->f[0]);
+    if (rc == GM_OK) rc = fr_reverse_dev(ln, ctx->sm_count, p->g[0], g_len, p->g[0]);
+    if (rc != GM_OK) { gm_sumcheck_free(p); return rc; }
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);   // inputs are copied at construction: no aliasing afterwards
   if (e != cudaSuccess) {
     set_error("sumcheck copy: %s", cudaGetErrorString(e));
@@ -880,8 +914,25 @@ int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void
   return sumcheck_load(ctx, f_dev, f_len, g_dev, g_len, twist, flavour, cudaMemcpyDeviceToDevice, out);
 }
 
+int gm_sumcheck_new_ex(gm_ctx* ctx, const void* f, size_t f_len, const void* g, size_t g_len, const uint64_t twist[4], int flavour,
+                       int input_flags, gm_sumcheck** out) {
+  GM_ARG(ctx && out && twist && (f || f_len == 0) && (g || g_len == 0), "NULL argument");
+  GM_ARG((input_flags & ~(GM_INPUT_DEVICE | GM_INPUT_BIG_ENDIAN)) == 0, "unknown input flag");
+  return sumcheck_load(ctx, f, f_len, g, g_len, twist, flavour, (input_flags & GM_INPUT_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       out, (input_flags & GM_INPUT_BIG_ENDIAN) != 0);
+}
+
+// From<&SpaceProver> for TimeProver (space_prover.rs:269-307) / ElasticProver::fold (elastic_prover.rs:44-57): the folded
+// vectors are already resident, only the flavour (final_foldings semantics) changes; round counters are kept
+int gm_sumcheck_set_flavour(gm_sumcheck* p, int flavour) {
+  GM_ARG(p, "NULL argument");
+  GM_ARG(flavour == GM_SUMCHECK_GEMINI_TIME || flavour == GM_SUMCHECK_HERRING_F || flavour == GM_SUMCHECK_GEMINI_SPACE, "unknown flavour");
+  p->flavour = flavour;
+  return GM_OK;
+}
+
 static bool sc_use_twist(const gm_sumcheck* p, const Fr& tw) {
-  return p->flavour == GM_SUMCHECK_GEMINI_TIME && tw != Fr::one();
+  return p->flavour != GM_SUMCHECK_HERRING_F && tw != Fr::one();
 }
 
 int gm_sumcheck_fold(gm_sumcheck* p, const uint64_t r[4]) {
@@ -976,8 +1027,11 @@ int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has)
     set_error("final_foldings on an empty vector");
     return GM_ERR_STATE;
   }
-  GM_CUDA(cudaMemcpyAsync(p->h_out, p->f[p->cur], 32, cudaMemcpyDeviceToHost, p->stream));
-  GM_CUDA(cudaMemcpyAsync(p->h_out + 1, p->g[p->cur], 32, cudaMemcpyDeviceToHost, p->stream));
+  // TimeProver / herring: f[0], g[0] (time_prover.rs:135-137); SpaceProver: the HEAD of the folded big-endian streams
+  // (space_prover.rs:260-266) = the last coefficient of the resident little-endian vectors
+  const bool space = p->flavour == GM_SUMCHECK_GEMINI_SPACE;
+  GM_CUDA(cudaMemcpyAsync(p->h_out, p->f[p->cur] + (space ? p->nf - 1 : 0), 32, cudaMemcpyDeviceToHost, p->stream));
+  GM_CUDA(cudaMemcpyAsync(p->h_out + 1, p->g[p->cur] + (space ? p->ng - 1 : 0), 32, cudaMemcpyDeviceToHost, p->stream));
   GM_CUDA(cudaStreamSynchronize(p->stream));
   memcpy(out_fg, p->h_out, 64);
   *out_has = 1;

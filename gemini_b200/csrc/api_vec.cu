@@ -26,6 +26,12 @@ int gm_dev_copy(gm_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
   return GM_OK;
 }
 
+int gm_fr_reverse_dev(gm_ctx* ctx, const void* in_dev, size_t n, void* out_dev) {
+  GM_ARG(ctx && ((in_dev && out_dev) || n == 0), "NULL argument");
+  GM_ENTER(ctx);
+  return fr_reverse_dev(lane_of(ctx), ctx->sm_count, reinterpret_cast<const Fr*>(in_dev), n, reinterpret_cast<Fr*>(out_dev));
+}
+
 int gm_fr_powers_dev(gm_ctx* ctx, const uint64_t x[4], size_t n, void* out_dev) {
   GM_ARG(ctx && x && (out_dev || n == 0), "NULL argument");
   GM_ENTER(ctx);

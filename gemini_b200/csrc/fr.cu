@@ -219,6 +219,19 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
   sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
 }
 
+// out[i] = in[n - 1 - i]: the big-endian streams of the elastic prover (Reverse(..) in /root/reference/src/kzg/space.rs:288-297,
+// src/snark/elastic_prover.rs:174-188) are the resident little-endian vectors read backwards.  In place when out == in.
+__global__ void __launch_bounds__(256)
+k_fr_reverse(const Fr* in, size_t n, Fr* out) {
+  const size_t half = (n + 1) / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = n - 1 - i;
+    const Fr a = load_fr(in + i), b = load_fr(in + j);
+    store_fr(out + i, b);
+    store_fr(out + j, a);
+  }
+}
+
 // splitmix64 counter stream -> Fr elements (the 255-bit value, minus r if needed, is used directly as
 // the Montgomery representative).  tests/util.py holds the numpy restatement.
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -404,6 +417,13 @@ static inline unsigned fold_grid(const gm_ctx* ctx, size_t outputs) { return fol
 int fr_fold_dev(const Lane& ln, int sm_count, const Fr* d_f, size_t n, const Fr& r, Fr* d_out) {
   if (n == 0) return GM_OK;
   LAUNCH_LN(ln, k_fr_fold, fold_grid_sm(sm_count, (n + 1) / 2), 256, 0, d_f, n, r, d_out);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+int fr_reverse_dev(const Lane& ln, int sm_count, const Fr* d_in, size_t n, Fr* d_out) {
+  if (n == 0) return GM_OK;
+  LAUNCH_LN(ln, k_fr_reverse, fold_grid_sm(sm_count, (n + 1) / 2), 256, 0, d_in, n, d_out);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

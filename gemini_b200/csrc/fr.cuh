@@ -12,6 +12,8 @@ inline int fr_fold_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& r, Fr* d_
   return fr_fold_dev(lane_of(ctx), ctx->sm_count, d_f, n, r, d_out);
 }
 int fr_random_dev(gm_ctx* ctx, Fr* d_out, size_t n, uint64_t seed);
+// d_out[i] = d_in[n - 1 - i] (in place when d_out == d_in)
+int fr_reverse_dev(const Lane& ln, int sm_count, const Fr* d_in, size_t n, Fr* d_out);
 
 // number of CTA partial slots a prover over vectors of these lengths can ever need
 size_t sc_max_ctas(size_t nf, size_t ng);

@@ -49,6 +49,16 @@ class DeviceFr:
         assert offset + n <= self.n
         return DeviceFr(self.ctx, n, self.ptr + 32 * offset)
 
+    def reversed(self) -> "DeviceFr":
+        """new vector with out[i] = self[n-1-i] (big-endian stream order <-> little-endian), on the device"""
+        v = DeviceFr(self.ctx, self.n)
+        check(lib.gm_fr_reverse_dev(self.ctx._h, C.c_void_p(self.ptr), self.n, C.c_void_p(v.ptr)))
+        return v
+
+    def reverse_(self) -> "DeviceFr":
+        check(lib.gm_fr_reverse_dev(self.ctx._h, C.c_void_p(self.ptr), self.n, C.c_void_p(self.ptr)))
+        return self
+
     def clone(self) -> "DeviceFr":
         v = DeviceFr(self.ctx, self.n)
         check(lib.gm_dev_copy(self.ctx._h, C.c_void_p(v.ptr), C.c_void_p(self.ptr), self.n * 32))

@@ -3,22 +3,29 @@
   * :class:`CommitterKey`       - /root/reference/src/kzg/time.rs:24-160 (in-memory, little-endian coefficients)
   * :class:`CommitterKeyStream` - /root/reference/src/kzg/space.rs:59-297 (big-endian streams, chunked MSM)
 
-The MSMs (the hot path) run on the GPU against the device-resident SRS.  The O(n) scalar preparation
-around them (Horner quotients, division by the vanishing polynomial, linear combinations) is host-side
-bookkeeping in this round - SURVEY.md 8(f) rank 1 lists it as the next tier to move onto the device.
+Everything runs on the device: the MSMs against the resident SRS, and the O(n) scalar preparation around them -
+the synthetic divisions of ``open`` / ``open_multi_points`` (``DeviceFr.div_linear``: a parallel suffix-Horner scan;
+division by the vanishing polynomial of k points = k successive linear divisions), the eta-combinations
+(``DeviceFr.axpy``) and the big-endian <-> little-endian reversals (``DeviceFr.reversed``).  Polynomials may be
+passed as host sequences / limb arrays (uploaded once) or as resident :class:`DeviceFr` /
+:class:`streams.ReverseStream` objects (nothing crosses PCIe but the 32-byte evaluations and 144-byte proofs).
 """
 from __future__ import annotations
 
-from collections import deque
 from typing import List, Sequence, Tuple
 
 import numpy as np
 
 from . import field
-from .context import Context, Srs, as_fr_array
-from .msm import ChunkedPippenger, HashMapPippenger, VariableBaseMSM, _DeviceStream, msm_chunks
+from .context import Context, Srs
+from .devvec import DeviceFr
+from .msm import ChunkedPippenger, HashMapPippenger, VariableBaseMSM, _DeviceStream, msm_chunks  # noqa: F401
 
 R = field.R
+
+# Device-resident scalars need no staging buffer, so ``max_msm_buffer`` (the reference's bound on HOST memory,
+# ChunkedPippenger::with_size) only bounds the chunk pushed per call from below; tests lower it to walk chunk boundaries.
+MIN_DEVICE_CHUNK = 1 << 16
 
 
 def vanishing_polynomial(points: Sequence[int]) -> List[int]:
@@ -33,38 +40,44 @@ def vanishing_polynomial(points: Sequence[int]) -> List[int]:
     return poly
 
 
-def _poly_div(f: Sequence[int], z: Sequence[int]) -> List[int]:
-    """DensePolynomial::div by a monic divisor, quotient only (time.rs:142-143)."""
-    f = [x % R for x in f]
-    dz = len(z) - 1
-    if len(f) <= dz:
-        return []
-    q = [0] * (len(f) - dz)
-    for i in range(len(f) - 1, dz - 1, -1):
-        c = f[i]
-        q[i - dz] = c
-        if c:
-            for j, zc in enumerate(z):
-                f[i - dz + j] = (f[i - dz + j] - c * zc) % R
-    return q
-
-
-def _linear_combination(polys: Sequence[Sequence[int]], coeffs: Sequence[int]) -> List[int]:
-    """misc::linear_combination (src/misc.rs:37-48)."""
-    n = max((len(p) for p in polys), default=0)
-    out = [0] * n
-    for p, c in zip(polys, coeffs):
-        for i, v in enumerate(p):
-            out[i] = (out[i] + c * v) % R
-    return out
-
-
 def _powers(x: int, n: int) -> List[int]:
     out, cur = [], 1
     for _ in range(n):
         out.append(cur)
         cur = cur * x % R
     return out
+
+
+def _resident(ctx: Context, polynomial) -> DeviceFr:
+    """little-endian coefficients on the device (no copy when they already are)"""
+    return polynomial if isinstance(polynomial, DeviceFr) else DeviceFr.from_host(ctx, polynomial)
+
+
+def _divide_by_points(poly: DeviceFr, points: Sequence[int]):
+    """quotient of poly by prod (X - p) as len(points) successive synthetic divisions on the device, and the
+    remainder in MONOMIAL form, highest degree first (the order of the reference's state deque, space.rs:128-166).
+    The k constants c_j of the divisions are the Newton form  rem = c_1 + c_2 (X - p_1) + c_3 (X - p_1)(X - p_2) ..."""
+    pts = [p % R for p in points]
+    k = len(pts)
+    q, cs = poly, []
+    for a in pts:
+        if q.n == 0:
+            cs.append(0)
+            continue
+        q, c = q.div_linear(a)
+        cs.append(c)
+    rem = [0] * k
+    basis = [1]
+    for j, c in enumerate(cs):
+        for d, b in enumerate(basis):
+            rem[d] = (rem[d] + c * b) % R
+        if j + 1 < k:
+            nb = [0] * (len(basis) + 1)
+            for d, b in enumerate(basis):
+                nb[d + 1] = (nb[d + 1] + b) % R
+                nb[d] = (nb[d] - pts[j] * b) % R
+            basis = nb
+    return q, rem[::-1]
 
 
 class CommitterKey:
@@ -92,11 +105,18 @@ class CommitterKey:
     def max_degree(self) -> int:
         return len(self.srs) - 1
 
+    def _commit_dev(self, v: DeviceFr) -> field.Point:
+        return field.jacobian_to_affine(self.ctx.msm_dev(self.srs, v.ptr, v.n)) if v.n else None
+
     def commit(self, polynomial) -> field.Point:
         """time.rs:81-83: one MSM against the SRS prefix (silently truncating to the shorter)."""
+        if isinstance(polynomial, DeviceFr):
+            return self._commit_dev(polynomial)
         return self._msm.msm_unchecked(self.srs, polynomial)
 
     def commit_raw(self, polynomial) -> np.ndarray:
+        if isinstance(polynomial, DeviceFr):
+            return self.ctx.msm_dev(self.srs, polynomial.ptr, polynomial.n)
         return self.ctx.msm(self.srs, polynomial)
 
     def index_by(self, indices: Sequence[int]) -> "CommitterKey":
@@ -130,27 +150,30 @@ class CommitterKey:
         """time.rs:98-107."""
         return [self.commit(p) for p in polynomials]
 
-    def open(self, polynomial: Sequence[int], evaluation_point: int) -> Tuple[int, field.Point]:
-        """time.rs:112-131: synthetic division (Horner) then an MSM over the quotient."""
-        quotient_rev = []
-        prev = 0
-        for c in reversed(list(polynomial)):
-            coeff = (c + prev * evaluation_point) % R
-            quotient_rev.append(coeff)
-            prev = coeff
-        if not quotient_rev:
+    def open(self, polynomial, evaluation_point: int) -> Tuple[int, field.Point]:
+        """time.rs:112-131: (evaluation, proof).  The reference runs a serial Horner recurrence and builds the quotient
+        with ``Vec::insert(0, ..)`` (O(n^2)); here the same quotient and remainder come from one parallel synthetic
+        division on the device, then one MSM over the quotient."""
+        f = _resident(self.ctx, polynomial)
+        if f.n == 0:
             return 0, None
-        quotient = quotient_rev[::-1]
-        return quotient[0], self._msm.msm_unchecked(self.srs, quotient[1:])
+        q, evaluation = f.div_linear(evaluation_point % R)
+        return evaluation, self._commit_dev(q)
 
-    def open_multi_points(self, polynomial: Sequence[int], eval_points: Sequence[int]) -> field.Point:
-        """time.rs:134-145."""
-        return self.commit(_poly_div(polynomial, vanishing_polynomial(eval_points)))
+    def open_multi_points(self, polynomial, eval_points: Sequence[int]) -> field.Point:
+        """time.rs:134-145: commit to polynomial / vanishing_polynomial(eval_points)."""
+        q, _ = _divide_by_points(_resident(self.ctx, polynomial), eval_points)
+        return self._commit_dev(q)
 
     def batch_open_multi_points(self, polynomials, eval_points: Sequence[int], eval_chal: int) -> field.Point:
-        """time.rs:149-159."""
-        etas = _powers(eval_chal, len(polynomials))
-        return self.open_multi_points(_linear_combination(polynomials, etas), eval_points)
+        """time.rs:149-159: eta-combination of the polynomials (misc::linear_combination), then open_multi_points."""
+        polys = [_resident(self.ctx, p) for p in polynomials]
+        if not polys:
+            return None
+        batched = DeviceFr.zeros(self.ctx, max(p.n for p in polys))
+        for p, eta in zip(polys, _powers(eval_chal % R, len(polys))):
+            batched.axpy(eta, p)
+        return self.open_multi_points(batched, eval_points)
 
 
 def _folded_len(n: int, k: int) -> int:
@@ -158,7 +181,10 @@ def _folded_len(n: int, k: int) -> int:
 
 
 class CommitterKeyStream:
-    """``CommitterKeyStream``: the SRS in BIG-endian stream order (``Reverse(powers_of_g)``, space.rs:288-297)."""
+    """``CommitterKeyStream``: the SRS in BIG-endian stream order (``Reverse(powers_of_g)``, space.rs:288-297).
+
+    Polynomial arguments are big-endian streams: host sequences / limb arrays (the reference's order), or a
+    :class:`streams.ReverseStream` / ``MatrixTensor`` / ``LinCombStream`` over resident vectors."""
 
     def __init__(self, ctx: Context, powers_of_g_be):
         self.ctx = ctx
@@ -175,68 +201,68 @@ class CommitterKeyStream:
     def __len__(self) -> int:
         return len(self.srs_be)
 
+    # -- helpers -------------------------------------------------------------------------------
+    def _le(self, stream_be) -> DeviceFr:
+        from .streams import as_le_device
+
+        return as_le_device(self.ctx, stream_be)
+
+    def _commit_le(self, le: DeviceFr, max_msm_buffer: int) -> field.Point:
+        """sum_d le[d] * g^(tau^d) against the big-endian SRS: the coefficients are reversed on the device and pushed in
+        chunks (msm_chunks / ChunkedPippenger semantics: the result does not depend on the chunking)."""
+        m = le.n
+        if m == 0:
+            return None
+        assert m <= len(self), "polynomial longer than the SRS"
+        be = le.reversed()
+        chunk = max(max_msm_buffer, MIN_DEVICE_CHUNK, 1)
+        st = _DeviceStream(self.ctx, self.srs_be, min(chunk, m))
+        off = len(self) - m
+        for s0 in range(0, m, chunk):
+            st.push_dev(off + s0, be.ptr + 32 * s0, min(chunk, m - s0))
+        out = st.finalize()
+        st.free()
+        be.free()
+        return out
+
+    # -- the reference's methods -----------------------------------------------------------------
     def commit(self, polynomial_be, step: int = 1 << 20) -> field.Point:
         """space.rs:169-177 -> msm_chunks (space.rs:22-55)."""
+        from .streams import LinCombStream, MatrixTensor, ReverseStream
+
+        if isinstance(polynomial_be, (ReverseStream, MatrixTensor, LinCombStream)):
+            return self._commit_le(self._le(polynomial_be), step)
         return msm_chunks(self.ctx, self.srs_be, polynomial_be, step)
 
-    def open(self, polynomial_be: Sequence[int], alpha: int, max_msm_buffer: int) -> Tuple[int, field.Point]:
-        """space.rs:95-125: quotient coefficients stream into the chunked MSM."""
-        poly = [x % R for x in polynomial_be]
-        n, off = len(poly), len(self) - len(poly)
-        st = _DeviceStream(self.ctx, self.srs_be, max(max_msm_buffer, 1))
-        cap = max(max_msm_buffer, 1)
-        prev, buf, start = 0, [], 0
-        for i, scalar in enumerate(poly):
-            buf.append(prev)
-            prev = (prev * alpha + scalar) % R
-            if len(buf) == cap:
-                st.push_range(off + start, buf)
-                start, buf = i + 1, []
-        if buf:
-            st.push_range(off + start, buf)
-        return prev, st.finalize()
+    def open(self, polynomial_be, alpha: int, max_msm_buffer: int) -> Tuple[int, field.Point]:
+        """space.rs:95-125: (evaluation, proof); the quotient never leaves the device."""
+        le = self._le(polynomial_be)
+        if le.n == 0:
+            return 0, None
+        q, evaluation = le.div_linear(alpha % R)
+        return evaluation, self._commit_le(q, max_msm_buffer)
 
-    def open_multi_points(self, polynomial_be: Sequence[int], points: Sequence[int], max_msm_buffer: int):
-        """space.rs:128-166: returns (remainder, proof)."""
-        zeros = vanishing_polynomial(points)
-        deg = len(zeros) - 1
-        poly = [x % R for x in polynomial_be]
-        off = len(self) - len(poly) + deg
-        it = iter(poly)
-        state = deque(next(it) for _ in range(len(points)))
-        cap = max(max_msm_buffer, 1)
-        st = _DeviceStream(self.ctx, self.srs_be, cap)
-        buf, start, i = [], 0, 0
-        for coeff in it:
-            qc = state.popleft()
-            state.append(coeff)
-            for k in range(len(points)):
-                state[k] = (state[k] - zeros[deg - k - 1] * qc) % R
-            buf.append(qc)
-            i += 1
-            if len(buf) == cap:
-                st.push_range(off + start, buf)
-                start, buf = i, []
-        if buf:
-            st.push_range(off + start, buf)
-        return list(state), st.finalize()
+    def open_multi_points(self, polynomial_be, points: Sequence[int], max_msm_buffer: int):
+        """space.rs:128-166: returns (remainder coefficients, highest degree first, and the proof)."""
+        le = self._le(polynomial_be)
+        assert le.n >= len(points), "the reference reads len(points) leading coefficients (unwrap on a shorter stream panics)"
+        q, rem = _divide_by_points(le, points)
+        return rem, self._commit_le(q, max_msm_buffer)
 
     def commit_folding(self, polynomials_be, challenges: Sequence[int], max_msm_buffer: int) -> List[field.Point]:
-        """space.rs:192-223.  The reference walks the FoldedPolynomialTree once and feeds one
-        ChunkedPippenger per level; here every level is produced by the device fold chain and committed
-        against the SRS range that lines its low-order end up with g^(tau^0)."""
-        f_le = as_fr_array(polynomials_be)[::-1].copy()
-        k = len(challenges)
-        if k == 0:
-            return []
-        levels = self.ctx.fr_fold_chain(f_le, challenges)
-        out = []
-        for lvl in levels:
-            m = lvl.shape[0]
-            st = _DeviceStream(self.ctx, self.srs_be, max(m, 1))
-            st.push_range(len(self) - m, np.ascontiguousarray(lvl[::-1]))
-            out.append(st.finalize())
-        return out
+        """space.rs:192-223.  The reference walks the FoldedPolynomialTree once and feeds one ChunkedPippenger per
+        level; here the device fold chain produces every level and each is committed against the SRS range that lines
+        its low-order end up with g^(tau^0).  ``polynomials_be``: big-endian stream or a tensorcheck.FoldedPolynomialTree."""
+        from .tensorcheck import FoldedPolynomialTree
+
+        if isinstance(polynomials_be, FoldedPolynomialTree):
+            levels = polynomials_be.levels
+        else:
+            if len(challenges) == 0:
+                return []
+            levels = self._le(polynomials_be).fold_chain([c % R for c in challenges])
+        n_levels = max(len(levels), 1)
+        return [self._commit_le(lvl, max_msm_buffer // n_levels) for lvl in levels]
 
     def open_folding(self, polynomials, points: Sequence[int], etas: Sequence[int], max_msm_buffer: int = 0):
         """space.rs:229-285 -> (remainders per level, evaluation proof).  ``polynomials``: tensorcheck.FoldedPolynomialTree.
@@ -245,41 +271,15 @@ class CommitterKeyStream:
         eta_i * quotient coefficients into one HashMapPippenger (all levels pair the coefficient of degree d with the
         same base g^(tau^d), so the map merges them).  Here: k synthetic divisions per level on the device
         (k = len(points)), the eta-combination of the quotients as one resident vector, ONE MSM."""
-        from .devvec import DeviceFr
-
         ctx = self.ctx
-        pts = [p % R for p in points]
-        k = len(pts)
         remainders, batched = [], None
         for i, lvl in enumerate(polynomials.levels):
-            q, cs = lvl, []
-            for a in pts:
-                if q.n == 0:
-                    cs.append(0)
-                    continue
-                q, c = q.div_linear(a)
-                cs.append(c)
-            # remainder in Newton form c_1 + c_2 (X - a_1) + c_3 (X - a_1)(X - a_2) ... -> monomial coefficients
-            rem = [0] * k
-            basis = [1]
-            for j, c in enumerate(cs):
-                for d, b in enumerate(basis):
-                    rem[d] = (rem[d] + c * b) % R
-                if j + 1 < k:
-                    nb = [0] * (len(basis) + 1)
-                    for d, b in enumerate(basis):
-                        nb[d + 1] = (nb[d + 1] + b) % R
-                        nb[d] = (nb[d] - pts[j] * b) % R
-                    basis = nb
-            remainders.append(rem[::-1])                      # deque order of the reference: highest degree first
+            q, rem = _divide_by_points(lvl, points)
+            remainders.append(rem)
             if q.n:
                 if batched is None:
                     batched = DeviceFr.zeros(ctx, max(l.n for l in polynomials.levels))
                 batched.axpy(etas[i] % R, q)
         if batched is None:
             return remainders, None
-        m = batched.n
-        st = _DeviceStream(ctx, self.srs_be, m)
-        st.push_range(len(self) - m, np.ascontiguousarray(batched.limbs()[::-1]))
-        return remainders, st.finalize()
-
+        return remainders, self._commit_le(batched, max_msm_buffer)

@@ -75,6 +75,10 @@ class _DeviceStream:
         arr = as_fr_array(scalars, montgomery=not bigint)
         check(lib.gm_msm_stream_push(self._h, None, 0, -1, base_offset, _ptr(arr), arr.shape[0], int(bigint)))
 
+    def push_dev(self, base_offset: int, scalars_dev_ptr: int, m: int, bigint: bool = False) -> None:
+        """scalars already resident on the device (gm_msm_stream_push_dev): no staging copy"""
+        check(lib.gm_msm_stream_push_dev(self._h, base_offset, C.c_void_p(scalars_dev_ptr), m, int(bigint)))
+
     def push_points(self, points, scalars, bigint: bool = False) -> None:
         parr = points if isinstance(points, np.ndarray) else field.g1_to_limbs(points)
         parr = np.ascontiguousarray(parr.reshape(-1, 12))

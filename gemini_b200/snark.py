@@ -165,35 +165,27 @@ def new_time(ctx: Context, r1cs: R1cs, ck: CommitterKey, transcript, timers: Opt
 
 
 # ---------------------------------------------------------------------------------------------------
-# Elastic prover (config 5) - STAGED: assembled from GPU-validated parts (stream commit, ElasticProver, commit_folding,
-# evaluate_folding, open_multi_points, open_folding) and checked on the CPU only through its oracle twin
-# (the CPU restatement of new_elastic equals the one of new_time, tests/test_oracle_kats.py); the composition itself has not run on a GPU yet - its parity
-# test waits in tests/staged_gpu_elastic.py (not collected) for the first GPU minutes of round 2.
+# Elastic prover (config 5): snark::Proof::new_elastic with every stream resident on the device
 # ---------------------------------------------------------------------------------------------------
-def elastic_tensorcheck(transcript, cks, witness_be: Sequence[int], body_le: DeviceFr, challenges: Sequence[int], max_msm_buffer: int) -> Dict:
-    """``tensorcheck`` of snark/elastic_prover.rs:109-167.  ``body_le``: the batched body polynomial, resident and
-    little-endian (the stream the reference re-reads is its reverse); ``witness_be``: big-endian host coefficients."""
-    from .msm import _DeviceStream
+def elastic_tensorcheck(transcript, cks, witness, body, challenges: Sequence[int], max_msm_buffer: int) -> Dict:
+    """``tensorcheck`` of snark/elastic_prover.rs:109-167.  ``witness`` / ``body``: big-endian streams
+    (streams.ReverseStream / LinCombStream over resident vectors, or host sequences)."""
+    from .streams import as_le_device
     from .tensorcheck import FoldedPolynomialTree, evaluate_folding
 
     ctx = cks.ctx
     chals = list(challenges)[:-1]                                              # strip_last
-    tree = FoldedPolynomialTree.from_le_device(ctx, body_le, chals)
-    # CommitterKeyStream::commit_folding (kzg/space.rs:192-223) against the resident levels
-    commitments = []
-    for lvl in tree.levels:
-        m = lvl.n
-        st = _DeviceStream(ctx, cks.srs_be, max(m, 1))
-        st.push_range(len(cks) - m, np.ascontiguousarray(lvl.limbs()[::-1]))
-        commitments.append(st.finalize())
+    tree = FoldedPolynomialTree(ctx, body, chals)
+    commitments = cks.commit_folding(tree, chals, max_msm_buffer)              # kzg/space.rs:192-223
     for c in commitments:
         transcript.append_g1(b"commitment", c)
     eval_chal = transcript.get_challenge(b"evaluation-chal")
     points = [eval_chal * eval_chal % R, eval_chal, (-eval_chal) % R]
     at_pos, at_neg = evaluate_folding(tree, points[1]), evaluate_folding(tree, points[2])
     fold_evals = [[x, y] for x, y in zip(at_pos, at_neg)]
-    w_le = DeviceFr.from_host(ctx, list(witness_be)[::-1])
-    evaluations_w = [w_le.evaluate(p) for p in points]
+    w_le = as_le_device(ctx, witness)
+    w_pos, w_neg = w_le.evaluate_pm(points[1])
+    evaluations_w = [w_le.evaluate(points[0]), w_pos, w_neg]                    # evaluate_be at the three points
     for e in evaluations_w:
         transcript.append_serializable(b"eval", e)
     for row in fold_evals:
@@ -201,43 +193,64 @@ def elastic_tensorcheck(transcript, cks, witness_be: Sequence[int], body_le: Dev
             transcript.append_serializable(b"eval", e)
     open_chal = transcript.get_challenge(b"open-chal")
     open_chals = [pow(open_chal, k, R) for k in range(len(challenges) + 1)]
-    _, proof_w = cks.open_multi_points(witness_be, points, max_msm_buffer)
+    _, proof_w = cks.open_multi_points(witness, points, max_msm_buffer)
     _, proof = cks.open_folding(tree, points, open_chals[1:], max_msm_buffer)
     total = field.jacobian_to_affine(ctx.g1_sum(np.stack([field.affine_to_jacobian_limbs(proof_w), field.affine_to_jacobian_limbs(proof)])))
     return {"base_polynomials_evaluations": [evaluations_w], "folded_polynomials_evaluations": fold_evals,
             "evaluation_proof": total, "folded_polynomials_commitments": commitments}
 
 
-def new_elastic(ctx: Context, r1cs: R1cs, cks, transcript, max_msm_buffer: int = 1 << 20) -> Dict:
+def new_elastic(ctx: Context, r1cs: R1cs, cks, transcript, max_msm_buffer: int = 1 << 20, timers: Optional[Dict[str, float]] = None) -> Dict:
     """snark::Proof::new_elastic (snark/elastic_prover.rs:169-267).  ``cks``: kzg.CommitterKeyStream (big-endian SRS).
-    The streams of the reference (Reverse(z), column-major matrices, MatrixTensor, LinCombStream) are the resident
-    little-endian vectors of the time prover read backwards, so the vector algebra is shared with ``new_time``; what
-    differs is the prover flavour (ElasticProver: rounds from the MIN length, Space -> Time hand-off) and the KZG side
-    (stream commit, commit_folding, open_multi_points + open_folding instead of one batched opening)."""
+
+    The reference's streams - ``Reverse(z)``, the column-major matrix streams, ``MatrixTensor``, ``LinCombStream`` - are
+    device-resident here (gemini_b200.streams): a stream is a resident little-endian vector read backwards, a
+    MatrixTensor is one tensor expansion + one transposed sparse product.  What differs from ``new_time`` is what the
+    reference changes too: the prover flavour (ElasticProver: rounds from the MIN length, Space -> Time hand-off) and
+    the KZG side (stream commit, commit_folding, open_multi_points + open_folding instead of one batched opening).
+    Nothing but transcript traffic (messages, evaluations, commitments) crosses PCIe."""
+    from .streams import LinCombStream, MatrixTensor, ReverseStream
     from .sumcheck import ElasticProver
 
+    def lap(name, t0):
+        if timers is not None:
+            ctx.synchronize()
+            timers[name] = timers.get(name, 0.0) + time.perf_counter() - t0
+
+    t0 = time.perf_counter()
     z_a, z_b, z_c = r1cs.a.matvec(r1cs.z), r1cs.b.matvec(r1cs.z), r1cs.c.matvec(r1cs.z)
-    w_be = r1cs.w.to_ints()[::-1]
-    witness_commitment = cks.commit(w_be)
+    lap("matrix-vector products", t0)
+    t0 = time.perf_counter()
+    witness = ReverseStream(r1cs.w)
+    witness_commitment = cks.commit(witness, max_msm_buffer)
+    lap("Commitment to w", t0)
     transcript.append_g1(b"witness", witness_commitment)
     alpha = transcript.get_challenge(b"alpha")
-    zc_alpha = z_c.evaluate(alpha)
+    zc_alpha = z_c.evaluate(alpha)                                               # evaluate_be(Reverse(z_c), alpha)
     transcript.append_serializable(b"zc(alpha)", zc_alpha)
-    first = _prove_sumcheck(transcript, ElasticProver(ctx, z_a.to_ints()[::-1], z_b.to_ints()[::-1], alpha))
+    t0 = time.perf_counter()
+    first = _prove_sumcheck(transcript, ElasticProver(ctx, ReverseStream(z_a), ReverseStream(z_b), alpha))
+    lap("First sumcheck", t0)
     eta = transcript.get_challenge(b"eta")
-    # MatrixTensor(a_colmaj, hadamard(b, powers2(alpha))) etc. = transposed SpMV with the expanded tensors
-    b_ch = tensor(ctx, first["challenges"])
-    c_ch = powers(ctx, alpha, b_ch.n)
-    a_ch = b_ch.hadamard(c_ch)
-    lhs = r1cs.at.matvec(a_ch)
-    lhs.axpy(eta, r1cs.bt.matvec(b_ch))
-    lhs.axpy(eta * eta % R, r1cs.ct.matvec(c_ch))
-    second = _prove_sumcheck(transcript, ElasticProver(ctx, lhs.to_ints()[::-1], r1cs.z.to_ints()[::-1], 1))
+    t0 = time.perf_counter()
+    b_tensors = first["challenges"]
+    c_tensors = [pow(alpha, 1 << k, R) for k in range(len(b_tensors))]           # powers2(alpha, len), misc.rs:68-77
+    a_tensors = [x * y % R for x, y in zip(b_tensors, c_tensors)]                # hadamard
+    a_alpha = MatrixTensor(ctx, r1cs.at, a_tensors)
+    b_alpha = MatrixTensor(ctx, r1cs.bt, b_tensors)
+    c_alpha = MatrixTensor(ctx, r1cs.ct, c_tensors)
+    lhs = LinCombStream(ctx, [a_alpha, b_alpha, c_alpha], [1, eta, eta * eta % R])
+    z_stream = ReverseStream(r1cs.z)
+    lhs.le()
+    lap("abc_tensored", t0)
+    t0 = time.perf_counter()
+    second = _prove_sumcheck(transcript, ElasticProver(ctx, lhs, z_stream, 1))
+    lap("Second sumcheck", t0)
     batch_challenge = transcript.get_challenge(b"batch_challenge")
-    body = DeviceFr.zeros(ctx, max(lhs.n, r1cs.z.n))
-    body.axpy(1, lhs)
-    body.axpy(batch_challenge, r1cs.z)
-    tc = elastic_tensorcheck(transcript, cks, w_be, body, second["challenges"], max_msm_buffer)
+    t0 = time.perf_counter()
+    body = LinCombStream(ctx, [lhs, z_stream], [1, batch_challenge])
+    tc = elastic_tensorcheck(transcript, cks, witness, body, second["challenges"], max_msm_buffer)
+    lap("Tensorcheck", t0)
     return {"witness_commitment": witness_commitment, "zc_alpha": zc_alpha,
             "first_sumcheck_msgs": (first["messages"], first["final_foldings"]),
             "second_sumcheck_msgs": (second["messages"], second["final_foldings"]),

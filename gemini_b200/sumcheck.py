@@ -21,7 +21,8 @@ from . import field
 from ._lib import check, lib
 from .context import Context, _ptr, as_fr_array
 
-GEMINI_TIME, HERRING_F = 0, 1
+GEMINI_TIME, HERRING_F, GEMINI_SPACE = 0, 1, 2
+INPUT_DEVICE, INPUT_BIG_ENDIAN = 1, 2
 
 
 def ark_log2(x: int) -> int:
@@ -33,27 +34,29 @@ def fold_polynomial(ctx: Context, f, r: int) -> List[int]:
     return field.fr_from_limbs(ctx.fr_fold(f, r))
 
 
+def _fr_input(x):
+    """(pointer argument, length, is_device) of one prover input: DeviceFr, torch tensor (device or pinned host),
+    (n,4) uint64 limb array, or a sequence of ints"""
+    if hasattr(x, "ptr") and hasattr(x, "n"):          # gemini_b200.devvec.DeviceFr
+        return C.c_void_p(x.ptr), x.n, True, x
+    if hasattr(x, "data_ptr"):
+        return _ptr(x), x.numel() * x.element_size() // 32, bool(x.is_cuda), x
+    arr = as_fr_array(x)
+    return _ptr(arr), arr.shape[0], False, arr
+
+
 class _DeviceProver:
-    def __init__(self, ctx: Context, f, g, twist: int, flavour: int):
+    def __init__(self, ctx: Context, f, g, twist: int, flavour: int, big_endian: bool = False):
         self.ctx = ctx
-        if hasattr(f, "ptr") and hasattr(f, "n"):  # gemini_b200.devvec.DeviceFr: device-resident inputs
-            tw = field.fr_to_limbs([twist])
-            h = C.c_void_p()
-            check(lib.gm_sumcheck_new_dev(ctx._h, C.c_void_p(f.ptr), f.n, C.c_void_p(g.ptr), g.n, _ptr(tw), flavour, C.byref(h)))
-        elif hasattr(f, "data_ptr") and f.is_cuda:
-            nf = f.numel() * f.element_size() // 32
-            ng = g.numel() * g.element_size() // 32
-            tw = field.fr_to_limbs([twist])
-            h = C.c_void_p()
-            check(lib.gm_sumcheck_new_dev(ctx._h, _ptr(f), nf, _ptr(g), ng, _ptr(tw), flavour, C.byref(h)))
-        else:
-            fa = f if hasattr(f, "data_ptr") else as_fr_array(f)
-            ga = g if hasattr(g, "data_ptr") else as_fr_array(g)
-            nf = fa.shape[0] if isinstance(fa, np.ndarray) else fa.numel() * fa.element_size() // 32
-            ng = ga.shape[0] if isinstance(ga, np.ndarray) else ga.numel() * ga.element_size() // 32
-            tw = field.fr_to_limbs([twist])
-            h = C.c_void_p()
-            check(lib.gm_sumcheck_new(ctx._h, _ptr(fa), nf, _ptr(ga), ng, _ptr(tw), flavour, C.byref(h)))
+        pf, nf, f_dev, keep_f = _fr_input(f)
+        pg, ng, g_dev, keep_g = _fr_input(g)
+        if f_dev != g_dev:
+            raise ValueError("f and g must both be host buffers or both be device buffers")
+        tw = field.fr_to_limbs([twist])
+        h = C.c_void_p()
+        flags = (INPUT_DEVICE if f_dev else 0) | (INPUT_BIG_ENDIAN if big_endian else 0)
+        check(lib.gm_sumcheck_new_ex(ctx._h, pf, nf, pg, ng, _ptr(tw), flavour, flags, C.byref(h)))
+        del keep_f, keep_g       # the prover copied its inputs (Witness::new clones, time_prover.rs:26-32)
         self._h = h
 
     # -- trait Prover ------------------------------------------------------------------------
@@ -149,14 +152,20 @@ class HerringTimeProver(_DeviceProver):
 
 
 class SpaceProver(_DeviceProver):
-    """sumcheck/space_prover.rs: inputs are BIG-endian streams (highest-degree coefficient first)."""
+    """sumcheck/space_prover.rs: inputs are BIG-endian streams (highest-degree coefficient first).
+
+    ``f_be`` / ``g_be``: host sequences or limb arrays in stream order (uploaded once, reversed on the device), or
+    :class:`streams.ReverseStream` / ``MatrixTensor`` / ``LinCombStream`` over resident vectors (no host traffic)."""
 
     def __init__(self, ctx: Context, f_be, g_be, twist: int = 1):
-        fa = as_fr_array(f_be)[::-1].copy()
-        ga = as_fr_array(g_be)[::-1].copy()
-        super().__init__(ctx, fa, ga, twist, GEMINI_TIME)
-        # required_rounds uses the MIN length (space_prover.rs:76-79)
-        check(lib.gm_sumcheck_set_rounds(self._h, 0, ark_log2(min(fa.shape[0], ga.shape[0]))))
+        from .streams import LinCombStream, MatrixTensor, ReverseStream, as_le_device
+
+        stream_types = (ReverseStream, MatrixTensor, LinCombStream)
+        if isinstance(f_be, stream_types) or isinstance(g_be, stream_types):
+            # resident little-endian vectors behind both streams: handed over as they are
+            super().__init__(ctx, as_le_device(ctx, f_be), as_le_device(ctx, g_be), twist, GEMINI_SPACE)
+        else:
+            super().__init__(ctx, f_be, g_be, twist, GEMINI_SPACE, big_endian=True)
 
     def _check_alignment(self, fold_first: bool) -> None:
         """The reference aligns the two folded streams (space_prover.rs:142-174) and asserts equal pair
@@ -176,17 +185,25 @@ class SpaceProver(_DeviceProver):
         assert f_pairs == g_pairs, "assert_eq!(f_pairs, g_pairs) fails in the reference"
 
     def next_message_raw(self, verifier_message):
-        if self.round() < self.rounds():
+        if self.is_space and self.round() < self.rounds():
             self._check_alignment(verifier_message is not None)
         return super().next_message_raw(verifier_message)
 
+    is_space = True
+
     def final_foldings(self):
-        if self.round() != self.rounds():
+        """head of the folded big-endian streams (space_prover.rs:260-266): gm_sumcheck_final_foldings of the SPACE
+        flavour reads the LAST coefficient of the resident little-endian vectors - 64 bytes, not the vectors"""
+        nf, ng = self.lengths()
+        if self.round() != self.rounds() or nf == 0 or ng == 0:
             return None
-        f, g, _ = self.state()
-        if not f or not g:
-            return None
-        return (f[-1], g[-1])  # head of the big-endian folded streams (space_prover.rs:260-266)
+        return super().final_foldings()
+
+    def into_time(self) -> None:
+        """From<&SpaceProver> for TimeProver (space_prover.rs:269-307): the folded vectors are already resident in
+        little-endian order; only the semantics of final_foldings change, round counters and twist are kept."""
+        check(lib.gm_sumcheck_set_flavour(self._h, GEMINI_TIME))
+        self.is_space = False
 
 
 class ElasticProver:
@@ -195,15 +212,15 @@ class ElasticProver:
 
     def __init__(self, ctx: Context, f_be, g_be, twist: int = 1, threshold: int = 22):
         self.p = SpaceProver(ctx, f_be, g_be, twist)
-        self.is_space = True
         self.threshold = threshold  # SPACE_TIME_THRESHOLD, src/lib.rs:76
 
+    @property
+    def is_space(self) -> bool:
+        return self.p.is_space
+
     def fold(self, r: int) -> None:
-        if self.is_space and self.p.rounds() - self.p.round() < self.threshold:
-            # From<&SpaceProver> for TimeProver (space_prover.rs:269-307): the folded vectors are already
-            # resident in little-endian order; only the Time semantics of final_foldings change.
-            self.p.__class__ = TimeProver
-            self.is_space = False
+        if self.p.is_space and self.p.rounds() - self.p.round() < self.threshold:
+            self.p.into_time()
         self.p.fold(r)
 
     def next_message(self, verifier_message):
@@ -220,7 +237,12 @@ class ElasticProver:
         return self.p.rounds()
 
     def final_foldings(self):
-        return self.p.final_foldings()
+        if self.p.is_space:
+            return self.p.final_foldings()
+        return _DeviceProver.final_foldings(self.p)
+
+    def free(self) -> None:
+        self.p.free()
 
 
 class Sumcheck:

@@ -41,11 +41,12 @@ class FoldedPolynomialTree:
         if _levels is not None:
             self.levels, self.n = _levels, _n
             return
-        if hasattr(coefficients_be, "ptr") and hasattr(coefficients_be, "n"):
-            raise TypeError("pass big-endian host coefficients, or use FoldedPolynomialTree.from_le_device")
-        arr = as_fr_array(coefficients_be)
-        self.n = arr.shape[0]
-        base = DeviceFr.from_host(ctx, arr[::-1].copy())
+        from .streams import as_le_device
+
+        # big-endian stream: host coefficients (one upload, reversed on the device) or a ReverseStream / MatrixTensor /
+        # LinCombStream over resident vectors (no host traffic)
+        base = as_le_device(ctx, coefficients_be)
+        self.n = base.n
         self.levels = base.fold_chain(self.challenges) if self.challenges else []
 
     @classmethod

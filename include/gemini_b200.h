@@ -119,6 +119,8 @@ int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, 
 /* points == NULL: bases are srs[base_offset .. base_offset+m) ; else m ad-hoc points */
 int gm_msm_stream_push(gm_msm_stream* s, const void* points, size_t stride_bytes, long inf_offset,
                        size_t base_offset, const uint64_t* scalars, size_t m, int scalars_are_bigint);
+/* scalars resident on the device (quotients / fold levels of the elastic prover): bases = srs[base_offset .. +m) */
+int gm_msm_stream_push_dev(gm_msm_stream* s, size_t base_offset, const void* scalars_dev, size_t m, int scalars_are_bigint);
 int gm_msm_stream_finalize(gm_msm_stream* s, uint64_t out_jacobian[18]);
 int gm_msm_stream_free(gm_msm_stream* s);
 
@@ -165,10 +167,19 @@ size_t gm_fr_fold_chain_len(size_t n, size_t k);
 /* ---- sumcheck provers: trait Prover (src/subprotocols/sumcheck/prover.rs:30-45) ---- */
 #define GM_SUMCHECK_GEMINI_TIME 0 /* TimeProver, sumcheck/time_prover.rs:42-137: rounds from max len, twisted message */
 #define GM_SUMCHECK_HERRING_F 1   /* herring TimeProver<FModule>, herring/time_prover.rs:44-137: rounds from min len */
+#define GM_SUMCHECK_GEMINI_SPACE 2 /* SpaceProver, sumcheck/space_prover.rs:38-266: messages of TimeProver, rounds from the MIN
+                                     length (:76-79), final foldings = head of the folded big-endian streams (:260-266).  The folded
+                                     vectors stay resident instead of re-streaming the input every round. */
+#define GM_INPUT_DEVICE 1         /* gm_sumcheck_new_ex: f, g are device pointers of the context's GPU (else host: pageable or pinned) */
+#define GM_INPUT_BIG_ENDIAN 2     /* f, g arrive highest-degree coefficient first, the stream order of the space / elastic provers */
 int gm_sumcheck_new(gm_ctx* ctx, const uint64_t* f, size_t f_len, const uint64_t* g, size_t g_len,
                     const uint64_t twist[4], int flavour, gm_sumcheck** out);
 int gm_sumcheck_new_dev(gm_ctx* ctx, const void* f_dev, size_t f_len, const void* g_dev, size_t g_len,
                         const uint64_t twist[4], int flavour, gm_sumcheck** out);
+int gm_sumcheck_new_ex(gm_ctx* ctx, const void* f, size_t f_len, const void* g, size_t g_len, const uint64_t twist[4], int flavour,
+                       int input_flags, gm_sumcheck** out);
+/* ElasticProver::fold's Space -> Time switch (elastic_prover.rs:44-57; From<&SpaceProver> for TimeProver, space_prover.rs:269-307) */
+int gm_sumcheck_set_flavour(gm_sumcheck* p, int flavour);
 /* next_message(Option<F>): challenge may be NULL (first call).  *out_has_msg = 0 <=> None. */
 int gm_sumcheck_next_message(gm_sumcheck* p, const uint64_t* challenge_or_null, uint64_t out_ab[8],
                              int* out_has_msg);
@@ -203,6 +214,8 @@ int gm_fr_random_dev(gm_ctx* ctx, void* out_dev, size_t n, uint64_t seed);
  *      unless they hand a scalar back to the host. ---- */
 int gm_dev_memset(gm_ctx* ctx, void* dev, int byte, size_t bytes);
 int gm_dev_copy(gm_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+/* out[i] = in[n-1-i] (in place when out == in): big-endian stream order <-> resident little-endian order */
+int gm_fr_reverse_dev(gm_ctx* ctx, const void* in_dev, size_t n, void* out_dev);
 /* out[i] = x^i, i < n: misc::powers (src/misc.rs:59-65) */
 int gm_fr_powers_dev(gm_ctx* ctx, const uint64_t x[4], size_t n, void* out_dev);
 /* out = (E, O) = (sum_{i even} f_i x^i, sum_{i odd} f_i x^i): f(x) = E + O and f(-x) = E - O;

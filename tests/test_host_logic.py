@@ -43,16 +43,37 @@ def test_splitmix_twin_is_canonical():
     assert all(0 <= v < R for v in vals) and len(set(vals)) == 5000
 
 
+class _HostVec:
+    """stand-in for DeviceFr on the CPU box: the host logic around the device divisions (Newton -> monomial remainder)"""
+
+    def __init__(self, coeffs):
+        self.c = [x % R for x in coeffs]
+        self.n = len(self.c)
+
+    def div_linear(self, a):
+        q, acc = [], 0
+        for c in reversed(self.c):
+            acc = (acc * a + c) % R
+            q.append(acc)
+        rem = q.pop()
+        return _HostVec(q[::-1]), rem
+
+
 def test_kzg_scalar_preparation_matches_oracle():
     pts = rand_scalars(3, 4)
     assert kzg.vanishing_polynomial(pts) == o.vanishing_polynomial(pts)
-    f = rand_scalars(20, 5)
     z = o.vanishing_polynomial(pts)
-    assert kzg._poly_div(f, z) == o.poly_div(f, z)
-    assert kzg._poly_div(f[:3], z) == []
-    polys = [rand_scalars(5, 6), rand_scalars(9, 7)]
-    eta = 77
-    assert kzg._linear_combination(polys, [1, eta]) == [(polys[0][i] if i < 5 else 0) % R + eta * polys[1][i] % R - (R if ((polys[0][i] if i < 5 else 0) + eta * polys[1][i] % R) >= R else 0) for i in range(9)]
+    for n in (20, 4, 3, 2, 0):
+        f = rand_scalars(n, 5)
+        q, rem = kzg._divide_by_points(_HostVec(f), pts)
+        assert q.c == o.poly_div(f, z)
+        # remainder, highest degree first: f - q * z
+        prod = [0] * max(n, 3)
+        for i, a in enumerate(q.c):
+            for j, b in enumerate(z):
+                prod[i + j] = (prod[i + j] + a * b) % R
+        want = [((f[d] if d < n else 0) - prod[d]) % R for d in range(3)]
+        assert rem == want[::-1]
 
 
 def test_shard_ranges_cover():
