@@ -121,7 +121,7 @@ def test_matrix_tensor_and_lincomb_streams(ctx):
     assert lc2.to_ints_be() == o.lincomb_stream([want, s2], coeffs[:2])
 
 
-@pytest.mark.parametrize("nf,ng", [(64, 64), (33, 32), (100, 97), (1 << 12, 1 << 12)])
+@pytest.mark.parametrize("nf,ng", [(64, 64), (33, 32), (65, 64), (1 << 12, 1 << 12)])
 def test_space_and_elastic_provers_from_device_streams(ctx, nf, ng):
     f_be, g_be = rand_scalars(nf, 90 + nf), rand_scalars(ng, 91 + ng)
     tw = rand_scalars(1, 92)[0]
