@@ -94,6 +94,14 @@ SIGNATURES = {
     "gm_sumcheck_state_dev": (_i, [_vp, _pp, _psz, _pp, _psz]),
     "gm_sumcheck_read_state": (_i, [_vp, _vp, _psz, _vp, _psz, _vp]),
     "gm_sumcheck_free": (_i, [_vp]),
+    "gm_transcript_new": (_i, [C.c_char_p, _sz, _pp]),
+    "gm_transcript_clone": (_i, [_vp, _pp]),
+    "gm_transcript_free": (_i, [_vp]),
+    "gm_transcript_append_message": (_i, [_vp, C.c_char_p, _sz, C.c_char_p, _sz]),
+    "gm_transcript_challenge_bytes": (_i, [_vp, C.c_char_p, _sz, _vp, _sz]),
+    "gm_transcript_append_fr": (_i, [_vp, C.c_char_p, _sz, _vp, _sz]),
+    "gm_transcript_get_challenge_fr": (_i, [_vp, C.c_char_p, _sz, _vp]),
+    "gm_sumcheck_prove": (_i, [_vp, _vp, _vp, _vp, _sz, _psz, _vp]),
     "gm_dev_alloc": (_i, [_vp, _sz, _pp]),
     "gm_dev_free": (_i, [_vp, _vp]),
     "gm_dev_upload": (_i, [_vp, _vp, _vp, _sz]),

@@ -246,7 +246,7 @@ struct Fp {
 };
 
 // ---------------------------------------------------------------------------
-// Lazy reduction for sums of products (the inner products of the sumcheck messages, like ark-ff's sum_of_products
+// Lazy reduction for sums of products (the inner products of the sumcheck messages in fr.cu, like ark-ff's sum_of_products
 // behind misc::ip_unsafe): acc += a*b keeps the full 2N-limb product and only folds the TOP half back below p (one
 // N-limb conditional subtraction), so a product costs N^2 IMAD.WIDE instead of the 2 N^2 of a Montgomery product;
 // one Montgomery reduction at the very end.  Invariant: acc < p * 2^(32N)  (top half < p).  Needs 2 bits of slack

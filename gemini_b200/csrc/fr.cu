@@ -127,59 +127,46 @@ __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, 
   }
 }
 
-// GM_LAZY_SUMCHECK (off): accumulate the sums with lazy reduction (FrAcc, fp.cuh) - the last product of every term
-// keeps its full 512 bits and the Montgomery reduction is paid once per thread, not once per term.  The accumulator
-// is validated on the host (tests/test_host_field.py::test_lazy_sum_of_products) and compiles to fused IMAD.WIDE, but
-// the GPU budget of round 1 ran out before the parity suite could be run with it, so the shipped kernels keep the
-// plain Montgomery accumulation that the parity tests have seen.
-#ifdef GM_LAZY_SUMCHECK
+// The sums of the round messages are accumulated with LAZY reduction (FrAcc, fp.cuh - like ark-ff's sum_of_products
+// behind misc::ip_unsafe): the last product of every term keeps its full 512 bits (64 IMAD.WIDE instead of the 128 of
+// a Montgomery product) and the Montgomery reduction is paid once per thread, not once per term.
+//   twist == 1:  a += fe*ge ; b += fe*go + ge*fo                          3 lazy products per pair
+//   twisted:     u = fe*t, v = ge*(t*twist) ; a += u*ge ; b += u*go + v*fo   2 full + 3 lazy (+ 2 to advance t, t*twist)
 using ScAcc = FrAcc;
 __device__ __forceinline__ Fr sc_acc_value(const ScAcc& a) { return a.reduce(); }
 template <bool TW>
 __device__ __forceinline__ void pair_contrib(ScAcc& a, ScAcc& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
-                                             const Fr& twist, const Fr& t) {
+                                             const Fr& t, const Fr& tt) {
   if (TW) {
-    a.mul_add(fe * ge, t);
-    b.mul_add(fe * go + (ge * fo) * twist, t);
+    const Fr u = fe * t;
+    const Fr v = ge * tt;
+    a.mul_add(u, ge);
+    b.mul_add(u, go);
+    b.mul_add(v, fo);
   } else {
     a.mul_add(fe, ge);
     b.mul_add(fe, go);
     b.mul_add(ge, fo);
   }
 }
-#else
-using ScAcc = Fr;
-__device__ __forceinline__ Fr sc_acc_value(const ScAcc& a) { return a; }
-template <bool TW>
-__device__ __forceinline__ void pair_contrib(ScAcc& a, ScAcc& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
-                                             const Fr& twist, const Fr& t) {
-  if (TW) {
-    a = a + (fe * ge) * t;
-    b = b + (fe * go + (ge * fo) * twist) * t;
-  } else {
-    a = a + fe * ge;
-    b = b + (fe * go + ge * fo);
-  }
-}
-#endif
 
 template <bool TW>
-__global__ void __launch_bounds__(SC_THREADS)
+__global__ void __launch_bounds__(SC_THREADS, 2)
 k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr twist, PowTable tab, int kpt,
              Fr* partials, unsigned int* ticket, Fr* out) {
   const size_t npairs = min((nf + 1) / 2, (ng + 1) / 2);
   const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
   ScAcc a = ScAcc::zero(), b = ScAcc::zero();
-  Fr t = Fr::one(), step = Fr::one();
-  if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }  // (twist^2)^SC_THREADS
+  Fr t = Fr::one(), tt = Fr::one(), step = Fr::one();
+  if (TW && i0 < npairs) { t = pow_from_table(tab, i0); tt = t * twist; step = tab.p[8]; }  // step = (twist^2)^SC_THREADS
 #pragma unroll 1
   for (int k = 0; k < kpt; k++) {
     const size_t i = i0 + (size_t)k * SC_THREADS;
     if (i >= npairs) break;
     Fr fe = load_fr_or_zero(f, 2 * i, nf), fo = load_fr_or_zero(f, 2 * i + 1, nf);
     Fr ge = load_fr_or_zero(g, 2 * i, ng), go = load_fr_or_zero(g, 2 * i + 1, ng);
-    pair_contrib<TW>(a, b, fe, fo, ge, go, twist, t);
-    if (TW) t = t * step;
+    pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
+    if (TW) { t = t * step; tt = tt * step; }
   }
   sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
 }
@@ -187,7 +174,7 @@ k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size
 // fold by (rf, rg) and message of the folded vectors with the squared twist `twist` (already squared
 // by the host) in one pass.  nf/ng are the lengths BEFORE the fold.
 template <bool TW>
-__global__ void __launch_bounds__(SC_THREADS)
+__global__ void __launch_bounds__(SC_THREADS, 2)   // 2 CTAs (16 warps) per SM: at most 128 registers
 k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr rf, Fr rg,
                   Fr* __restrict__ f_out, Fr* __restrict__ g_out, Fr twist, PowTable tab, int kpt,
                   Fr* partials, unsigned int* ticket, Fr* out) {
@@ -195,8 +182,8 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
   const size_t npairs = max((nf2 + 1) / 2, (ng2 + 1) / 2);  // every element must be folded
   const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
   ScAcc a = ScAcc::zero(), b = ScAcc::zero();
-  Fr t = Fr::one(), step = Fr::one();
-  if (TW && i0 < npairs) { t = pow_from_table(tab, i0); step = tab.p[8]; }
+  Fr t = Fr::one(), tt = Fr::one(), step = Fr::one();
+  if (TW && i0 < npairs) { t = pow_from_table(tab, i0); tt = t * twist; step = tab.p[8]; }
 #pragma unroll 1
   for (int k = 0; k < kpt; k++) {
     const size_t i = i0 + (size_t)k * SC_THREADS;
@@ -213,8 +200,8 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
     if (2 * i + 1 < nf2) store_fr(f_out + 2 * i + 1, fo);
     if (2 * i < ng2) store_fr(g_out + 2 * i, ge);
     if (2 * i + 1 < ng2) store_fr(g_out + 2 * i + 1, go);
-    pair_contrib<TW>(a, b, fe, fo, ge, go, twist, t);
-    if (TW) t = t * step;
+    pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
+    if (TW) { t = t * step; tt = tt * step; }
   }
   sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
 }

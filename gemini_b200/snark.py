@@ -49,22 +49,11 @@ class R1cs:
 
 
 def _prove_sumcheck(transcript, prover) -> Dict:
-    """Sumcheck::prove (src/subprotocols/sumcheck/proof.rs:36-66)."""
-    messages, challenges = [], []
-    vm = None
-    while True:
-        msg = prover.next_message(vm)
-        if msg is None:
-            break
-        transcript.append_serializable(b"evaluations", msg)
-        ch = transcript.get_challenge(b"challenge")
-        vm = ch
-        messages.append(msg)
-        challenges.append(ch)
-    ff = prover.final_foldings()
-    transcript.append_serializable(b"final-folding", ff[0])
-    transcript.append_serializable(b"final-folding", ff[1])
-    return {"messages": messages, "challenges": challenges, "rounds": prover.rounds(), "final_foldings": [ff]}
+    """Sumcheck::prove (src/subprotocols/sumcheck/proof.rs:36-66): one native call for device provers + Merlin."""
+    from .sumcheck import Sumcheck
+
+    sc = Sumcheck.prove_transcript(prover, transcript)
+    return {"messages": sc.messages, "challenges": sc.challenges, "rounds": sc.rounds, "final_foldings": [tuple(sc.final_foldings[0])]}
 
 
 def tensorcheck_new_time(transcript, ck: CommitterKey, base_polynomials: Sequence[DeviceFr], body_polynomials) -> Dict:

@@ -189,6 +189,23 @@ class SpaceProver(_DeviceProver):
             self._check_alignment(verifier_message is not None)
         return super().next_message_raw(verifier_message)
 
+    def check_alignment_all_rounds(self) -> None:
+        """the alignment asserts of every remaining round, from the lengths alone (before a native prove loop)"""
+        if not self.is_space:
+            return
+        nf, ng = self.lengths()
+        for k in range(self.round(), self.rounds()):
+            if k > self.round():       # every message after the first folds by the previous challenge first
+                nf, ng = (nf + 1) // 2, (ng + 1) // 2
+            a, b = nf, ng
+            if a != b:
+                if a > b:
+                    a -= a - b + (b % 2)
+                else:
+                    b -= b - a + (a % 2)
+                assert a >= 1 and b >= 1, "stream exhausted during alignment (reference panics: unwrap on None)"
+                assert (a - 2 + a % 2) // 2 == (b - 2 + b % 2) // 2, "assert_eq!(f_pairs, g_pairs) fails in the reference"
+
     is_space = True
 
     def final_foldings(self):
@@ -253,6 +270,43 @@ class Sumcheck:
         self.challenges = challenges
         self.rounds = rounds
         self.final_foldings = final_foldings
+
+    @classmethod
+    def prove_transcript(cls, prover, transcript) -> "Sumcheck":
+        """Sumcheck::prove (proof.rs:36-66) against a transcript.  With a device prover and the native Merlin transcript
+        the whole Fiat-Shamir loop is ONE call into the library (gm_sumcheck_prove): message kernel, 64-byte D2H,
+        transcript append, challenge, next launch - without returning to Python between rounds.  Any other
+        prover / transcript pair runs the same loop here."""
+        from .transcript import MerlinTranscript
+
+        inner = prover.p if isinstance(prover, ElasticProver) else prover
+        if isinstance(inner, _DeviceProver) and isinstance(transcript, MerlinTranscript):
+            if isinstance(inner, SpaceProver):
+                inner.check_alignment_all_rounds()
+            cap = inner.rounds() + 1
+            msgs = np.empty((cap, 8), dtype=np.uint64)
+            chals = np.empty((cap, 4), dtype=np.uint64)
+            fin = np.empty(8, dtype=np.uint64)
+            k = C.c_size_t(0)
+            check(lib.gm_sumcheck_prove(inner._h, transcript._h, _ptr(msgs), _ptr(chals), cap, C.byref(k), _ptr(fin)))
+            k = int(k.value)
+            flat = field.fr_from_limbs(msgs[:k].reshape(-1, 4))
+            messages = [(flat[2 * i], flat[2 * i + 1]) for i in range(k)]
+            return cls(messages, field.fr_from_limbs(chals[:k]), inner.rounds(), [tuple(field.fr_from_limbs(fin.reshape(2, 4)))])
+        messages, challenges = [], []
+        vm = None
+        while True:
+            msg = prover.next_message(vm)
+            if msg is None:
+                break
+            transcript.append_serializable(b"evaluations", msg)
+            vm = transcript.get_challenge(b"challenge")
+            messages.append(msg)
+            challenges.append(vm)
+        ff = prover.final_foldings()
+        transcript.append_serializable(b"final-folding", ff[0])
+        transcript.append_serializable(b"final-folding", ff[1])
+        return cls(messages, challenges, prover.rounds(), [ff])
 
     @classmethod
     def prove(cls, prover, challenge_fn: Callable[[Tuple[int, int]], int]) -> "Sumcheck":

@@ -200,6 +200,24 @@ int gm_sumcheck_read_state(gm_sumcheck* p, uint64_t* out_f, size_t* f_len, uint6
                            uint64_t out_twist[4]);
 int gm_sumcheck_free(gm_sumcheck* p);
 
+/* ---- Fiat-Shamir: merlin::Transcript + GeminiTranscript (src/transcript.rs:8-34), host-side, no device needed ---- */
+typedef struct gm_transcript gm_transcript;
+/* merlin::Transcript::new(label) */
+int gm_transcript_new(const uint8_t* label, size_t label_len, gm_transcript** out);
+int gm_transcript_clone(const gm_transcript* t, gm_transcript** out);
+int gm_transcript_free(gm_transcript* t);
+int gm_transcript_append_message(gm_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t len);
+int gm_transcript_challenge_bytes(gm_transcript* t, const uint8_t* label, size_t label_len, uint8_t* out, size_t n);
+/* append_serializable of 1 or 2 Fr (Montgomery limbs in, 32-byte little-endian canonical integers hashed) */
+int gm_transcript_append_fr(gm_transcript* t, const uint8_t* label, size_t label_len, const uint64_t* mont, size_t count);
+/* get_challenge::<Fr>: 64 PRF bytes -> Fr::from_random_bytes with retry; Montgomery limbs out */
+int gm_transcript_get_challenge_fr(gm_transcript* t, const uint8_t* label, size_t label_len, uint64_t out_mont[4]);
+/* Sumcheck::prove (src/subprotocols/sumcheck/proof.rs:36-66): the whole Fiat-Shamir loop as one call.  out_msgs receives
+ * rounds x (a | b) and out_challenges rounds x Fr (Montgomery limbs; `capacity` rounds of room, gm_sumcheck_rounds(p) is
+ * enough), out_final the final foldings, which are also appended to the transcript (b"final-folding") as the reference does. */
+int gm_sumcheck_prove(gm_sumcheck* p, gm_transcript* t, uint64_t* out_msgs, uint64_t* out_challenges, size_t capacity, size_t* out_rounds,
+                      uint64_t out_final[8]);
+
 /* ---- raw device buffers for callers that keep vectors resident (bench, pipelines) ---- */
 int gm_dev_alloc(gm_ctx* ctx, size_t bytes, void** out_dev);
 int gm_dev_free(gm_ctx* ctx, void* dev);

@@ -109,5 +109,5 @@ def test_new_time_with_merlin_runs(ctx):
     r1 = o.dummy_r1cs(12345, n)
     ck = gm.CommitterKey(ctx, srs)
     got = snark.new_time(ctx, snark.R1cs.dummy(ctx, n, 12345), ck, MerlinTranscript())
-    want = o.snark_new_time(r1, srs, MerlinTranscript())
+    want = o.snark_new_time(r1, srs, o.MerlinTranscript())
     assert got == want

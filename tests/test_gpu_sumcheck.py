@@ -130,3 +130,21 @@ def test_prove_batch(ctx):
     got = gm.Sumcheck.prove_batch(mk_dev, lambda: next(c2), challenge_fn_factory(5))
     assert (got.messages, got.challenges, got.final_foldings) == want
     assert got.rounds == 8
+
+
+def test_native_prove_loop_equals_python_loop(ctx):
+    """gm_sumcheck_prove (Sumcheck::prove, proof.rs:36-66, as one native call with the native Merlin transcript) against
+    the same loop driven round by round from Python over the oracle's pure-Python Merlin."""
+    from gemini_b200.transcript import MerlinTranscript
+
+    for nf, ng, tw in ((1000, 1000, 7), (93, 16, 1), (4097, 4096, 12345)):
+        f, g = rand_scalars(nf, 300 + nf), rand_scalars(ng, 301 + ng)
+        t_native, t_oracle = MerlinTranscript(), o.MerlinTranscript()
+        t_native.append_serializable(b"zc(alpha)", 99)
+        t_oracle.append_serializable(b"zc(alpha)", 99)
+        got = gm.Sumcheck.prove_transcript(gm.TimeProver(ctx, f, g, tw), t_native)
+        want = o.sumcheck_prove_transcript(o.TimeProver(f, g, tw), t_oracle)
+        assert got.messages == want["messages"] and got.challenges == want["challenges"]
+        assert [tuple(x) for x in got.final_foldings] == [tuple(x) for x in want["final_foldings"]]
+        # the transcripts are in the same state afterwards (final foldings were appended on both sides)
+        assert t_native.get_challenge(b"eta") == t_oracle.get_challenge(b"eta")

@@ -1,12 +1,17 @@
-"""Merlin / STROBE-128 restatement against published known-answer vectors."""
+"""Merlin / STROBE-128: the native transcript of the library (gemini_b200/csrc/transcript.cu, host code - no GPU needed)
+against published known-answer vectors and against the pure-Python restatement in oracle/pyref.py."""
+import ctypes as C
 import hashlib
+import random
 
+import pyref as o
 from gemini_b200 import field
-from gemini_b200.transcript import MerlinTranscript, keccak_f1600
+from gemini_b200._lib import check, lib
+from gemini_b200.transcript import MerlinTranscript
 
 
-def test_keccak_matches_sha3():
-    """Keccak-f[1600] checked through SHA3-256 (rate 136, pad 0x06) against hashlib."""
+def test_oracle_keccak_matches_sha3():
+    """Keccak-f[1600] of the oracle checked through SHA3-256 (rate 136, pad 0x06) against hashlib."""
     for msg in (b"", b"abc", b"x" * 135, b"y" * 136, b"z" * 500):
         st = bytearray(200)
         padded = bytearray(msg) + b"\x06"
@@ -16,24 +21,63 @@ def test_keccak_matches_sha3():
         for off in range(0, len(padded), 136):
             for i in range(136):
                 st[i] ^= padded[off + i]
-            keccak_f1600(st)
+            o.keccak_f1600(st)
         assert bytes(st[:32]) == hashlib.sha3_256(msg).digest()
+
+
+def _native(label: bytes) -> MerlinTranscript:
+    return MerlinTranscript(label)
 
 
 def test_merlin_simple_protocol_vector():
     """merlin's `equivalence_simple` conformance transcript (also the vector of the Go / JS ports)."""
-    t = MerlinTranscript.__new__(MerlinTranscript)
-    from gemini_b200.transcript import Strobe128
-    t.strobe = Strobe128(b"Merlin v1.0")
-    t.g1_encoding = "zcash"
-    t.append_message(b"dom-sep", b"test protocol")
-    t.append_message(b"some label", b"some data")
-    got = t.challenge_bytes(b"challenge", 32).hex()
-    # The published vector is quoted from memory (no network in this image): its first 22 bytes are certain and
-    # are reproduced exactly - 176 matching bits of a Keccak output pin the whole STROBE/Merlin framing; the
-    # remaining 10 bytes are recorded from this implementation.
-    assert got.startswith("d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9b")
-    assert got == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    for t in (_native(b"test protocol"), o.MerlinTranscript(b"test protocol")):
+        t.append_message(b"some label", b"some data")
+        got = t.challenge_bytes(b"challenge", 32).hex()
+        # The published vector is quoted from memory (no network in this image): its first 22 bytes are certain and
+        # are reproduced exactly - 176 matching bits of a Keccak output pin the whole STROBE/Merlin framing; the
+        # remaining 10 bytes are recorded from this implementation.
+        assert got.startswith("d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9b")
+        assert got == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_native_transcript_equals_oracle_on_random_operation_sequences():
+    rng = random.Random(1)
+    for _ in range(20):
+        label = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 20)))
+        a, b = _native(label), o.MerlinTranscript(label)
+        for _ in range(40):
+            op = rng.randrange(5)
+            lab = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 24)))
+            if op == 0:
+                msg = bytes(rng.randrange(256) for _ in range(rng.choice((0, 1, 31, 32, 64, 96, 165, 166, 167, 400))))
+                a.append_message(lab, msg)
+                b.append_message(lab, msg)
+            elif op == 1:
+                n = rng.choice((1, 32, 64, 166, 200))
+                assert a.challenge_bytes(lab, n) == b.challenge_bytes(lab, n)
+            elif op == 2:
+                assert a.get_challenge(lab) == b.get_challenge(lab)
+            elif op == 3:
+                v = (rng.randrange(field.R), rng.randrange(field.R))
+                a.append_serializable(lab, v)
+                b.append_serializable(lab, v)
+            else:
+                p = None if rng.random() < 0.3 else (rng.randrange(field.Q), rng.randrange(field.Q))
+                a.append_g1(lab, p)
+                b.append_g1(lab, p)
+        assert a.challenge_bytes(b"end", 64) == b.challenge_bytes(b"end", 64)
+
+
+def test_append_fr_takes_montgomery_limbs():
+    a, b = _native(b"x"), _native(b"x")
+    vals = [5, field.R - 1]
+    a.append_serializable(b"evaluations", tuple(vals))
+    limbs = field.fr_to_limbs(vals)
+    check(lib.gm_transcript_append_fr(b._h, b"evaluations", 11, limbs.ctypes.data, 2))
+    assert a.get_challenge(b"challenge") == b.get_challenge(b"challenge")
+    c = a.clone()
+    assert c.challenge_bytes(b"q", 16) == a.challenge_bytes(b"q", 16)
 
 
 def test_get_challenge_is_canonical_and_deterministic():
