@@ -1,6 +1,8 @@
 // Modular inversion by batched division steps (Bernstein-Yang "safegcd", in the 30-bit-limb form popularised by
-// Pornin and by libsecp256k1's modinv32) - STAGED for round 2: validated on the host against Python integers
-// (tests/test_host_field.py::test_fast_inverse_divsteps), not yet used by any kernel.
+// Pornin and by libsecp256k1's modinv32).  Validated on the host against Python integers
+// (tests/test_host_field.py::test_fast_inverse_divsteps) and on the device (tests/test_gpu_arith.py, selftest op 7);
+// it is the inversion of every latency-critical kernel: k_aff_invert (one per warp of every affine level) and
+// k_normalize / xyzz_to_jacobian_normalized (the tail of every MSM).
 //
 // Why: the Kaliski almost-inverse of fp.cuh walks ~540 dependent big-number iterations (0.11-0.16 ms on B200, the
 // fixed cost of every affine level of the MSM and of k_normalize).  Here 30 division steps are decided on the low
@@ -195,14 +197,14 @@ GM_HD Fp<P> fp_inv_divsteps(const Fp<P>& a) {
   return (x * r2) * r2;
 }
 
-// The inversion the latency-critical kernels call (k_aff_invert, k_normalize): Kaliski today; -DGM_FAST_INV switches them
-// to the division-step inverse once it has passed the GPU parity suite.
+// The inversion the latency-critical kernels call (k_aff_invert, k_normalize).  -DGM_KALISKI_INV switches back to
+// the binary almost-inverse of fp.cuh (A/B measurements).
 template <class P>
 GM_HD Fp<P> fp_inv_serial(const Fp<P>& a) {
-#ifdef GM_FAST_INV
-  return fp_inv_divsteps(a);
-#else
+#ifdef GM_KALISKI_INV
   return fp_inv(a);
+#else
+  return fp_inv_divsteps(a);
 #endif
 }
 

@@ -13,6 +13,7 @@
 //   Jacobian : X | Y | Z, 144 B = arkworks' Projective<Config>; identity is (1,1,0)
 #pragma once
 #include "fp.cuh"
+#include "fp_inv_fast.cuh"
 
 namespace gm {
 
@@ -133,7 +134,7 @@ GM_HD XYZZ xyzz_from_jacobian(const Jacobian& j) {
 GM_HD Jacobian xyzz_to_jacobian_normalized(const XYZZ& a) {
   Jacobian j;
   if (a.is_identity()) { j.x = Fq::one(); j.y = Fq::one(); j.z = Fq::zero(); return j; }
-  Fq izzz = fp_inv(a.zzz);
+  Fq izzz = fp_inv_serial(a.zzz);
   Fq t = a.zz * izzz;       // = ZZ / ZZZ = 1 / Z
   j.x = a.x * t.sqr();      // X / ZZ
   j.y = a.y * izzz;         // Y / ZZZ

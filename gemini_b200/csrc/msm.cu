@@ -35,7 +35,6 @@
 #include "common.cuh"
 #include "g1.cuh"
 #include "g1_affine.cuh"
-#include "fp_inv_fast.cuh"
 #include "msm.cuh"
 #include "msm_mem.cuh"
 

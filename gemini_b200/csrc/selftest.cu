@@ -17,6 +17,7 @@ __global__ void k_selftest_field(int op, const F* a, const F* b, F* r, size_t n)
     case 3: z = fp_inv(x); break;
     case 4: z = x.from_mont(); break;
     case 5: z = x.to_mont(); break;
+    case 7: z = fp_inv_divsteps(x); break;
     default: z = x.sqr(); break;
   }
   r[i] = z;
@@ -46,7 +47,7 @@ using namespace gm;
 extern "C" int gm_selftest_field(gm_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, size_t n) {
   GM_ARG(ctx && a && b && r, "NULL argument");
   GM_ARG(field == 0 || field == 1, "field must be 0 (Fq) or 1 (Fr)");
-  GM_ARG(op >= 0 && op <= 6, "unknown op");
+  GM_ARG(op >= 0 && op <= 7, "unknown op");
   GM_TRY(set_device(ctx));
   const size_t bytes = n * (field == 0 ? 48 : 32);
   void *da, *db, *dr;

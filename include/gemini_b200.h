@@ -256,7 +256,8 @@ int gm_fr_div_linear_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_
 int gm_fr_fold_chain_dev(gm_ctx* ctx, const void* f_dev, size_t n, const uint64_t* challenges, size_t k, void* out_levels_dev);
 
 /* ---- self-test kernels (parity tests of the device field / curve arithmetic) ---- */
-/* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 sqr;  field: 0 = Fq (12 u32), 1 = Fr (8 u32) */
+/* op: 0 mul, 1 add, 2 sub, 3 inv (binary almost-inverse), 4 from_mont, 5 to_mont, 6 sqr, 7 inv (division steps: the one the
+ * MSM kernels use);  field: 0 = Fq (12 u32), 1 = Fr (8 u32) */
 int gm_selftest_field(gm_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, size_t n);
 /* op: 0 xyzz += affine, 1 xyzz += -affine, 2 xyzz += xyzz, 3 xyzz = 2*xyzz; out = normalised Jacobian (36 u32) */
 int gm_selftest_curve(gm_ctx* ctx, int op, const uint32_t* acc_xyzz, const uint32_t* other, uint32_t* out_jac, size_t n);

@@ -49,6 +49,12 @@ def test_field_ops(ctx, fid, p, n32):
     r2 = np.zeros_like(a2)
     check(lib.gm_selftest_field(ctx._h, fid, 3, P(a2), P(a2), P(r2), len(A2)))
     assert unpack32(r2) == [pow(x * Ri % p, -1, p) * Rm % p for x in A2]
+    # op 7: the division-step inverse used by k_aff_invert / k_normalize, on many more inputs
+    A3 = [x for x in A if x]
+    a3 = pack32(A3, n32)
+    r3 = np.zeros_like(a3)
+    check(lib.gm_selftest_field(ctx._h, fid, 7, P(a3), P(a3), P(r3), len(A3)))
+    assert unpack32(r3) == [pow(x * Ri % p, -1, p) * Rm % p for x in A3]
 
 
 def _fq_l(x):
