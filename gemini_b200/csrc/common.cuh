@@ -76,14 +76,14 @@ struct MsmScratch {
   DevBuf meta;       // counters and size histogram of the work list
   DevBuf scan_tmp;
   DevBuf bases_tmp;  // ad-hoc bases (hostbases / stream pushes with points)
-  // affine levels (msm.cu 3b): point ping-pong, prefix products, slot descriptors, butterfly products, warp totals
-  DevBuf aff_a, aff_b, aff_prefix, aff_meta, aff_others, aff_totals, aff_counts[2], aff_starts[2];
+  // affine levels (msm.cu 3b): x|y planes of the level outputs (ping-pong), prefix products, pair kinds, butterfly
+  // products, warp totals
+  DevBuf aff_a, aff_b, aff_prefix, aff_meta, aff_others, aff_totals;
   void release() {
     scalars.release(); digits.release(); sorted.release(); counts.release(); starts.release();
     cursor.release(); poff.release(); buckets.release(); partials.release(); work.release();
     split.release(); small.release(); meta.release(); scan_tmp.release(); bases_tmp.release();
     aff_a.release(); aff_b.release(); aff_prefix.release(); aff_meta.release(); aff_others.release(); aff_totals.release();
-    for (int k = 0; k < 2; k++) { aff_counts[k].release(); aff_starts[k].release(); }
   }
 };
 

@@ -9,9 +9,12 @@
 //                       (variable_base.rs:21-61), per-bucket histogram            [HBM: 32 B/term in]
 //   2 scan              exclusive prefix sum of the W * 2^(c-1) bucket counts
 //   3 k_scatter         counting sort: point references grouped by (window, bucket)
-//   3b k_aff_prepare / k_aff_invert / k_aff_finish  (x levels)
+//   3b k_aff_prepare / k_aff_invert / k_aff_finish  (x R levels)
 //                       pairwise bucket sums in AFFINE coordinates with shared inversions (g1_affine.cuh):
-//                       6 instead of 10 Fq products per addition; the survivors go on to rows 4-6
+//                       6 instead of 10 Fq products per addition; the survivors go on to rows 4-6.
+//                       Every bucket's run of references starts at a multiple of 2^R (the scan pads the counts), so
+//                       pair s of a level is positions (2s, 2s+1) of the level below: no per-slot search, no
+//                       per-level counts / scans, coalesced loads; level outputs are x / y planes (SoA)
 //   4 k_classify / k_worklist_fill
 //                       buckets are cut into work items of <= SPLIT references and the items are
 //                       ordered by size (largest first) so that the 32 lanes of a warp run equally
@@ -167,12 +170,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   return r;
 }
 
-__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ tile_sums, uint32_t M) {
+// pad = 2^R - 1: every count is rounded up to a multiple of 2^R, so every start is a multiple of 2^R (affine levels)
+__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ tile_sums, uint32_t M, uint32_t pad) {
   __shared__ uint32_t sh[33];
   const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < M) ? in[base + k] : 0; s += v[k]; }
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < M) ? ((in[base + k] + pad) & ~pad) : 0; s += v[k]; }
   uint32_t total;
   uint32_t off = block_exclusive_scan(s, sh, &total);
 #pragma unroll
@@ -226,40 +230,15 @@ __global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W
 // -------------------------------------------------------------------------------------------
 static constexpr int AFF_THREADS = 128;
 
-__global__ void k_aff_counts(const uint32_t* __restrict__ in_counts, uint32_t M, uint32_t* __restrict__ out_counts) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < M) out_counts[i] = (in_counts[i] + 1u) >> 1;
-}
-
-// largest b in [lo, hi] with starts[b] <= s (starts = exclusive scan of the counts; starts[lo] <= s)
-__device__ __forceinline__ uint32_t bucket_of_slot(const uint32_t* __restrict__ starts, uint32_t lo, uint32_t hi, uint32_t s) {
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
-    if (__ldg(starts + mid) <= s) lo = mid; else hi = mid - 1u;
-  }
-  return lo;
-}
-// the same search in a window of the scan staged in shared memory: win[i] = starts[b_lo + i], i < span
-static constexpr int AFF_WIN = 480;   // window entries per warp (a warp's slots rarely span more buckets)
-__device__ __forceinline__ uint32_t bucket_of_slot_win(const uint32_t* win, uint32_t span, uint32_t s) {
-  uint32_t lo = 0, hi = span - 1u;
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
-    if (win[mid] <= s) lo = mid; else hi = mid - 1u;
-  }
-  return lo;
-}
-
-template <bool FIRST>
-__device__ __forceinline__ Affine aff_load_input(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e, int rec_q) {
-  if (FIRST) {
-    const uint32_t ref = __ldg(refs + e);
-    Affine p = load_ro(rec_at(in, ref & 0x7FFFFFFFu, rec_q));
-    if (ref >> 31) p.y = p.y.neg();   // -(0,0) = (0,0): the identity stays the identity
-    return p;
-  }
-  return load_ro(in + e);
-}
+// A level's input: level 0 gathers table points through the sorted references (NONE marks the padding between
+// buckets), later levels read the x / y planes the level below wrote ((0,0) = identity = padding).
+struct AffIn {
+  const Affine* table;       // level 0
+  const uint32_t* refs;      // level 0: sorted references, 2 * n_slots of them
+  const Fq* x;               // level >= 1
+  const Fq* y;
+  int rec_q;
+};
 
 __device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, int m) {
   Fq r;
@@ -268,82 +247,80 @@ __device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, int m) {
   return r;
 }
 
-// x coordinate only (48 of the 96 bytes): all the classification of a generic pair needs
 template <bool FIRST>
-__device__ __forceinline__ Fq aff_load_x(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, uint32_t e, int rec_q) {
-  const Affine* p = FIRST ? rec_at(in, __ldg(refs + e) & 0x7FFFFFFFu, rec_q) : in + e;
-  return load_ro(&p->x);
+__device__ __forceinline__ Affine aff_load_point(const AffIn& in, uint32_t e, uint32_t ref) {
+  Affine p;
+  if (FIRST) {
+    if (ref == NONE) { p.x = Fq::zero(); p.y = Fq::zero(); return p; }
+    p = load_ro(rec_at(in.table, ref & 0x7FFFFFFFu, in.rec_q));
+    if (ref >> 31) p.y = p.y.neg();   // -(0,0) = (0,0): the identity stays the identity
+    return p;
+  }
+  p.x = load_ro(in.x + e);
+  p.y = load_ro(in.y + e);
+  return p;
 }
 
+// what k_aff_prepare knows about a slot after the cheap part: the two references (level 0) and the x coordinates
 struct AffSlot {
-  uint32_t e0;
-  bool valid, has2;
+  uint2 ref;      // level 0 only
   Fq x1, x2;
+  bool valid;
 };
 
 template <bool FIRST>
-__device__ __forceinline__ void aff_fetch_slot(AffSlot& sl, uint32_t s, uint32_t n_slots, uint32_t b_lo, uint32_t b_hi, const uint32_t* win,
-                                               const Affine* __restrict__ in, const uint32_t* __restrict__ refs,
-                                               const uint32_t* __restrict__ in_counts, const uint32_t* __restrict__ in_starts,
-                                               const uint32_t* __restrict__ out_starts, int rec_q) {
+__device__ __forceinline__ void aff_fetch_slot(AffSlot& sl, const AffIn& in, uint32_t s, uint32_t n_slots) {
   sl.valid = s < n_slots;
   if (!sl.valid) return;
-  uint32_t gb, start;
-  if (win != nullptr) { const uint32_t w = bucket_of_slot_win(win, b_hi - b_lo + 1u, s); gb = b_lo + w; start = win[w]; }
-  else { gb = bucket_of_slot(out_starts, b_lo, b_hi, s); start = __ldg(out_starts + gb); }
-  const uint32_t j = s - start;
-  sl.e0 = __ldg(in_starts + gb) + 2u * j;
-  sl.has2 = 2u * j + 1u < __ldg(in_counts + gb);
-  sl.x1 = aff_load_x<FIRST>(in, refs, sl.e0, rec_q);
-  sl.x2 = sl.has2 ? aff_load_x<FIRST>(in, refs, sl.e0 + 1u, rec_q) : sl.x1;
+  if (FIRST) {
+    sl.ref = __ldg(reinterpret_cast<const uint2*>(in.refs) + s);
+    sl.x1 = sl.ref.x == NONE ? Fq::zero() : load_ro(&rec_at(in.table, sl.ref.x & 0x7FFFFFFFu, in.rec_q)->x);
+    sl.x2 = sl.ref.y == NONE ? Fq::zero() : load_ro(&rec_at(in.table, sl.ref.y & 0x7FFFFFFFu, in.rec_q)->x);
+  } else {
+    sl.x1 = load_ro(in.x + 2u * s);
+    sl.x2 = load_ro(in.x + 2u * s + 1u);
+  }
+}
+
+// slots of one level = ceil(S / 2^(level+1)), S = padded length of the sorted reference array (device side)
+__device__ __forceinline__ uint32_t aff_level_slots(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts, uint32_t M,
+                                                    uint32_t pad, int level) {
+  const uint32_t S = __ldg(starts + M - 1) + ((__ldg(counts + M - 1) + pad) & ~pad);
+  return S >> (level + 1);
 }
 
 template <bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS, 4)
-k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ in_counts,
-              const uint32_t* __restrict__ in_starts, const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts,
-              uint32_t M, int G, int rec_q, Fq* __restrict__ prefix, uint2* __restrict__ slot_meta,
-              Fq* __restrict__ others, Fq* __restrict__ warp_totals) {
-  const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
+k_aff_prepare(AffIn in, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts, uint32_t M, uint32_t pad, int level, int G,
+              Fq* __restrict__ prefix, uint8_t* __restrict__ kinds, Fq* __restrict__ others, Fq* __restrict__ warp_totals) {
+  const uint32_t n_slots = aff_level_slots(starts, counts, M, pad, level);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
   if (base64 >= n_slots) return;                      // whole warp out of range
   const uint32_t base = (uint32_t)base64;
-  const uint32_t last = (uint32_t)min((uint64_t)n_slots - 1u, base64 + 32u * (uint32_t)G - 1u);
-  const uint32_t b_lo = bucket_of_slot(out_starts, 0, M - 1, base);
-  const uint32_t b_hi = bucket_of_slot(out_starts, b_lo, M - 1, last);
-  // stage the scan entries of the buckets this warp touches in shared memory: the per-slot search then costs a few
-  // shared loads instead of a chain of dependent global loads
-  __shared__ uint32_t sh_win[AFF_THREADS / 32][AFF_WIN];
-  const uint32_t* win = nullptr;
-  if (b_hi - b_lo < (uint32_t)AFF_WIN) {
-    uint32_t* w = sh_win[threadIdx.x >> 5];
-    for (uint32_t i = lane; i <= b_hi - b_lo; i += 32u) w[i] = __ldg(out_starts + b_lo + i);
-    __syncwarp();
-    win = w;
-  }
   Fq run = Fq::one();
-  // the gathers of slot k+1 (bucket search, references, x coordinates) are issued before the product of slot k
+  // the loads of slot k+1 (references, x coordinates) are issued before the product of slot k
   AffSlot cur, nxt;
-  aff_fetch_slot<FIRST>(cur, base + lane, n_slots, b_lo, b_hi, win, in, refs, in_counts, in_starts, out_starts, rec_q);
+  aff_fetch_slot<FIRST>(cur, in, base + lane, n_slots);
 #pragma unroll 1
   for (int k = 0; k < G; k++) {
     if (!cur.valid) break;
     const uint32_t s = base + (uint32_t)k * 32u + lane;
     nxt.valid = false;
-    if (k + 1 < G) aff_fetch_slot<FIRST>(nxt, s + 32u, n_slots, b_lo, b_hi, win, in, refs, in_counts, in_starts, out_starts, rec_q);
+    if (k + 1 < G) aff_fetch_slot<FIRST>(nxt, in, s + 32u, n_slots);
     Fq den = cur.x2 - cur.x1;
     uint32_t kind = PK_ADD;
-    if (!cur.has2) {
-      kind = PK_PASS1;
+    if (FIRST && cur.ref.y == NONE) {
+      kind = cur.ref.x == NONE ? PK_ZERO : PK_PASS1;      // padding / odd leftover of a bucket
     } else if (den.is_zero() || cur.x1.is_zero() || cur.x2.is_zero()) {
-      // rare: equal x (P + P, P - P) or a possible identity (0, 0): classify with the full points
-      const Affine p1 = aff_load_input<FIRST>(in, refs, cur.e0, rec_q);
-      const Affine p2 = aff_load_input<FIRST>(in, refs, cur.e0 + 1u, rec_q);
+      // rare (common only in the padding of the upper levels): equal x (P + P, P - P) or a possible identity (0, 0)
+      const Affine p1 = aff_load_point<FIRST>(in, 2u * s, FIRST ? cur.ref.x : 0u);
+      const Affine p2 = aff_load_point<FIRST>(in, 2u * s + 1u, FIRST ? cur.ref.y : 0u);
       kind = aff_pair_kind(p1, p2, true, den);
+      if (kind == PK_PASS1 && p1.is_identity()) kind = PK_ZERO;
     }
-    slot_meta[s] = make_uint2(cur.e0, kind);
+    kinds[s] = (uint8_t)kind;
     if (aff_kind_needs_inverse(kind)) {
       store_rw(prefix + s, run);
       run = run * den;
@@ -362,13 +339,12 @@ k_aff_prepare(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, 
   if (lane == 0) store_rw(warp_totals + warp, g);
 }
 
-// spread = 32: one inversion per WARP (lane 0).  The binary almost-inverse branches three ways per step, so 32
-// different inputs in one warp run every branch every step; with few inversions (they are a serial stage of the
-// level) it is faster to leave 31 lanes idle.  spread = 1: one inversion per thread (large levels).
+// spread = 32: one inversion per WARP (lane 0): with few inversions (they are a serial stage of the level) it is faster
+// to leave 31 lanes idle than to run 32 data-dependent loops in lock step.  spread = 1: one inversion per thread.
 __global__ void __launch_bounds__(128)
-k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ out_starts, uint32_t M, int G, int spread,
+k_aff_invert(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts, uint32_t M, uint32_t pad, int level, int G, int spread,
              Fq* __restrict__ warp_totals) {
-  const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
+  const uint32_t n_slots = aff_level_slots(starts, counts, M, pad, level);
   const uint64_t n_warps = ((uint64_t)n_slots + 32u * (uint32_t)G - 1u) / (32u * (uint32_t)G);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t % (uint32_t)spread) return;
@@ -379,11 +355,10 @@ k_aff_invert(const uint32_t* __restrict__ out_counts, const uint32_t* __restrict
 
 template <bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS, 4)
-k_aff_finish(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ out_counts,
-             const uint32_t* __restrict__ out_starts, uint32_t M, int G, int rec_q, const Fq* __restrict__ prefix,
-             const uint2* __restrict__ slot_meta, const Fq* __restrict__ others, const Fq* __restrict__ warp_totals,
-             Affine* __restrict__ out) {
-  const uint32_t n_slots = __ldg(out_starts + M - 1) + __ldg(out_counts + M - 1);
+k_aff_finish(AffIn in, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts, uint32_t M, uint32_t pad, int level, int G,
+             const Fq* __restrict__ prefix, const uint8_t* __restrict__ kinds, const Fq* __restrict__ others,
+             const Fq* __restrict__ warp_totals, Fq* __restrict__ out_x, Fq* __restrict__ out_y) {
+  const uint32_t n_slots = aff_level_slots(starts, counts, M, pad, level);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t base64 = (uint64_t)warp * 32u * (uint32_t)G;
@@ -395,35 +370,44 @@ k_aff_finish(const Affine* __restrict__ in, const uint32_t* __restrict__ refs, c
   for (int k = G - 1; k >= 0; k--) {
     const uint32_t s = base + (uint32_t)k * 32u + lane;
     if (s >= n_slots) continue;
-    const uint2 sm = slot_meta[s];
-    const uint32_t e0 = sm.x, kind = sm.y;
+    const uint32_t kind = kinds[s];
     Affine r;
     if (kind == PK_ZERO) { r.x = Fq::zero(); r.y = Fq::zero(); }
-    else if (kind == PK_PASS1) r = aff_load_input<FIRST>(in, refs, e0, rec_q);
-    else if (kind == PK_PASS2) r = aff_load_input<FIRST>(in, refs, e0 + 1u, rec_q);
     else {
-      const Affine p1 = aff_load_input<FIRST>(in, refs, e0, rec_q);
-      const Affine p2 = aff_load_input<FIRST>(in, refs, e0 + 1u, rec_q);
-      const Fq den = (kind == PK_ADD) ? (p2.x - p1.x) : p1.y.dbl();
-      const Fq inv_den = inv * load_rw(prefix + s);
-      inv = inv * den;
-      r = aff_pair_finish(kind, p1, p2, inv_den);
+      uint2 ref = make_uint2(0u, 0u);
+      if (FIRST) ref = __ldg(reinterpret_cast<const uint2*>(in.refs) + s);
+      if (kind == PK_PASS1) r = aff_load_point<FIRST>(in, 2u * s, ref.x);
+      else if (kind == PK_PASS2) r = aff_load_point<FIRST>(in, 2u * s + 1u, ref.y);
+      else {
+        const Affine p1 = aff_load_point<FIRST>(in, 2u * s, ref.x);
+        const Affine p2 = aff_load_point<FIRST>(in, 2u * s + 1u, ref.y);
+        const Fq den = (kind == PK_ADD) ? (p2.x - p1.x) : p1.y.dbl();
+        const Fq inv_den = inv * load_rw(prefix + s);
+        inv = inv * den;
+        r = aff_pair_finish(kind, p1, p2, inv_den);
+      }
     }
-    store_rw(out + s, r);
+    store_rw(out_x + s, r.x);
+    store_rw(out_y + s, r.y);
   }
 }
 
 // -------------------------------------------------------------------------------------------
 // 4. work list, largest items first
 // -------------------------------------------------------------------------------------------
-__global__ void k_classify(const uint32_t* __restrict__ counts, uint32_t M, uint32_t split, uint32_t* __restrict__ poff,
+// shift = number of affine levels that ran: bucket gb now holds ceil(counts[gb] / 2^shift) points
+__device__ __forceinline__ uint32_t eff_count(const uint32_t* __restrict__ counts, uint32_t gb, int shift) {
+  return (counts[gb] + (1u << shift) - 1u) >> shift;
+}
+
+__global__ void k_classify(const uint32_t* __restrict__ counts, uint32_t M, int shift, uint32_t split, uint32_t* __restrict__ poff,
                            uint32_t* __restrict__ split_list, Meta* meta) {
   __shared__ uint32_t sh[SPLIT + 1];
   for (uint32_t k = threadIdx.x; k <= split; k += blockDim.x) sh[k] = 0;
   __syncthreads();
   const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb < M) {
-    const uint32_t cnt = counts[gb];
+    const uint32_t cnt = eff_count(counts, gb, shift);
     uint32_t po = NONE;
     if (cnt) {
       const uint32_t m = (cnt + split - 1) / split;
@@ -452,7 +436,7 @@ __global__ void k_size_scan(Meta* meta, uint32_t split) {
   }
 }
 
-__global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M, uint32_t split, uint2* __restrict__ work, Meta* meta) {
+__global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M, int shift, uint32_t split, uint2* __restrict__ work, Meta* meta) {
   __shared__ uint32_t blk_cnt[SPLIT + 1];
   __shared__ uint32_t blk_base[SPLIT + 1];
   for (uint32_t k = threadIdx.x; k <= split; k += blockDim.x) blk_cnt[k] = 0;
@@ -460,7 +444,7 @@ __global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M,
   const uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t cnt = 0, m = 0, tail = 0, r_tail = 0, r_full = 0;
   if (gb < M) {
-    cnt = counts[gb];
+    cnt = eff_count(counts, gb, shift);
     if (cnt) {
       m = (cnt + split - 1) / split;
       tail = cnt - (m - 1) * split;
@@ -484,19 +468,19 @@ __global__ void k_worklist_fill(const uint32_t* __restrict__ counts, uint32_t M,
 // -------------------------------------------------------------------------------------------
 // 5. bucket accumulation: one thread per work item
 // -------------------------------------------------------------------------------------------
-// DIRECT: the input is the point array left by the affine levels (slot = position, no sign), not a reference list
+// DIRECT: the input is the x / y planes left by the affine levels (slot = position, no sign), not a reference list
 template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 3)  // 3 CTAs/SM: at most 168 registers per thread
-k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ counts,
-             const uint32_t* __restrict__ starts, const uint32_t* __restrict__ poff, const uint2* __restrict__ work,
-             const Meta* __restrict__ meta, uint32_t split, int rec_q, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
-             uint32_t* __restrict__ live) {
+k_accumulate(const Affine* __restrict__ bases, const Fq* __restrict__ px, const Fq* __restrict__ py, const uint32_t* __restrict__ sorted,
+             const uint32_t* __restrict__ counts, const uint32_t* __restrict__ starts, int shift, const uint32_t* __restrict__ poff,
+             const uint2* __restrict__ work, const Meta* __restrict__ meta, uint32_t split, int rec_q, XYZZ* __restrict__ buckets,
+             XYZZ* __restrict__ partials, uint32_t* __restrict__ live) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= meta->n_items) return;
   const uint2 item = work[j];
   const uint32_t gb = item.x, k = item.y;
-  const uint32_t cnt = counts[gb];
-  const uint32_t first = starts[gb] + k * split;
+  const uint32_t cnt = eff_count(counts, gb, shift);
+  const uint32_t first = (starts[gb] >> shift) + k * split;
   const uint32_t len = min(split, cnt - k * split);
   const uint32_t po = poff[gb];
   // streamed MSM: the bucket persists across chunks (live[gb] != 0 once it has been written)
@@ -504,7 +488,8 @@ k_accumulate(const Affine* __restrict__ bases, const uint32_t* __restrict__ sort
   for (uint32_t e = 0; e < len; e++) {
     Affine p;
     if (DIRECT) {
-      p = load_ro(bases + first + e);
+      p.x = load_ro(px + first + e);
+      p.y = load_ro(py + first + e);
     } else {
       const uint32_t ref = __ldg(sorted + first + e);
       p = load_ro(rec_at(bases, ref & 0x7FFFFFFFu, rec_q));
@@ -530,7 +515,7 @@ __device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ poff,
+k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restrict__ counts, int shift, const uint32_t* __restrict__ poff,
                 const Meta* __restrict__ meta, uint32_t split, const XYZZ* __restrict__ partials, XYZZ* __restrict__ buckets,
                 uint32_t* __restrict__ live) {
   extern __shared__ uint4 sh_raw[];
@@ -541,7 +526,7 @@ k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restr
   const uint32_t gwarp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
   for (uint32_t s = gwarp; s < ns; s += gridDim.x * warps_per_cta) {
     const uint32_t gb = split_list[s];
-    const uint32_t m = (counts[gb] + split - 1) / split;
+    const uint32_t m = (eff_count(counts, gb, shift) + split - 1) / split;
     if (m > 32) continue;
     XYZZ acc = XYZZ::identity();
     if (lane < m) acc = load_rw(partials + poff[gb] + lane);
@@ -560,7 +545,7 @@ k_split_combine(const uint32_t* __restrict__ split_list, const uint32_t* __restr
   }
   for (uint32_t s = blockIdx.x; s < ns; s += gridDim.x) {
     const uint32_t gb = split_list[s];
-    const uint32_t m = (counts[gb] + split - 1) / split;
+    const uint32_t m = (eff_count(counts, gb, shift) + split - 1) / split;
     if (m <= 32) continue;
     const XYZZ* src = partials + poff[gb];
     XYZZ acc = XYZZ::identity();
@@ -682,8 +667,23 @@ static AffShape aff_shape(const gm_ctx* ctx, size_t slots) {
   return sh;
 }
 
-// Phase A: digits, counting sort, work list, bucket accumulation.  Buckets go to `buckets`; when `live` is given the
-// buckets persist across calls (streamed MSM) and are updated in place, otherwise they are (re)written and the
+// Padded length of the sorted reference array when every bucket's run starts at a multiple of A = 2^levels: an upper bound
+// from the host's point of view (each non-empty bucket pads by at most A - 1), itself a multiple of A.
+static size_t padded_refs_bound(size_t refs, size_t M, int levels) {
+  const size_t A = (size_t)1 << levels;
+  return (refs + std::min(M, refs) * (A - 1) + A - 1) & ~(A - 1);
+}
+
+// HBM the affine levels of one pass need on top of the sort buffers: x / y planes of the first two level outputs,
+// the prefix products and the pair kinds of the first (largest) level
+static size_t affine_scratch_bytes(size_t refs, size_t M, int levels) {
+  if (levels <= 0) return 0;
+  const size_t S = padded_refs_bound(refs, M, levels);
+  return (S >> 1) * (sizeof(Affine) + sizeof(Fq) + 1) + (levels > 1 ? (S >> 2) * sizeof(Affine) : 0);
+}
+
+// Phase A: digits, counting sort, affine levels, work list, bucket accumulation.  Buckets go to `buckets`; when `live` is
+// given the buckets persist across calls (streamed MSM) and are updated in place, otherwise they are (re)written and the
 // per-call counts (ctx->msm.counts) tell which ones are valid.
 static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint,
                                const MsmPlan& P, XYZZ* buckets, uint32_t* live) {
@@ -698,8 +698,38 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   const int rec_q = merged ? B.rec_q : 6;
   const size_t refs = (size_t)P.W * n;
 
+  // affine levels before the XYZZ accumulation (0 = none); their scratch is optional: without it the XYZZ path runs alone
+  int levels = affine_levels(refs, M);
+  if (levels > 0) {
+    // the level scratch of a very large pass must not crowd out the buffers the XYZZ path needs anyway: skip the levels
+    // when the part still to be allocated exceeds half of the free HBM (only looked at above 8 GB of scratch;
+    // msm_accumulate sizes its passes so that this does not happen)
+    const size_t need = affine_scratch_bytes(refs, M, levels);
+    if (need > ((size_t)8 << 30)) {
+      const size_t have = S.aff_a.cap + S.aff_b.cap + S.aff_prefix.cap + S.aff_meta.cap;
+      size_t free_b = 0, total_b = 0;
+      if (need > have && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need - have > free_b / 2) levels = 0;
+    }
+  }
+  size_t s_max = padded_refs_bound(refs, M, levels);
+  if (levels > 0) {
+    const size_t s1 = s_max >> 1, s2 = levels > 1 ? s_max >> 2 : 0;
+    const size_t warps1 = (size_t)aff_shape(ctx, s1).warps + (size_t)ctx->sm_count * 64;   // the first level has the most warps
+    const bool ok = S.aff_a.reserve(s1 * sizeof(Affine)) == GM_OK && S.aff_b.reserve(s2 * sizeof(Affine) + 16) == GM_OK &&
+                    S.aff_prefix.reserve(s1 * sizeof(Fq)) == GM_OK && S.aff_meta.reserve(s1 + 16) == GM_OK &&
+                    S.aff_others.reserve(warps1 * 32 * sizeof(Fq)) == GM_OK && S.aff_totals.reserve(warps1 * sizeof(Fq)) == GM_OK;
+    if (!ok) {
+      S.aff_a.release(); S.aff_b.release(); S.aff_prefix.release(); S.aff_meta.release();
+      cudaGetLastError();
+      levels = 0;
+      s_max = refs;
+    }
+  }
+  const uint32_t pad = (1u << levels) - 1u;
+  const size_t refs_eff = s_max >> levels;   // upper bound of the points the XYZZ accumulation still has to add
+
   GM_TRY(S.digits.reserve(refs * 4));
-  GM_TRY(S.sorted.reserve(refs * 4));
+  GM_TRY(S.sorted.reserve(s_max * 4 + 16));
   GM_TRY(S.counts.reserve(M * 4));
   GM_TRY(S.starts.reserve(M * 4));
   GM_TRY(S.cursor.reserve(M * 4));
@@ -709,37 +739,6 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   static_assert(sizeof(Meta) <= 16384, "Meta fits its slot");
   GM_TRY(S.meta.reserve(16384));
   Meta* meta = S.meta.as<Meta>();
-
-  // affine levels before the XYZZ accumulation (0 = none); their scratch is optional: without it the XYZZ path runs alone
-  int levels = affine_levels(refs, M);
-  size_t slot_bound[9];
-  slot_bound[0] = refs;
-  for (int r = 0; r < levels; r++) slot_bound[r + 1] = (slot_bound[r] + std::min(M, slot_bound[r])) / 2 + 1;
-  if (levels > 0) {
-    // the level scratch of a very large pass must not crowd out the buffers the XYZZ path needs anyway: skip the levels
-    // when the part still to be allocated exceeds half of the free HBM (only looked at above 8 GB of scratch)
-    const size_t need = slot_bound[1] * (sizeof(Affine) + sizeof(Fq) + sizeof(uint2)) + (levels > 1 ? slot_bound[2] * sizeof(Affine) : 0);
-    if (need > ((size_t)8 << 30)) {
-      const size_t have = S.aff_a.cap + S.aff_b.cap + S.aff_prefix.cap + S.aff_meta.cap;
-      size_t free_b = 0, total_b = 0;
-      if (need > have && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need - have > free_b / 2) levels = 0;
-    }
-  }
-  if (levels > 0) {
-    const size_t s1 = slot_bound[1], s2 = levels > 1 ? slot_bound[2] : 0;
-    const size_t warps1 = (size_t)aff_shape(ctx, s1).warps + (size_t)ctx->sm_count * 64;   // the first level has the most warps
-    const bool ok = S.aff_a.reserve(s1 * sizeof(Affine)) == GM_OK && S.aff_b.reserve(s2 * sizeof(Affine) + 16) == GM_OK &&
-                    S.aff_prefix.reserve(s1 * sizeof(Fq)) == GM_OK && S.aff_meta.reserve(s1 * sizeof(uint2)) == GM_OK &&
-                    S.aff_others.reserve(warps1 * 32 * sizeof(Fq)) == GM_OK && S.aff_totals.reserve(warps1 * sizeof(Fq)) == GM_OK &&
-                    S.aff_counts[0].reserve(M * 4) == GM_OK && S.aff_counts[1].reserve(M * 4) == GM_OK &&
-                    S.aff_starts[0].reserve(M * 4) == GM_OK && S.aff_starts[1].reserve(M * 4) == GM_OK;
-    if (!ok) {
-      S.aff_a.release(); S.aff_b.release(); S.aff_prefix.release(); S.aff_meta.release();
-      cudaGetLastError();
-      levels = 0;
-    }
-  }
-  const size_t refs_eff = slot_bound[levels];   // upper bound of the points the XYZZ accumulation still has to add
 
   // references per work item: enough items to keep every SM busy with several waves, but long enough that the
   // per-item partial sums of a hot bucket stay few
@@ -756,75 +755,98 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   cudaStream_t st = ctx->stream;
   GM_CUDA(cudaMemsetAsync(S.counts.p, 0, M * 4, st));
   GM_CUDA(cudaMemsetAsync(meta, 0, sizeof(Meta), st));
+  // the padding between the buckets' runs reads as NONE (only the levels look at it)
+  if (levels > 0) GM_CUDA(cudaMemsetAsync(S.sorted.p, 0xFF, s_max * 4, st));
 
   const uint32_t n32 = (uint32_t)n;
   const uint32_t M32 = (uint32_t)M;
+  const uint32_t* counts = S.counts.as<uint32_t>();
+  const uint32_t* starts = S.starts.as<uint32_t>();
   GM_CUDA(cudaEventRecord(ctx->ev[2], st));
   LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
-  LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, S.counts.as<uint32_t>(), S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
+  LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, counts, S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32, pad);
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
   LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
   LAUNCH(ctx, k_scatter, dim3((n32 + 255) / 256, P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, merged ? 1 : 0, ref_offset, ref_stride, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
   GM_CUDA(cudaEventRecord(ctx->ev[3], st));
 
-  // ---- affine levels ----
-  const uint32_t* cur_counts = S.counts.as<uint32_t>();
-  const uint32_t* cur_starts = S.starts.as<uint32_t>();
-  const Affine* cur_pts = d_bases;
+  // ---- affine levels: level r pairs positions (2s, 2s+1) of level r-1 (level 0: of the sorted references) ----
+  Fq* cur_x = nullptr;
+  Fq* cur_y = nullptr;
   for (int r = 0; r < levels; r++) {
-    uint32_t* oc = S.aff_counts[r & 1].as<uint32_t>();
-    uint32_t* os = S.aff_starts[r & 1].as<uint32_t>();
-    Affine* out = (r & 1) ? S.aff_b.as<Affine>() : S.aff_a.as<Affine>();
-    LAUNCH(ctx, k_aff_counts, (unsigned)((M + 255) / 256), 256, 0, cur_counts, M32, oc);
-    LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, oc, os, S.scan_tmp.as<uint32_t>(), M32);
-    LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
-    LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, os, S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
-    const AffShape shp = aff_shape(ctx, slot_bound[r + 1]);
+    const size_t slots = s_max >> (r + 1);
+    DevBuf& ob = (r & 1) ? S.aff_b : S.aff_a;
+    Fq* out_x = ob.as<Fq>();
+    Fq* out_y = out_x + slots;
+    const AffShape shp = aff_shape(ctx, slots);
     const int G = shp.G;
     const unsigned ctas = shp.warps * 32 / AFF_THREADS;
-    // few inversions: one per single-warp CTA (lane 0 only: the three-way branch of the almost-inverse does not diverge)
+    // few inversions: one per single-warp CTA (lane 0 only: data-dependent loops do not diverge)
     const int spread = shp.warps <= (uint32_t)ctx->sm_count * 24 ? 32 : 1;
     const unsigned inv_threads = spread == 32 ? 32u : 128u;
     const unsigned inv_ctas = (unsigned)(((size_t)shp.warps * spread + inv_threads - 1) / inv_threads);
     Fq* prefix = S.aff_prefix.as<Fq>();
-    uint2* smeta = S.aff_meta.as<uint2>();
+    uint8_t* kinds = S.aff_meta.as<uint8_t>();
     Fq* others = S.aff_others.as<Fq>();
     Fq* totals = S.aff_totals.as<Fq>();
-    const uint32_t* refs0 = r == 0 ? S.sorted.as<uint32_t>() : nullptr;
+    AffIn in;
+    in.table = d_bases; in.refs = S.sorted.as<uint32_t>(); in.x = cur_x; in.y = cur_y; in.rec_q = rec_q;
     if (r == 0)
-      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, rec_q, prefix, smeta, others, totals);
+      LAUNCH(ctx, k_aff_prepare<true>, ctas, AFF_THREADS, 0, in, starts, counts, M32, pad, r, G, prefix, kinds, others, totals);
     else
-      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, cur_counts, cur_starts, oc, os, M32, G, rec_q, prefix, smeta, others, totals);
-    LAUNCH(ctx, k_aff_invert, inv_ctas, inv_threads, 0, oc, os, M32, G, spread, totals);
+      LAUNCH(ctx, k_aff_prepare<false>, ctas, AFF_THREADS, 0, in, starts, counts, M32, pad, r, G, prefix, kinds, others, totals);
+    LAUNCH(ctx, k_aff_invert, inv_ctas, inv_threads, 0, starts, counts, M32, pad, r, G, spread, totals);
     if (r == 0)
-      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, rec_q, prefix, smeta, others, totals, out);
+      LAUNCH(ctx, k_aff_finish<true>, ctas, AFF_THREADS, 0, in, starts, counts, M32, pad, r, G, prefix, kinds, others, totals, out_x, out_y);
     else
-      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, cur_pts, refs0, oc, os, M32, G, rec_q, prefix, smeta, others, totals, out);
-    cur_counts = oc; cur_starts = os; cur_pts = out;
+      LAUNCH(ctx, k_aff_finish<false>, ctas, AFF_THREADS, 0, in, starts, counts, M32, pad, r, G, prefix, kinds, others, totals, out_x, out_y);
+    cur_x = out_x; cur_y = out_y;
   }
 
-  LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, cur_counts, M32, split, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
+  LAUNCH(ctx, k_classify, (unsigned)((M + 255) / 256), 256, 0, counts, M32, levels, split, S.poff.as<uint32_t>(), S.split.as<uint32_t>(), meta);
   LAUNCH(ctx, k_size_scan, 1, 32, 0, meta, split);
-  LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, cur_counts, M32, split, S.work.as<uint2>(), meta);
+  LAUNCH(ctx, k_worklist_fill, (unsigned)((M + 255) / 256), 256, 0, counts, M32, levels, split, S.work.as<uint2>(), meta);
   const unsigned acc_ctas = (unsigned)((max_items + ACC_THREADS - 1) / ACC_THREADS);
   if (levels > 0)
-    LAUNCH(ctx, k_accumulate<true>, acc_ctas, ACC_THREADS, 0, cur_pts, (const uint32_t*)nullptr, cur_counts, cur_starts, S.poff.as<uint32_t>(),
-           S.work.as<uint2>(), meta, split, rec_q, buckets, S.partials.as<XYZZ>(), live);
+    LAUNCH(ctx, k_accumulate<true>, acc_ctas, ACC_THREADS, 0, (const Affine*)nullptr, cur_x, cur_y, (const uint32_t*)nullptr, counts, starts, levels,
+           S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, split, rec_q, buckets, S.partials.as<XYZZ>(), live);
   else
-    LAUNCH(ctx, k_accumulate<false>, acc_ctas, ACC_THREADS, 0, d_bases, S.sorted.as<uint32_t>(), cur_counts, cur_starts, S.poff.as<uint32_t>(),
-           S.work.as<uint2>(), meta, split, rec_q, buckets, S.partials.as<XYZZ>(), live);
+    LAUNCH(ctx, k_accumulate<false>, acc_ctas, ACC_THREADS, 0, d_bases, (const Fq*)nullptr, (const Fq*)nullptr, S.sorted.as<uint32_t>(), counts, starts, 0,
+           S.poff.as<uint32_t>(), S.work.as<uint2>(), meta, split, rec_q, buckets, S.partials.as<XYZZ>(), live);
   GM_CUDA(cudaEventRecord(ctx->ev[4], st));
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_split_combine, (unsigned)std::min<size_t>(max_split, (size_t)ctx->sm_count * 4), RED_THREADS, red_sh, S.split.as<uint32_t>(),
-         cur_counts, S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), buckets, live);
+         counts, levels, S.poff.as<uint32_t>(), meta, split, S.partials.as<XYZZ>(), buckets, live);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
 
+// Largest pass (a power-of-two number of terms, at most 2^27: W * n references are addressed with 31 bits + sign) whose
+// sort buffers and affine-level scratch fit in the HBM that is free now plus what the scratch arena already holds.
+static size_t msm_pass_size(gm_ctx* ctx, const MsmBases& B, size_t n) {
+  size_t m = (size_t)1 << 27;
+  if (n <= ((size_t)1 << 24)) return std::min(n, m);     // up to 2^24 terms always fit next to their table (19 GB)
+  const MsmScratch& S = ctx->msm;
+  const size_t have = S.digits.cap + S.sorted.cap + S.aff_a.cap + S.aff_b.cap + S.aff_prefix.cap + S.aff_meta.cap;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return std::min(n, m);
+  const size_t budget = have + free_b - std::min<size_t>(free_b, (size_t)4 << 30);   // keep 4 GB of head room
+  while (m > ((size_t)1 << 22)) {
+    const MsmPlan P = B.table != nullptr ? msm_plan_merged(std::min(m, n), B.c) : msm_plan(std::min(m, n));
+    const size_t M = (size_t)(P.merged ? 1 : P.W) * P.nb;
+    const size_t refs = (size_t)P.W * std::min(m, n);
+    const int levels = affine_levels(refs, M);
+    const size_t need = refs * 4 + padded_refs_bound(refs, M, levels) * 4 + affine_scratch_bytes(refs, M, levels);
+    if (need <= budget) break;
+    m >>= 1;
+  }
+  return std::min(n, m);
+}
+
 
 int msm_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc) {
-  // W * n references are addressed with 32 bits (31 + sign for table references): run very large inputs as several passes
-  const size_t max_pass = (size_t)1 << 27;
+  // very large inputs run as several passes (reference width, HBM for the level scratch); each pass reduces its buckets
+  const size_t max_pass = msm_pass_size(ctx, B, n);
   for (size_t off = 0; off < n; off += max_pass) {
     const size_t m = std::min(max_pass, n - off);
     const MsmPlan P = plan_for(B, m);
@@ -864,7 +886,7 @@ void msm_describe_plan(size_t n, bool with_table, int sm_count, int out[8]) {
   const int levels = affine_levels(refs, M);
   gm_ctx fake;
   fake.sm_count = sm_count;
-  const size_t s1 = (refs + std::min(M, refs)) / 2 + 1;
+  const size_t s1 = padded_refs_bound(refs, M, levels) >> 1;
   const AffShape sh = aff_shape(&fake, s1);
   out[0] = P.c; out[1] = P.W; out[2] = (int)P.nb; out[3] = P.merged ? 1 : 0; out[4] = levels;
   out[5] = sh.G; out[6] = (int)sh.warps; out[7] = P.L;

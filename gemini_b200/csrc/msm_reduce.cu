@@ -19,7 +19,9 @@ namespace gm {
   } while (0)
 
 // 7. running-sum reduction over slices of L consecutive buckets of one window
-__global__ void __launch_bounds__(64, 6)   // <= 170 registers: 12 warps / SM (ncu r02: 255 registers = 8 warps, latency bound)
+// (ncu r02: 255 registers, 8 warps / SM, 67 % sm throughput.  Capping the registers at 168 for 12 warps / SM spills
+// 1.2 KB per thread and was measured slower: 1.90 vs 1.72 ms for the whole reduction at 2^20.)
+__global__ void __launch_bounds__(128)
 k_bucket_chunks(const XYZZ* __restrict__ buckets, const uint32_t* __restrict__ counts, uint32_t nb, int L, uint32_t nchunks,
                 int W, XYZZ* __restrict__ chunk_s, XYZZ* __restrict__ chunk_w) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,7 +223,7 @@ int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_
   XYZZ* part = reinterpret_cast<XYZZ*>(sm + off_bp);
   XYZZ* win_sum = reinterpret_cast<XYZZ*>(sm + off_ws);
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
-  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 63) / 64, Weff), 64, 0, buckets, valid, P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
+  LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, buckets, valid, P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
   LAUNCH(ctx, k_rowcol, dim3(2 * H2 + L2, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
   LAUNCH(ctx, k_weighted, dim3(nparts, Weff), RED_THREADS, red_sh, row_sum, col_sum, H2, L2, log_l2, ctas_c, part);
   LAUNCH(ctx, k_window_total, Weff, 2 * RED_THREADS, 2 * red_sh, part, nparts, wrow_sum, H2, log_l, P.c, merged ? 1 : 0, win_sum);
