@@ -205,109 +205,20 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ co
 // -------------------------------------------------------------------------------------------
 // 3. counting-sort scatter
 // -------------------------------------------------------------------------------------------
-// Each thread places SCATTER_ILP references: the cursor atomics return a value the store depends on, so a thread with one
-// item spends its life waiting for one L2 round trip (ncu r02: 282 warps stalled on the long scoreboard per issue at
-// 83 % occupancy); several independent atomics per thread multiply the requests in flight.
-static constexpr int SCATTER_ILP = 4;
-__global__ void __launch_bounds__(256)
-k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W, uint32_t nb, int merged, uint32_t ref_offset,
-          uint32_t ref_stride, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+// Measured on B200 (profiles/r02_summary.md): 2^24 terms = 201 M references in 6.2 ms.  The kernel waits on the cursor atomics
+// (they return the position the store depends on); 4 independent atomics per thread, and a two-pass variant that first groups
+// the references by the top 8 bits of the bucket index so that the scatter works inside an L2-sized window, were both
+// measured and gave 6.2 and 7.5 ms: the rate of returning L2 atomics is the bound, not latency or DRAM traffic.  A
+// register-free prefetch.global.L2 ring for the table gathers of the first affine level was measured too: 65.8 vs 55.1 ms.
+__global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W, uint32_t nb, int merged, uint32_t ref_offset,
+                          uint32_t ref_stride, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = blockIdx.y;
-  const uint32_t i0 = blockIdx.x * (256u * SCATTER_ILP) + threadIdx.x;
-  uint32_t code[SCATTER_ILP], pos[SCATTER_ILP];
-#pragma unroll
-  for (int k = 0; k < SCATTER_ILP; k++) {
-    const uint32_t i = i0 + (uint32_t)k * 256u;
-    code[k] = i < n ? __ldg(digits + (size_t)w * n + i) : SKIP;
-  }
-#pragma unroll
-  for (int k = 0; k < SCATTER_ILP; k++)
-    pos[k] = warp_agg_atomic_inc(cursor, (merged ? 0 : (size_t)w * nb) + (code[k] & 0x7FFFFFFFu), code[k] != SKIP);
+  const uint32_t code = i < n ? digits[(size_t)w * n + i] : SKIP;
+  const bool live = code != SKIP;
+  const uint32_t pos = warp_agg_atomic_inc(cursor, (merged ? 0 : (size_t)w * nb) + (code & 0x7FFFFFFFu), live);
   // reference into the base table: level w of the precomputed table when merged
-#pragma unroll
-  for (int k = 0; k < SCATTER_ILP; k++)
-    if (code[k] != SKIP) sorted[pos[k]] = (i0 + (uint32_t)k * 256u + ref_offset + (uint32_t)w * ref_stride) | (code[k] & 0x80000000u);
-}
-
-// -------------------------------------------------------------------------------------------
-// 3'. Large sorts in two passes.  One pass of k_scatter drops 4-byte references at random places of a > 100 MB array:
-//     every store dirties a different 32-byte sector and most of them leave L2 before their neighbours arrive (ncu r02, 2^24
-//     terms: 5.2 GB written and 4.5 GB read for 0.8 GB of references, 6.5 ms).  k_partition first groups (code, reference)
-//     items by the top bits of their bucket index - at most PART_MAX groups, a CTA stages PART_TILE items, reserves one range
-//     per group with one atomic and writes runs of consecutive items - and k_scatter_items then walks the grouped items in
-//     order, so that the CTAs in flight at any time scatter into a window of a few MB that lives in L2.
-static constexpr int PART_BITS = 8;
-static constexpr int PART_MAX = 1 << PART_BITS;
-static constexpr int PART_THREADS = 256;
-static constexpr int PART_ITEMS = 16;
-static constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
-
-// part_cursor[p] = start of the first bucket of group p (the groups' regions in the item array mirror the buckets' runs)
-__global__ void k_part_init(const uint32_t* __restrict__ starts, uint32_t M, int part_shift, uint32_t* __restrict__ part_start,
-                            uint32_t* __restrict__ part_cursor) {
-  const uint32_t p = threadIdx.x;
-  const uint32_t first = p << part_shift;
-  if (p < PART_MAX) {
-    const uint32_t v = first < M ? starts[first] : 0xFFFFFFFFu;
-    part_start[p] = v;
-    part_cursor[p] = v;
-  }
-}
-
-__global__ void __launch_bounds__(PART_THREADS)
-k_partition(const uint32_t* __restrict__ digits, uint32_t n, uint32_t nb, int merged, uint32_t ref_offset, uint32_t ref_stride,
-            int part_shift, uint32_t* __restrict__ part_cursor, uint2* __restrict__ items) {
-  __shared__ uint32_t hist[PART_MAX];
-  __shared__ uint32_t base[PART_MAX];
-  const int w = blockIdx.y;
-  for (int k = threadIdx.x; k < PART_MAX; k += PART_THREADS) hist[k] = 0;
-  __syncthreads();
-  const uint32_t tile0 = blockIdx.x * PART_TILE;
-  uint32_t code[PART_ITEMS], rank[PART_ITEMS];
-#pragma unroll
-  for (int k = 0; k < PART_ITEMS; k++) {
-    const uint32_t i = tile0 + (uint32_t)k * PART_THREADS + threadIdx.x;
-    code[k] = i < n ? __ldg(digits + (size_t)w * n + i) : SKIP;
-    const bool live = code[k] != SKIP;
-    const uint32_t gb = (merged ? 0u : (uint32_t)w * nb) + (code[k] & 0x7FFFFFFFu);
-    // shared-memory counters, warp-aggregated like the global ones: all-equal scalars put a whole tile in one group
-    rank[k] = warp_agg_atomic_inc(hist, live ? (gb >> part_shift) : 0u, live);
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < PART_MAX; k += PART_THREADS) base[k] = hist[k] ? atomicAdd(part_cursor + k, hist[k]) : 0u;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < PART_ITEMS; k++) {
-    if (code[k] == SKIP) continue;
-    const uint32_t i = tile0 + (uint32_t)k * PART_THREADS + threadIdx.x;
-    const uint32_t gb = (merged ? 0u : (uint32_t)w * nb) + (code[k] & 0x7FFFFFFFu);
-    const uint32_t ref = (i + ref_offset + (uint32_t)w * ref_stride) | (code[k] & 0x80000000u);
-    items[base[gb >> part_shift] + rank[k]] = make_uint2(gb, ref);
-  }
-}
-
-// position t of the item array belongs to the group whose region contains it; it holds an item if it lies below that
-// group's cursor (the regions have slack: they are as long as the buckets' padded runs)
-__global__ void __launch_bounds__(256)
-k_scatter_items(const uint2* __restrict__ items, uint32_t total, const uint32_t* __restrict__ part_start, const uint32_t* __restrict__ part_cursor,
-                uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-  __shared__ uint32_t ps[PART_MAX], pc[PART_MAX];
-  for (int k = threadIdx.x; k < PART_MAX; k += blockDim.x) { ps[k] = part_start[k]; pc[k] = part_cursor[k]; }
-  __syncthreads();
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = t < total;
-  uint2 it = make_uint2(0u, 0u);
-  if (live) {
-    int lo = 0, hi = PART_MAX - 1;      // largest group with ps[group] <= t (empty tail groups have ps = 0xFFFFFFFF)
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (ps[mid] <= t) lo = mid; else hi = mid - 1;
-    }
-    live = t < pc[lo];
-    if (live) it = items[t];
-  }
-  const uint32_t pos = warp_agg_atomic_inc(cursor, it.x, live);
-  if (live) sorted[pos] = it.y;
+  if (live) sorted[pos] = (i + ref_offset + (uint32_t)w * ref_stride) | (code & 0x80000000u);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -376,20 +287,6 @@ __device__ __forceinline__ void aff_fetch_slot(AffSlot& sl, const AffIn& in, uin
   }
 }
 
-// Gather latency of the first level: the table points a slot needs sit at random places of a multi-GB table, a warp can
-// only keep a slot or two of loads in flight in registers, and 16 warps per SM do not cover DRAM latency with that
-// (ncu r02, k_aff_prepare<1> at 2^24: 11.8 warps stalled on the long scoreboard per issue, 46 % sm throughput).
-// prefetch.global.L2 costs no registers: the references of the slot AFF_PF_REFS iterations ahead are loaded (coalesced)
-// into a small ring, and AFF_PF iterations ahead their table records are requested into L2, so the demand loads hit L2.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_record(const Affine* table, uint32_t ref, int rec_q, uint32_t first, uint32_t last) {
-  if (ref == NONE) return;
-  const char* p = reinterpret_cast<const char*>(rec_at(table, ref & 0x7FFFFFFFu, rec_q));
-  prefetch_l2(p + first);
-  prefetch_l2(p + last);
-}
-static constexpr int AFF_PF = 3;         // prefetch distance in loop iterations (slots of this lane)
-
 // slots of one level = ceil(S / 2^(level+1)), S = padded length of the sorted reference array (device side)
 __device__ __forceinline__ uint32_t aff_level_slots(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts, uint32_t M,
                                                     uint32_t pad, int level) {
@@ -411,28 +308,10 @@ k_aff_prepare(AffIn in, const uint32_t* __restrict__ starts, const uint32_t* __r
   // the loads of slot k+1 (references, x coordinates) are issued before the product of slot k
   AffSlot cur, nxt;
   aff_fetch_slot<FIRST>(cur, in, base + lane, n_slots);
-  // level 0: references of the slots AFF_PF .. 2 AFF_PF - 1 iterations ahead (see prefetch_l2)
-  const uint2 none2 = make_uint2(NONE, NONE);
-  uint2 ring[AFF_PF];
-  if (FIRST) {
-#pragma unroll
-    for (int a = 0; a < AFF_PF; a++) {
-      const uint32_t sa = base + (uint32_t)(AFF_PF + a) * 32u + lane;
-      ring[a] = (AFF_PF + a < G && sa < n_slots) ? __ldg(reinterpret_cast<const uint2*>(in.refs) + sa) : none2;
-    }
-  }
 #pragma unroll 1
   for (int k = 0; k < G; k++) {
     if (!cur.valid) break;
     const uint32_t s = base + (uint32_t)k * 32u + lane;
-    if (FIRST) {
-      prefetch_record(in.table, ring[0].x, in.rec_q, 0, 47);
-      prefetch_record(in.table, ring[0].y, in.rec_q, 0, 47);
-#pragma unroll
-      for (int a = 0; a + 1 < AFF_PF; a++) ring[a] = ring[a + 1];
-      const uint32_t sa = s + (uint32_t)(2 * AFF_PF) * 32u;
-      ring[AFF_PF - 1] = (k + 2 * AFF_PF < G && sa < n_slots) ? __ldg(reinterpret_cast<const uint2*>(in.refs) + sa) : none2;
-    }
     nxt.valid = false;
     if (k + 1 < G) aff_fetch_slot<FIRST>(nxt, in, s + 32u, n_slots);
     Fq den = cur.x2 - cur.x1;
@@ -492,29 +371,9 @@ k_aff_finish(AffIn in, const uint32_t* __restrict__ starts, const uint32_t* __re
   const uint32_t base = (uint32_t)base64;
   // 1 / (my total) = 1 / (warp total) * (product of the other lanes' totals)
   Fq inv = load_rw(warp_totals + warp) * load_rw(others + (size_t)warp * 32u + lane);
-  // level 0: the loop walks the slots downwards; ring = references of the slots AFF_PF .. 2 AFF_PF - 1 iterations ahead
-  const uint2 none2 = make_uint2(NONE, NONE);
-  uint2 ring[AFF_PF];
-  if (FIRST) {
-#pragma unroll
-    for (int a = 0; a < AFF_PF; a++) {
-      const int ka = G - 1 - (AFF_PF + a);
-      const uint32_t sa = base + (uint32_t)max(ka, 0) * 32u + lane;
-      ring[a] = (ka >= 0 && sa < n_slots) ? __ldg(reinterpret_cast<const uint2*>(in.refs) + sa) : none2;
-    }
-  }
 #pragma unroll 1
   for (int k = G - 1; k >= 0; k--) {
     const uint32_t s = base + (uint32_t)k * 32u + lane;
-    if (FIRST) {
-      prefetch_record(in.table, ring[0].x, in.rec_q, 0, 95);
-      prefetch_record(in.table, ring[0].y, in.rec_q, 0, 95);
-#pragma unroll
-      for (int a = 0; a + 1 < AFF_PF; a++) ring[a] = ring[a + 1];
-      const int ka = k - 2 * AFF_PF;
-      const uint32_t sa = base + (uint32_t)max(ka, 0) * 32u + lane;
-      ring[AFF_PF - 1] = (ka >= 0 && sa < n_slots) ? __ldg(reinterpret_cast<const uint2*>(in.refs) + sa) : none2;
-    }
     if (s >= n_slots) continue;
     const uint32_t kind = kinds[s];
     Affine r;
@@ -881,12 +740,7 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   GM_TRY(S.cursor.reserve(M * 4));
   GM_TRY(S.poff.reserve(M * 4));
   const size_t ntiles = (M + SCAN_TILE - 1) / SCAN_TILE;
-  GM_TRY(S.scan_tmp.reserve((ntiles + 4 + 2 * PART_MAX) * 4 + 16));
-  // two-pass sort (k_partition + k_scatter_items) for large passes; its item array borrows the prefix-product buffer of
-  // the levels (8 bytes per padded reference <= 48 bytes per first-level slot), so it needs the levels' scratch
-  int part_shift = 0;
-  while (((M - 1) >> part_shift) >= (size_t)PART_MAX) part_shift++;
-  const bool two_pass = levels > 0 && refs >= ((size_t)1 << env_int("GM_SORT_2PASS_LOG", 40)) && S.aff_prefix.cap >= s_max * sizeof(uint2);
+  GM_TRY(S.scan_tmp.reserve(ntiles * 4 + 16));
   static_assert(sizeof(Meta) <= 16384, "Meta fits its slot");
   GM_TRY(S.meta.reserve(16384));
   Meta* meta = S.meta.as<Meta>();
@@ -918,18 +772,7 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, counts, S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32, pad);
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
   LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
-  if (two_pass) {
-    uint32_t* part_start = S.scan_tmp.as<uint32_t>() + ((ntiles + 3) & ~(size_t)3);
-    uint32_t* part_cursor = part_start + PART_MAX;
-    uint2* items = S.aff_prefix.as<uint2>();      // free until the first level runs
-    LAUNCH(ctx, k_part_init, 1, PART_MAX, 0, starts, M32, part_shift, part_start, part_cursor);
-    LAUNCH(ctx, k_partition, dim3((n32 + PART_TILE - 1) / PART_TILE, P.W), PART_THREADS, 0, S.digits.as<uint32_t>(), n32, P.nb, merged ? 1 : 0,
-           ref_offset, ref_stride, part_shift, part_cursor, items);
-    LAUNCH(ctx, k_scatter_items, (unsigned)((s_max + 255) / 256), 256, 0, items, (uint32_t)s_max, part_start, part_cursor, S.cursor.as<uint32_t>(),
-           S.sorted.as<uint32_t>());
-  } else {
-    LAUNCH(ctx, k_scatter, dim3((n32 + 256 * SCATTER_ILP - 1) / (256 * SCATTER_ILP), P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, merged ? 1 : 0, ref_offset, ref_stride, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
-  }
+  LAUNCH(ctx, k_scatter, dim3((n32 + 255) / 256, P.W), 256, 0, S.digits.as<uint32_t>(), n32, P.W, P.nb, merged ? 1 : 0, ref_offset, ref_stride, S.cursor.as<uint32_t>(), S.sorted.as<uint32_t>());
   GM_CUDA(cudaEventRecord(ctx->ev[3], st));
 
   // ---- affine levels: level r pairs positions (2s, 2s+1) of level r-1 (level 0: of the sorted references) ----

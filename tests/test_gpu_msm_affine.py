@@ -14,15 +14,10 @@ pytestmark = pytest.mark.gpu
 G = golden_util.load()
 
 
-@pytest.fixture(params=[(1, False), (2, False), (5, False), (2, True), (4, True)], ids=lambda p: f"levels{p[0]}{'-2pass' if p[1] else ''}")
+@pytest.fixture(params=[1, 2, 4, 5])
 def levels(request, monkeypatch):
-    """(number of forced affine levels, two-pass sort forced on): GM_SORT_2PASS_LOG=0 sends every input through
-    k_partition + k_scatter_items, which large passes (>= 2^23 references) use on their own"""
-    lv, two_pass = request.param
-    monkeypatch.setenv("GM_MSM_AFFINE", str(lv))
-    if two_pass:
-        monkeypatch.setenv("GM_SORT_2PASS_LOG", "0")
-    return lv
+    monkeypatch.setenv("GM_MSM_AFFINE", str(request.param))
+    return request.param
 
 
 def run(ctx, bases, scalars):
