@@ -57,6 +57,7 @@ struct gm_msm_stream {
   cudaEvent_t copied[2] = {}, consumed[2] = {};
   bool used[2] = {false, false};
   unsigned turn = 0;
+  bool holds_ctx_ref = true;   // false for the context's own internal stream (gm_msm_g1 of large host inputs)
 };
 
 struct gm_sumcheck {
@@ -148,6 +149,7 @@ int gm_shutdown(gm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     comm_destroy(ctx);
+    if (ctx->host_stream) { gm_msm_stream_free(ctx->host_stream); ctx->host_stream = nullptr; }
     ctx->msm.release();
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
@@ -499,16 +501,52 @@ int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void
                     out_jacobian);
 }
 
+static int stream_create(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, bool holds_ctx_ref, gm_msm_stream** out);
+static int stream_flush(gm_msm_stream* s);
+
+// Host scalars.  A large input is fed through the context's internal msm stream in a few chunks: the H2D copy of
+// chunk k+1 (copy stream, double-buffered staging) overlaps the sort and bucket accumulation of chunk k, the buckets stay
+// resident and the reduction runs once - msm_chunks (src/kzg/space.rs:22-55) applied to our own entry point.  It is what
+// makes a call from ordinary pageable memory (an arkworks &[Fr]) cost little more than one from pinned memory: the
+// driver's staged pageable copy (about 11 GB/s) hides behind the kernels instead of preceding them.
+// GM_E2E_CHUNKS overrides the number of chunks (1 = one copy, then the one-shot pipeline).
+static int msm_host(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n, bool bigint, uint64_t out[18],
+                    bool sharded) {
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  int chunks = 1;
+  if (n >= ((size_t)1 << 23)) chunks = 4;
+  if (const char* e = getenv("GM_E2E_CHUNKS")) { if (atoi(e) > 0) chunks = atoi(e); }
+  if (chunks <= 1 || n < (size_t)chunks) {
+    GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
+    if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, bigint, out, sharded);
+  }
+  if (!ctx->host_stream) GM_TRY(stream_create(ctx, nullptr, 0, /*holds_ctx_ref=*/false, &ctx->host_stream));
+  gm_msm_stream* s = ctx->host_stream;
+  const size_t step = (n + chunks - 1) / chunks;
+  GM_TRY(stream_flush(s));                      // nothing pending: resets the plan
+  GM_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(XYZZ), ctx->stream));
+  s->srs = srs;
+  s->chunk_cap = step;
+  for (size_t off = 0; off < n; off += step) {
+    const size_t m = std::min(step, n - off);
+    GM_TRY(gm_msm_stream_push(s, nullptr, 0, -1, base_offset + off, scalars + 4 * off, m, bigint ? 1 : 0));
+  }
+  const int rc = sharded ? gm_msm_stream_finalize_sharded(s, out) : gm_msm_stream_finalize(s, out);
+  s->srs = nullptr;
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaEventSynchronize(ctx->ev[1]));
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  return rc;
+}
+
 int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
               int scalars_are_bigint, uint64_t out_jacobian[18]) {
   GM_ARG(ctx && srs && out_jacobian && (scalars || n == 0), "NULL argument");
   GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
   GM_ENTER(ctx);
   n = std::min(n, srs->n - base_offset);
-  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
-  if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian);
+  return msm_host(ctx, srs, base_offset, scalars, n, scalars_are_bigint != 0, out_jacobian, /*sharded=*/false);
 }
 
 // Multi-GPU MSM: `srs` holds THIS rank's contiguous range of the points and `scalars` the matching
@@ -530,11 +568,7 @@ int gm_msm_g1_sharded(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const 
   GM_ARG(base_offset <= srs->n, "base_offset beyond the SRS");
   GM_ENTER(ctx);
   n = std::min(n, srs->n - base_offset);
-  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
-  if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, scalars_are_bigint != 0, out_jacobian,
-                    /*sharded=*/true);
+  return msm_host(ctx, srs, base_offset, scalars, n, scalars_are_bigint != 0, out_jacobian, /*sharded=*/true);
 }
 
 int gm_msm_g1_checked(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, size_t bases_len, const uint64_t* scalars,
@@ -587,6 +621,7 @@ int gm_g1_sum(gm_ctx* ctx, const uint64_t* jacobians, size_t k, uint64_t out_jac
 }
 
 // ---- streamed MSM ------------------------------------------------------------------------
+static int stream_create(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, bool holds_ctx_ref, gm_msm_stream** out);
 static int stream_flush(gm_msm_stream* s) {
   if (s->plan_set && s->dirty) {
     GM_TRY(msm_stream_reduce(s->ctx, s->plan, s->buckets.as<XYZZ>(), s->live.as<uint32_t>(), s->d_acc));
@@ -600,10 +635,15 @@ static int stream_flush(gm_msm_stream* s) {
 int gm_msm_stream_new(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, gm_msm_stream** out) {
   GM_ARG(ctx && out, "NULL argument");
   GM_ENTER(ctx);
+  return stream_create(ctx, srs_or_null, chunk_cap, /*holds_ctx_ref=*/true, out);
+}
+
+static int stream_create(gm_ctx* ctx, const gm_srs* srs_or_null, size_t chunk_cap, bool holds_ctx_ref, gm_msm_stream** out) {
   gm_msm_stream* s = new (std::nothrow) gm_msm_stream();
   if (!s) return GM_ERR_OOM;
   s->ctx = ctx;
-  ctx_retain(ctx);
+  s->holds_ctx_ref = holds_ctx_ref;
+  if (holds_ctx_ref) ctx_retain(ctx);
   s->srs = srs_or_null;
   s->chunk_cap = chunk_cap;
   cudaError_t e = cudaMalloc(&s->d_acc, sizeof(XYZZ));
@@ -738,8 +778,9 @@ int gm_msm_stream_free(gm_msm_stream* s) {
       if (s->consumed[k]) cudaEventDestroy(s->consumed[k]);
     }
   }
+  const bool release = s->holds_ctx_ref;
   delete s;
-  ctx_release(ctx);
+  if (release) ctx_release(ctx);
   return GM_OK;
 }
 

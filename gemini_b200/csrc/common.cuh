@@ -119,6 +119,7 @@ struct gm_ctx {
   gm::DevBuf fr_red;         // reduction partials + ticket + result of the Fr vector helpers
   gm::DevBuf fr_div;         // level arrays of the synthetic-division scan
   gm_comm* comm = nullptr;   // set by gm_comm_init (multi-GPU jobs)
+  gm_msm_stream* host_stream = nullptr;   // internal msm stream of gm_msm_g1 for large host inputs (chunked H2D / compute overlap)
 };
 
 struct gm_srs {
