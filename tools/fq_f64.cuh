@@ -13,7 +13,7 @@
 // The identical source runs on the host (std::fma), where tests/test_host_field.py compares it with
 // Python integers.
 #pragma once
-#include "fp.cuh"
+#include "../gemini_b200/csrc/fp.cuh"
 #if !defined(__CUDA_ARCH__)
 #include <cmath>
 #include <cstring>

@@ -1,6 +1,6 @@
 // Throughput of Fq Montgomery multiplication on B200: integer (IMAD.WIDE) path, FP64 (DFMA) path, and both
 // at once with the warps of each CTA split between the two pipes.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gemini_b200/csrc -o tools/bin/mul_microbench tools/mul_microbench.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/mul_microbench tools/mul_microbench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "fq_f64.cuh"
