@@ -352,10 +352,12 @@ int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len) {
   GM_ENTER(ctx);
   if (srs->n == 0) return GM_OK;
   srs_drop_tables(srs);
-  // table 0 covers the whole SRS; tables 1, 2 cover prefixes 8x and 64x shorter (kept while >= 2^12 points)
+  // table 0 covers the whole SRS; tables 1..4 cover prefixes 8x, 64x, 512x and 4096x shorter (kept while >= 2^12 points),
+  // each with the window size its own length calls for: a short commitment (the 23 fold levels of tensorcheck go down
+  // to 2 coefficients) then reduces a few thousand buckets instead of the 2^21 of the full table
   size_t prefix = srs->n;
   size_t expect = expected_msm_len ? std::min(expected_msm_len, srs->n) : srs->n;
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < 5; k++) {
     if (k > 0 && prefix < ((size_t)1 << 12)) break;
     const MsmPlan P = msm_plan_merged(std::min(expect, prefix), 0);
     GM_ARG((double)P.W * (double)prefix < 2147483648.0, "SRS too large for a precomputed table (W * n must stay below 2^31)");

@@ -136,7 +136,7 @@ struct gm_srs {
     int c = 0, W = 0;
     int rec_q = 6;  // 16-byte quads per record (8 = padded to 128 B)
   };
-  PreTable pre[3];
+  PreTable pre[5];
   int npre = 0;
 };
 

@@ -87,9 +87,9 @@ int gm_srs_fill_g1(gm_ctx* ctx, const uint64_t point_xy[12], size_t n, gm_srs** 
 /* Optional, one-time (key setup, like CommitterKey::new): store 2^(c*w) * P_i for every window w next to
  * the points (levels x n x 96 B of HBM; 1.3 GB for n = 2^20, 19 GB for n = 2^24).  MSMs over this SRS
  * then use ONE shared bucket set for all windows: no per-window running sums and no serial 2^(c*w)
- * doubling tail.  expected_msm_len (0 = the SRS length) picks the window size.  Two further tables over the
- * first n/8 and n/64 points (with smaller windows) serve short commitments against a long SRS - the fold
- * levels committed by tensorcheck.  Results are identical. */
+ * doubling tail.  expected_msm_len (0 = the SRS length) picks the window size.  Up to four further tables over the
+ * first n/8, n/64, n/512 and n/4096 points (with smaller windows) serve short commitments against a long SRS - the
+ * fold levels committed by tensorcheck.  Results are identical. */
 int gm_srs_precompute(gm_ctx* ctx, gm_srs* srs, size_t expected_msm_len);
 int gm_srs_precompute_info(const gm_srs* srs, int* out_window_bits, int* out_levels);
 size_t gm_srs_len(const gm_srs* srs);

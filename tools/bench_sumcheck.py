@@ -23,6 +23,7 @@ def run(ctx, logn, reps, emit):
 
     from gemini_b200 import field
     from gemini_b200._lib import check, lib
+    from gemini_b200.transcript import MerlinTranscript
 
     class _A:
         pass
@@ -54,17 +55,21 @@ def run(ctx, logn, reps, emit):
             check(lib.gm_sumcheck_new_dev(ctx._h, C.c_void_p(d_f), n, C.c_void_p(d_g), n, C.c_void_p(tw.ctypes.data), flavour, C.byref(h)))
             out = np.empty(8, dtype=np.uint64)
             has = C.c_int(0)
-            chal = [field.fr_to_limbs([rng.randrange(field.R)]) for _ in range(args.logn + 1)]
+            # Sumcheck::prove (proof.rs:36-66) as the library runs it: the whole Fiat-Shamir loop in one native call,
+            # challenges drawn from a Merlin transcript on the host after every 64-byte message
+            tr = MerlinTranscript()
+            msgs = np.empty((args.logn + 2, 8), dtype=np.uint64)
+            chs = np.empty((args.logn + 2, 4), dtype=np.uint64)
+            fin = np.empty(8, dtype=np.uint64)
+            kk = C.c_size_t(0)
             ctx.l2_flush()
             ctx.synchronize()
             l0 = ctx.launch_count
             t0 = time.perf_counter()
             check(lib.gm_sumcheck_timer_start(h))     # CUDA events on the prover's own stream
-            check(lib.gm_sumcheck_next_message(h, None, C.c_void_p(out.ctypes.data), C.byref(has)))
-            k = 0
-            while has.value:
-                check(lib.gm_sumcheck_next_message(h, C.c_void_p(chal[k].ctypes.data), C.c_void_p(out.ctypes.data), C.byref(has)))
-                k += 1
+            check(lib.gm_sumcheck_prove(h, tr._h, C.c_void_p(msgs.ctypes.data), C.c_void_p(chs.ctypes.data), args.logn + 2, C.byref(kk),
+                                        C.c_void_p(fin.ctypes.data)))
+            k = int(kk.value)
             msf = C.c_float(0)
             check(lib.gm_sumcheck_timer_stop(h, C.byref(msf)))
             ms = float(msf.value)
