@@ -60,26 +60,6 @@ struct gm_msm_stream {
   bool holds_ctx_ref = true;   // false for the context's own internal stream (gm_msm_g1 of large host inputs)
 };
 
-struct gm_sumcheck {
-  gm_ctx* ctx = nullptr;
-  cudaStream_t stream = nullptr;        // private: distinct provers run concurrently (proof.rs:85 drives them from rayon)
-  cudaEvent_t ev[2] = {nullptr, nullptr};  // per-call device time
-  cudaEvent_t tm[2] = {nullptr, nullptr};  // gm_sumcheck_timer_start / _stop
-  float last_ms = 0.f;
-  int slot = -1;                        // pinned 64-byte message slot of the context (-1: own allocation)
-  Fr* f[2] = {nullptr, nullptr};
-  Fr* g[2] = {nullptr, nullptr};
-  int cur = 0;
-  size_t nf = 0, ng = 0;
-  Fr twist;
-  size_t round = 0, tot_rounds = 0;
-  int flavour = 0;
-  Fr* d_partials = nullptr;
-  unsigned int* d_ticket = nullptr;
-  Fr* d_out = nullptr;   // 2 Fr
-  Fr* h_out = nullptr;   // pinned, 2 Fr
-};
-
 static size_t ceil_log2(size_t x) {  // ark_std::log2
   size_t r = 0;
   while (((size_t)1 << r) < x) r++;
@@ -124,9 +104,9 @@ int gm_init(int device_id, gm_ctx** out_ctx) {
   GM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) GM_CUDA(cudaEventCreate(&ev));
   GM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-  ctx->pinned_bytes = 65536;  // first 4 KB: call results; 64-byte slots after it: sumcheck round messages
+  ctx->pinned_bytes = 4096 + 1024 * sizeof(ScMailbox);  // first 4 KB: call results; then the mailboxes of the sumcheck handles
   GM_CUDA(cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault));
-  for (uint32_t k = (uint32_t)((ctx->pinned_bytes - 4096) / 64); k-- > 0;) ctx->free_slots.push_back(k);
+  for (uint32_t k = (uint32_t)((ctx->pinned_bytes - 4096) / sizeof(ScMailbox)); k-- > 0;) ctx->free_slots.push_back(k);
   // short-lived vectors (prover state, DeviceFr temporaries) come from the stream-ordered pool: keep freed
   // blocks cached instead of returning them to the driver at every synchronisation
   cudaMemPool_t pool;
@@ -893,10 +873,11 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
     if (!ctx->free_slots.empty()) {
       p->slot = (int)ctx->free_slots.back();
       ctx->free_slots.pop_back();
-      p->h_out = reinterpret_cast<Fr*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 4096 + 64 * (size_t)p->slot);
+      p->mbox = reinterpret_cast<ScMailbox*>(reinterpret_cast<uint8_t*>(ctx->pinned) + 4096 + sizeof(ScMailbox) * (size_t)p->slot);
     }
   }
-  if (e == cudaSuccess && p->slot < 0) e = cudaHostAlloc((void**)&p->h_out, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess && p->slot < 0) e = cudaHostAlloc((void**)&p->mbox, sizeof(ScMailbox), cudaHostAllocDefault);
+  if (e == cudaSuccess) { memset(p->mbox, 0, sizeof(ScMailbox)); p->h_out = p->mbox->msg; }
   if (e != cudaSuccess) {
     set_error("sumcheck alloc: %s", cudaGetErrorString(e));
     gm_sumcheck_free(p);
@@ -1122,8 +1103,8 @@ int gm_sumcheck_free(gm_sumcheck* p) {
   if (p->slot >= 0) {
     std::lock_guard<std::recursive_mutex> guard(ctx->mu);
     ctx->free_slots.push_back((uint32_t)p->slot);
-  } else if (p->h_out) {
-    cudaFreeHost(p->h_out);
+  } else if (p->mbox) {
+    cudaFreeHost(p->mbox);
   }
   delete p;
   ctx_release(ctx);

@@ -6,6 +6,20 @@
 
 namespace gm {
 
+// Mailbox of the persistent tail kernel of a sumcheck (k_sc_tail, fr.cu): pinned host memory that the device reads and
+// writes directly (UVA).  The device publishes round messages (msg, then msg_seq), the host answers with challenges
+// (chal, then chal_seq); `abort` ends the kernel early, `status` reports how it ended.
+struct ScMailbox {
+  Fr msg[2];                   // (a, b) of the last published round; also the 64-byte D2H slot of the ordinary rounds
+  Fr chal;
+  volatile uint32_t msg_seq;   // device -> host: messages published so far
+  volatile uint32_t chal_seq;  // host -> device: challenges published so far
+  volatile uint32_t abort;     // host -> device
+  volatile uint32_t status;    // device -> host: 0 running, 1 finished, 2 gave up waiting for the host
+  uint32_t pad[36];            // 256 bytes
+};
+static_assert(sizeof(ScMailbox) == 256, "mailbox layout");
+
 // d_out[i] = d_f[2i] + r * d_f[2i+1]   (asynchronous on the lane's stream)
 int fr_fold_dev(const Lane& ln, int sm_count, const Fr* d_f, size_t n, const Fr& r, Fr* d_out);
 inline int fr_fold_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& r, Fr* d_out) {
@@ -35,4 +49,33 @@ int fr_spmv_dev(gm_ctx* ctx, const uint32_t* d_rowptr, const uint32_t* d_col, co
 size_t fr_div_scratch_elems(size_t n);
 int fr_div_linear_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& a, Fr* d_q, Fr* d_rem, Fr* d_scratch);
 
+// The last rounds of a sumcheck as ONE persistent single-CTA kernel: `rounds` x (wait for a challenge in the mailbox,
+// fold f and g, publish the message of the folded vectors), ping-ponging between the cur / alt buffers.  `twist` is the
+// prover's twist BEFORE the first of these rounds.
+int sc_tail_dev(const Lane& ln, Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, const Fr& twist, bool use_twist, int rounds,
+                ScMailbox* mbox);
+static constexpr size_t SC_TAIL_MAX = (size_t)1 << 13;   // vectors of at most this many elements finish in the tail kernel
+
 }  // namespace gm
+
+struct gm_sumcheck {
+  gm_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;        // private: distinct provers run concurrently (proof.rs:85 drives them from rayon)
+  cudaEvent_t ev[2] = {nullptr, nullptr};  // per-call device time
+  cudaEvent_t tm[2] = {nullptr, nullptr};  // gm_sumcheck_timer_start / _stop
+  float last_ms = 0.f;
+  int slot = -1;                        // pinned 64-byte message slot of the context (-1: own allocation)
+  gm::Fr* f[2] = {nullptr, nullptr};
+  gm::Fr* g[2] = {nullptr, nullptr};
+  int cur = 0;
+  size_t nf = 0, ng = 0;
+  gm::Fr twist;
+  size_t round = 0, tot_rounds = 0;
+  int flavour = 0;
+  gm::Fr* d_partials = nullptr;
+  unsigned int* d_ticket = nullptr;
+  gm::Fr* d_out = nullptr;   // 2 Fr
+  gm::Fr* h_out = nullptr;   // pinned, 2 Fr (= mbox->msg)
+  gm::ScMailbox* mbox = nullptr;   // pinned, device-visible (UVA): the persistent tail kernel's mailbox
+};
+
