@@ -88,7 +88,6 @@ SIGNATURES = {
     "gm_sumcheck_round": (_sz, [_vp]),
     "gm_sumcheck_set_rounds": (_i, [_vp, _sz, _sz]),
     "gm_sumcheck_final_foldings": (_i, [_vp, _vp, _pi]),
-    "gm_sumcheck_last_device_ms": (C.c_float, [_vp]),
     "gm_sumcheck_timer_start": (_i, [_vp]),
     "gm_sumcheck_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "gm_sumcheck_state_dev": (_i, [_vp, _pp, _psz, _pp, _psz]),

@@ -877,7 +877,7 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
     }
   }
   if (e == cudaSuccess && p->slot < 0) e = cudaHostAlloc((void**)&p->mbox, sizeof(ScMailbox), cudaHostAllocDefault);
-  if (e == cudaSuccess) { memset(p->mbox, 0, sizeof(ScMailbox)); p->h_out = p->mbox->msg; }
+  if (e == cudaSuccess) { memset(p->mbox, 0, sizeof(ScMailbox)); p->h_out = reinterpret_cast<Fr*>(p->mbox->pad); }
   if (e != cudaSuccess) {
     set_error("sumcheck alloc: %s", cudaGetErrorString(e));
     gm_sumcheck_free(p);
@@ -992,7 +992,7 @@ int gm_sumcheck_next_message(gm_sumcheck* p, const uint64_t* challenge_or_null, 
     return GM_OK;
   }
   const Lane ln = lane_of(p);
-  GM_CUDA(cudaEventRecord(p->ev[0], p->stream));
+  const uint32_t seq = ++p->seq;       // the kernel publishes (a, b) and this number in the pinned mailbox
   if (challenge_or_null) {
     Fr rg;
     fr_from_u64(rg, challenge_or_null);
@@ -1000,20 +1000,22 @@ int gm_sumcheck_next_message(gm_sumcheck* p, const uint64_t* challenge_or_null, 
     const Fr new_twist = p->twist.sqr();
     const int nxt = p->cur ^ 1;
     GM_TRY(sc_fold_message_dev(ln, p->f[p->cur], p->nf, p->g[p->cur], p->ng, rf, rg, p->f[nxt], p->g[nxt], new_twist,
-                               sc_use_twist(p, new_twist), p->d_partials, p->d_ticket, p->d_out));
+                               sc_use_twist(p, new_twist), p->d_partials, p->d_ticket, p->d_out, p->mbox, seq));
     p->cur = nxt;
     p->nf = (p->nf + 1) / 2;
     p->ng = (p->ng + 1) / 2;
     p->twist = new_twist;
   } else {
     GM_TRY(sc_message_dev(ln, p->f[p->cur], p->nf, p->g[p->cur], p->ng, p->twist, sc_use_twist(p, p->twist), p->d_partials,
-                          p->d_ticket, p->d_out));
+                          p->d_ticket, p->d_out, p->mbox, seq));
   }
-  GM_CUDA(cudaMemcpyAsync(p->h_out, p->d_out, 64, cudaMemcpyDeviceToHost, p->stream));
-  GM_CUDA(cudaEventRecord(p->ev[1], p->stream));
-  GM_CUDA(cudaStreamSynchronize(p->stream));
-  memcpy(out_ab, p->h_out, 64);
-  cudaEventElapsedTime(&p->last_ms, p->ev[0], p->ev[1]);
+  // no D2H copy, no stream synchronisation: the last CTA of the kernel wrote the message into pinned memory
+  if (!sc_wait_message(p->stream, p->mbox, seq)) {
+    GM_CUDA(cudaStreamSynchronize(p->stream));
+    set_error("sumcheck round: the message never arrived");
+    return GM_ERR_CUDA;
+  }
+  memcpy(out_ab, (const void*)p->mbox->msg, 64);
   p->round++;
   *out_has_msg = 1;
   return GM_OK;
@@ -1027,7 +1029,6 @@ int gm_sumcheck_set_rounds(gm_sumcheck* p, size_t round, size_t tot_rounds) {
   p->tot_rounds = tot_rounds;
   return GM_OK;
 }
-float gm_sumcheck_last_device_ms(const gm_sumcheck* p) { return p ? p->last_ms : -1.f; }
 int gm_sumcheck_timer_start(gm_sumcheck* p) {
   GM_ARG(p, "NULL argument");
   GM_CUDA(cudaSetDevice(p->ctx->device));

@@ -80,7 +80,10 @@ __device__ __forceinline__ Fr warp_sum_fr(Fr v) {
 }
 
 // CTA sum of (a, b); then the last CTA to arrive sums all CTA partials into out[0..1].
-__device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, unsigned int* ticket, Fr* out) {
+// mb != nullptr: the message also goes straight into the prover's pinned mailbox (msg, then msg_seq = seq), where the
+// host is spinning for it - no D2H copy and no stream synchronisation on the round's critical path.
+__device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, unsigned int* ticket, Fr* out, ScMailbox* mb = nullptr,
+                                                      uint32_t seq = 0) {
   __shared__ Fr sh[2 * (SC_THREADS / 32)];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -123,6 +126,13 @@ __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, 
       store_fr(out, x);
       store_fr(out + 1, y);
       *ticket = 0;  // re-arm for the next round
+      if (mb != nullptr) {
+        volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(&mb->msg[0]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { dst[j] = x.v[j]; dst[8 + j] = y.v[j]; }
+        __threadfence_system();
+        mb->msg_seq = seq;
+      }
     }
   }
 }
@@ -153,7 +163,7 @@ __device__ __forceinline__ void pair_contrib(ScAcc& a, ScAcc& b, const Fr& fe, c
 template <bool TW>
 __global__ void __launch_bounds__(SC_THREADS, 2)
 k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr twist, PowTable tab, int kpt,
-             Fr* partials, unsigned int* ticket, Fr* out) {
+             Fr* partials, unsigned int* ticket, Fr* out, ScMailbox* mb, uint32_t seq) {
   const size_t npairs = min((nf + 1) / 2, (ng + 1) / 2);
   const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
   ScAcc a = ScAcc::zero(), b = ScAcc::zero();
@@ -168,7 +178,7 @@ k_sc_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size
     pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
     if (TW) { t = t * step; tt = tt * step; }
   }
-  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
+  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out, mb, seq);
 }
 
 // fold by (rf, rg) and message of the folded vectors with the squared twist `twist` (already squared
@@ -177,7 +187,7 @@ template <bool TW>
 __global__ void __launch_bounds__(SC_THREADS, 2)   // 2 CTAs (16 warps) per SM: at most 128 registers
 k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr rf, Fr rg,
                   Fr* __restrict__ f_out, Fr* __restrict__ g_out, Fr twist, PowTable tab, int kpt,
-                  Fr* partials, unsigned int* ticket, Fr* out) {
+                  Fr* partials, unsigned int* ticket, Fr* out, ScMailbox* mb, uint32_t seq) {
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
   const size_t npairs = max((nf2 + 1) / 2, (ng2 + 1) / 2);  // every element must be folded
   const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;
@@ -203,7 +213,7 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
     pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
     if (TW) { t = t * step; tt = tt * step; }
   }
-  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out);
+  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out, mb, seq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -225,17 +235,16 @@ __device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
 
 template <bool TW>
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
-k_sc_tail(Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, Fr twist, PowTable tab, int rounds, ScMailbox* mb) {
+k_sc_tail(Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, Fr twist, PowTable tab, int rounds, ScMailbox* mb, uint32_t msg_seq0) {
   __shared__ Fr sh_red[2 * (TAIL_THREADS / 32)];
   __shared__ Fr sh_ch[2];        // rf, rg of the round
   __shared__ int sh_stop;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t seq0 = 0;
   for (int round = 0; round < rounds; round++) {
     if (threadIdx.x == 0) {
       int stop = 0;
       const long long t0 = clock64();
-      while (ld_sys_u32(&mb->chal_seq) < seq0 + (uint32_t)round + 1u) {
+      while (ld_sys_u32(&mb->chal_seq) < (uint32_t)round + 1u) {
         if (ld_sys_u32(&mb->abort)) { stop = 1; break; }
         if (clock64() - t0 > 4000000000ll) { stop = 2; break; }   // ~2 s at 1.965 GHz
         __nanosleep(200);
@@ -297,7 +306,7 @@ k_sc_tail(Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, Fr t
 #pragma unroll
         for (int j = 0; j < 8; j++) { dst[j] = x.v[j]; dst[8 + j] = y.v[j]; }
         __threadfence_system();
-        mb->msg_seq = seq0 + (uint32_t)round + 1u;
+        mb->msg_seq = msg_seq0 + (uint32_t)round + 1u;
         __threadfence_system();
       }
     }
@@ -552,16 +561,16 @@ size_t sc_max_ctas(size_t nf, size_t ng) {
 }
 
 int sc_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
-                   Fr* d_partials, unsigned int* d_ticket, Fr* d_out) {
+                   Fr* d_partials, unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq) {
   const size_t npairs = std::min((nf + 1) / 2, (ng + 1) / 2);
   const int kpt = sc_pairs_per_thread(npairs);
   const unsigned grid = sc_grid(npairs, kpt);
   if (use_twist) {
     PowTable tab = make_pow_table(twist, npairs);
-    LAUNCH_LN(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
+    LAUNCH_LN(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out, mb, seq);
   } else {
     PowTable tab;  // unused
-    LAUNCH_LN(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out);
+    LAUNCH_LN(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out, mb, seq);
   }
   GM_CUDA(cudaGetLastError());
   return GM_OK;
@@ -569,7 +578,7 @@ int sc_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, siz
 
 int sc_fold_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
                         Fr* d_f_out, Fr* d_g_out, const Fr& new_twist, bool use_twist, Fr* d_partials,
-                        unsigned int* d_ticket, Fr* d_out) {
+                        unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq) {
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
   const size_t npairs = std::max((nf2 + 1) / 2, (ng2 + 1) / 2);
   const int kpt = sc_pairs_per_thread(npairs);
@@ -577,25 +586,25 @@ int sc_fold_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g
   if (use_twist) {
     PowTable tab = make_pow_table(new_twist, npairs);
     LAUNCH_LN(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
-           d_partials, d_ticket, d_out);
+           d_partials, d_ticket, d_out, mb, seq);
   } else {
     PowTable tab;
     LAUNCH_LN(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
-           d_partials, d_ticket, d_out);
+           d_partials, d_ticket, d_out, mb, seq);
   }
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }
 
 int sc_tail_dev(const Lane& ln, Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, const Fr& twist, bool use_twist, int rounds,
-                ScMailbox* mbox) {
+                ScMailbox* mbox, uint32_t msg_seq0) {
   if (rounds > 26) { set_error("sumcheck tail: too many rounds for the power table"); return GM_ERR_ARG; }
   PowTable tab;   // entries 1 .. rounds + 12 are read: the kernel shifts through the table as the twist squares
   if (use_twist) tab = make_pow_table(twist, (size_t)1 << (rounds + 12));
   if (use_twist)
-    LAUNCH_LN(ln, k_sc_tail<true>, 1, TAIL_THREADS, 0, f_cur, f_alt, g_cur, g_alt, nf, ng, twist, tab, rounds, mbox);
+    LAUNCH_LN(ln, k_sc_tail<true>, 1, TAIL_THREADS, 0, f_cur, f_alt, g_cur, g_alt, nf, ng, twist, tab, rounds, mbox, msg_seq0);
   else
-    LAUNCH_LN(ln, k_sc_tail<false>, 1, TAIL_THREADS, 0, f_cur, f_alt, g_cur, g_alt, nf, ng, twist, tab, rounds, mbox);
+    LAUNCH_LN(ln, k_sc_tail<false>, 1, TAIL_THREADS, 0, f_cur, f_alt, g_cur, g_alt, nf, ng, twist, tab, rounds, mbox, msg_seq0);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

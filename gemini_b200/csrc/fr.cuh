@@ -32,12 +32,13 @@ int fr_reverse_dev(const Lane& ln, int sm_count, const Fr* d_in, size_t n, Fr* d
 // number of CTA partial slots a prover over vectors of these lengths can ever need
 size_t sc_max_ctas(size_t nf, size_t ng);
 // (a, b) of the current vectors -> d_out[0..1]
+// (mb, seq): the message is also published in the prover's pinned mailbox (msg, then msg_seq = seq)
 int sc_message_dev(const Lane& ln, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
-                   Fr* d_partials, unsigned int* d_ticket, Fr* d_out);
+                   Fr* d_partials, unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq);
 // fold f by rf, g by rg into the out buffers and compute the message of the folded vectors
 int sc_fold_message_dev(const Lane& ln, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg,
                         Fr* d_f_out, Fr* d_g_out, const Fr& new_twist, bool use_twist, Fr* d_partials,
-                        unsigned int* d_ticket, Fr* d_out);
+                        unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq);
 
 // ---- vector helpers of the time prover (all asynchronous on ctx->stream) ----
 int fr_powers_dev(gm_ctx* ctx, const Fr& x, size_t n, Fr* d_out);
@@ -53,7 +54,9 @@ int fr_div_linear_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& a, Fr* d_q
 // fold f and g, publish the message of the folded vectors), ping-ponging between the cur / alt buffers.  `twist` is the
 // prover's twist BEFORE the first of these rounds.
 int sc_tail_dev(const Lane& ln, Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, const Fr& twist, bool use_twist, int rounds,
-                ScMailbox* mbox);
+                ScMailbox* mbox, uint32_t msg_seq0);
+// host side of the mailbox: spin until the device has published message `seq` (false: the kernel died or 10 s passed)
+bool sc_wait_message(cudaStream_t stream, ScMailbox* mb, uint32_t seq);
 static constexpr size_t SC_TAIL_MAX = (size_t)1 << 13;   // vectors of at most this many elements finish in the tail kernel
 
 }  // namespace gm
@@ -76,6 +79,7 @@ struct gm_sumcheck {
   unsigned int* d_ticket = nullptr;
   gm::Fr* d_out = nullptr;   // 2 Fr
   gm::Fr* h_out = nullptr;   // pinned, 2 Fr (= mbox->msg)
-  gm::ScMailbox* mbox = nullptr;   // pinned, device-visible (UVA): the persistent tail kernel's mailbox
+  gm::ScMailbox* mbox = nullptr;   // pinned, device-visible (UVA): round messages land here, the tail kernel reads challenges from it
+  uint32_t seq = 0;                // messages published so far (mbox->msg_seq after the last round)
 };
 

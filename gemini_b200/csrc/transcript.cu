@@ -149,6 +149,25 @@ struct gm_transcript {
   }
 };
 
+namespace gm {
+bool sc_wait_message(cudaStream_t stream, ScMailbox* mb, uint32_t seq) {
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  while ((int32_t)(mb->msg_seq - seq) < 0) {
+    if ((++spins & 0xFFFu) == 0) {
+      if (cudaStreamQuery(stream) != cudaErrorNotReady) {     // nothing is running any more: the message is there, or never will be
+        cudaGetLastError();
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return (int32_t)(mb->msg_seq - seq) >= 0;
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return false;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return true;
+}
+}  // namespace gm
+
 using namespace gm;
 
 extern "C" {
@@ -198,6 +217,7 @@ int gm_transcript_get_challenge_fr(gm_transcript* t, const uint8_t* label, size_
   return GM_OK;
 }
 
+
 // The last rounds through the persistent tail kernel (k_sc_tail, fr.cu): `c` is the challenge drawn after message k - 1,
 // R = messages still to come.  The kernel is launched once; per round the host writes the challenge into the mailbox,
 // spins until the message appears, feeds it to the transcript and draws the next challenge.  On return `c` is the
@@ -206,30 +226,21 @@ static int prove_tail(gm_sumcheck* p, gm_transcript* t, uint64_t* out_msgs, uint
   static const uint8_t L_EVAL[] = "evaluations", L_CHAL[] = "challenge";
   const int R = (int)(p->tot_rounds - p->round);
   ScMailbox* mb = p->mbox;
-  mb->msg_seq = 0; mb->chal_seq = 0; mb->abort = 0; mb->status = 0;
+  mb->chal_seq = 0; mb->abort = 0; mb->status = 0;
   std::atomic_thread_fence(std::memory_order_seq_cst);
+  const uint32_t seq0 = p->seq;
   const bool use_twist = p->flavour != GM_SUMCHECK_HERRING_F && p->twist != Fr::one();
   const Lane ln{p->stream, &p->ctx->launches};
   const int nxt = p->cur ^ 1;
-  GM_TRY(sc_tail_dev(ln, p->f[p->cur], p->f[nxt], p->g[p->cur], p->g[nxt], p->nf, p->ng, p->twist, use_twist, R, mb));
+  GM_TRY(sc_tail_dev(ln, p->f[p->cur], p->f[nxt], p->g[p->cur], p->g[nxt], p->nf, p->ng, p->twist, use_twist, R, mb, seq0));
   int rc = GM_OK;
   for (int j = 0; j < R && rc == GM_OK; j++) {
     memcpy(&mb->chal, c.v, 32);
     std::atomic_thread_fence(std::memory_order_release);
     mb->chal_seq = (uint32_t)j + 1u;
-    const auto t0 = std::chrono::steady_clock::now();
-    unsigned spins = 0;
-    while (mb->msg_seq < (uint32_t)j + 1u) {
-      if ((++spins & 0x3FFFu) == 0) {
-        if (mb->status == 2) { set_error("sumcheck tail kernel timed out waiting for the host"); rc = GM_ERR_STATE; break; }
-        if (cudaStreamQuery(p->stream) != cudaErrorNotReady) {     // the kernel is gone: a launch or execution error
-          if (mb->msg_seq >= (uint32_t)j + 1u) break;
-          set_error("sumcheck tail kernel ended early: %s", cudaGetErrorString(cudaGetLastError()));
-          rc = GM_ERR_CUDA;
-          break;
-        }
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) { set_error("sumcheck tail: no message for 5 s"); rc = GM_ERR_STATE; break; }
-      }
+    if (!sc_wait_message(p->stream, mb, seq0 + (uint32_t)j + 1u)) {
+      set_error(mb->status == 2 ? "sumcheck tail kernel timed out waiting for the host" : "sumcheck tail: the message never arrived");
+      rc = GM_ERR_STATE;
     }
     if (rc != GM_OK) break;
     std::atomic_thread_fence(std::memory_order_acquire);
@@ -256,6 +267,7 @@ static int prove_tail(gm_sumcheck* p, gm_transcript* t, uint64_t* out_msgs, uint
   }
   p->cur ^= (R & 1);
   p->round += (size_t)R;
+  p->seq = seq0 + (uint32_t)R;
   return GM_OK;
 }
 

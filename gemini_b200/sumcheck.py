@@ -106,9 +106,6 @@ class _DeviceProver:
         check(lib.gm_sumcheck_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
 
-    def last_device_ms(self) -> float:
-        return float(lib.gm_sumcheck_last_device_ms(self._h))
-
     # -- inspection --------------------------------------------------------------------------
     def lengths(self) -> Tuple[int, int]:
         nf, ng = C.c_size_t(0), C.c_size_t(0)

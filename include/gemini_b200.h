@@ -189,8 +189,7 @@ size_t gm_sumcheck_round(const gm_sumcheck* p);
 /* override the round counters (From<&SpaceProver> for TimeProver, space_prover.rs:269-307) */
 int gm_sumcheck_set_rounds(gm_sumcheck* p, size_t round, size_t tot_rounds);
 int gm_sumcheck_final_foldings(gm_sumcheck* p, uint64_t out_fg[8], int* out_has);
-/* device time of the last next_message call of THIS handle, and a CUDA-event stopwatch on the handle's stream */
-float gm_sumcheck_last_device_ms(const gm_sumcheck* p);
+/* a CUDA-event stopwatch on the handle's own stream */
 int gm_sumcheck_timer_start(gm_sumcheck* p);
 int gm_sumcheck_timer_stop(gm_sumcheck* p, float* out_ms);
 /* device pointers of the current (folded) vectors, valid until the next call on the handle */
