@@ -877,7 +877,7 @@ static int sumcheck_alloc(gm_ctx* ctx, size_t f_len, size_t g_len, const uint64_
     }
   }
   if (e == cudaSuccess && p->slot < 0) e = cudaHostAlloc((void**)&p->mbox, sizeof(ScMailbox), cudaHostAllocDefault);
-  if (e == cudaSuccess) { memset(p->mbox, 0, sizeof(ScMailbox)); p->h_out = reinterpret_cast<Fr*>(p->mbox->pad); }
+  if (e == cudaSuccess) { memset(p->mbox, 0, sizeof(ScMailbox)); p->h_out = p->mbox->scratch; }
   if (e != cudaSuccess) {
     set_error("sumcheck alloc: %s", cudaGetErrorString(e));
     gm_sumcheck_free(p);

@@ -81,7 +81,10 @@ __device__ __forceinline__ Fr warp_sum_fr(Fr v) {
 
 // CTA sum of (a, b); then the last CTA to arrive sums all CTA partials into out[0..1].
 // mb != nullptr: the message also goes straight into the prover's pinned mailbox (msg, then msg_seq = seq), where the
-// host is spinning for it - no D2H copy and no stream synchronisation on the round's critical path.
+// host is spinning for it - no D2H copy and no stream synchronisation on the round's critical path (measured at 2^24:
+// 2.37 -> 1.98 ms for the 24 rounds).  A persistent single-CTA kernel for the last rounds, fed challenges through the
+// same mailbox, was measured on top of this and did not pay (2.03 ms: one CTA is slower than a small grid, and the
+// launch it saves is all that was left): removed.
 __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, unsigned int* ticket, Fr* out, ScMailbox* mb = nullptr,
                                                       uint32_t seq = 0) {
   __shared__ Fr sh[2 * (SC_THREADS / 32)];
@@ -214,108 +217,6 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
     if (TW) { t = t * step; tt = tt * step; }
   }
   sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out, mb, seq);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent tail: once the vectors are short a round is a few microseconds of arithmetic, and a launch + 64-byte D2H +
-// stream synchronisation + 32-byte H2D per round costs ten times that (measured: ~50 us per small round).  k_sc_tail is
-// ONE CTA that stays resident for all remaining rounds and talks to the host through a mailbox in pinned memory
-// (ScMailbox, fr.cuh): it spins on chal_seq, folds, publishes (a, b) and bumps msg_seq; the host (gm_sumcheck_prove)
-// spins on msg_seq, feeds the message to the transcript and writes the next challenge.  The round trip is two PCIe
-// reads instead of a launch and a synchronisation.  The kernel gives up (status = 2) if the host stays silent for
-// about two seconds, and ends at once when the host sets `abort`, so it can never hang the device.
-// ---------------------------------------------------------------------------------------------
-static constexpr int TAIL_THREADS = 512;   // one CTA: 128 registers per thread, no spills
-
-__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <bool TW>
-__global__ void __launch_bounds__(TAIL_THREADS, 1)
-k_sc_tail(Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, Fr twist, PowTable tab, int rounds, ScMailbox* mb, uint32_t msg_seq0) {
-  __shared__ Fr sh_red[2 * (TAIL_THREADS / 32)];
-  __shared__ Fr sh_ch[2];        // rf, rg of the round
-  __shared__ int sh_stop;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int round = 0; round < rounds; round++) {
-    if (threadIdx.x == 0) {
-      int stop = 0;
-      const long long t0 = clock64();
-      while (ld_sys_u32(&mb->chal_seq) < (uint32_t)round + 1u) {
-        if (ld_sys_u32(&mb->abort)) { stop = 1; break; }
-        if (clock64() - t0 > 4000000000ll) { stop = 2; break; }   // ~2 s at 1.965 GHz
-        __nanosleep(200);
-      }
-      if (!stop) {
-        __threadfence_system();
-        Fr c;
-        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(&mb->chal);
-#pragma unroll
-        for (int j = 0; j < 8; j++) c.v[j] = ld_sys_u32(src + j);
-        sh_ch[1] = c;
-        sh_ch[0] = c * twist;      // time_prover.rs:77
-      } else if (stop == 2) {
-        mb->status = 2;
-        __threadfence_system();
-      }
-      sh_stop = stop;
-    }
-    __syncthreads();
-    if (sh_stop) return;
-    const Fr rf = sh_ch[0], rg = sh_ch[1];
-    twist = twist.sqr();
-    // table of the squared twist: (twist'^2)^(2^k) = tab.p[k + 1] of the previous round
-    const int shift = round + 1;
-    const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
-    const size_t npairs = max((nf2 + 1) / 2, (ng2 + 1) / 2);
-    ScAcc a = ScAcc::zero(), b = ScAcc::zero();
-    for (size_t i = threadIdx.x; i < npairs; i += TAIL_THREADS) {
-      Fr fe = load_fr_or_zero(f_cur, 4 * i, nf);
-      if (4 * i + 1 < nf) fe = fe + rf * load_fr(f_cur + 4 * i + 1);
-      Fr fo = load_fr_or_zero(f_cur, 4 * i + 2, nf);
-      if (4 * i + 3 < nf) fo = fo + rf * load_fr(f_cur + 4 * i + 3);
-      Fr ge = load_fr_or_zero(g_cur, 4 * i, ng);
-      if (4 * i + 1 < ng) ge = ge + rg * load_fr(g_cur + 4 * i + 1);
-      Fr go = load_fr_or_zero(g_cur, 4 * i + 2, ng);
-      if (4 * i + 3 < ng) go = go + rg * load_fr(g_cur + 4 * i + 3);
-      if (2 * i < nf2) store_fr(f_alt + 2 * i, fe);
-      if (2 * i + 1 < nf2) store_fr(f_alt + 2 * i + 1, fo);
-      if (2 * i < ng2) store_fr(g_alt + 2 * i, ge);
-      if (2 * i + 1 < ng2) store_fr(g_alt + 2 * i + 1, go);
-      Fr t = Fr::one(), tt = Fr::one();
-      if (TW) {
-        for (int k = 0; k + shift < 40 && (i >> k); k++)
-          if ((i >> k) & 1ull) t = t * tab.p[k + shift];
-        tt = t * twist;
-      }
-      pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
-    }
-    Fr x = warp_sum_fr(sc_acc_value(a)), y = warp_sum_fr(sc_acc_value(b));
-    if (lane == 0) { sh_red[2 * wid] = x; sh_red[2 * wid + 1] = y; }
-    __syncthreads();        // also orders this round's stores to f_alt / g_alt before the next round reads them
-    if (wid == 0) {
-      x = lane < TAIL_THREADS / 32 ? sh_red[2 * lane] : Fr::zero();
-      y = lane < TAIL_THREADS / 32 ? sh_red[2 * lane + 1] : Fr::zero();
-      x = warp_sum_fr(x);
-      y = warp_sum_fr(y);
-      if (lane == 0) {
-        volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(&mb->msg[0]);
-#pragma unroll
-        for (int j = 0; j < 8; j++) { dst[j] = x.v[j]; dst[8 + j] = y.v[j]; }
-        __threadfence_system();
-        mb->msg_seq = msg_seq0 + (uint32_t)round + 1u;
-        __threadfence_system();
-      }
-    }
-    Fr* s1 = f_cur; f_cur = f_alt; f_alt = s1;
-    Fr* s2 = g_cur; g_cur = g_alt; g_alt = s2;
-    nf = nf2; ng = ng2;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { mb->status = 1; __threadfence_system(); }
 }
 
 // out[i] = in[n - 1 - i]: the big-endian streams of the elastic prover (Reverse(..) in /root/reference/src/kzg/space.rs:288-297,
@@ -592,19 +493,6 @@ int sc_fold_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g
     LAUNCH_LN(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out, mb, seq);
   }
-  GM_CUDA(cudaGetLastError());
-  return GM_OK;
-}
-
-int sc_tail_dev(const Lane& ln, Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, const Fr& twist, bool use_twist, int rounds,
-                ScMailbox* mbox, uint32_t msg_seq0) {
-  if (rounds > 26) { set_error("sumcheck tail: too many rounds for the power table"); return GM_ERR_ARG; }
-  PowTable tab;   // entries 1 .. rounds + 12 are read: the kernel shifts through the table as the twist squares
-  if (use_twist) tab = make_pow_table(twist, (size_t)1 << (rounds + 12));
-  if (use_twist)
-    LAUNCH_LN(ln, k_sc_tail<true>, 1, TAIL_THREADS, 0, f_cur, f_alt, g_cur, g_alt, nf, ng, twist, tab, rounds, mbox, msg_seq0);
-  else
-    LAUNCH_LN(ln, k_sc_tail<false>, 1, TAIL_THREADS, 0, f_cur, f_alt, g_cur, g_alt, nf, ng, twist, tab, rounds, mbox, msg_seq0);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
 }

@@ -6,17 +6,14 @@
 
 namespace gm {
 
-// Mailbox of the persistent tail kernel of a sumcheck (k_sc_tail, fr.cu): pinned host memory that the device reads and
-// writes directly (UVA).  The device publishes round messages (msg, then msg_seq), the host answers with challenges
-// (chal, then chal_seq); `abort` ends the kernel early, `status` reports how it ended.
+// Mailbox of a sumcheck prover: pinned host memory that the device writes directly (UVA).  The last CTA of a round's
+// kernel publishes the message (msg, then msg_seq); the host spins on msg_seq instead of copying and synchronising.
 struct ScMailbox {
-  Fr msg[2];                   // (a, b) of the last published round; also the 64-byte D2H slot of the ordinary rounds
-  Fr chal;
+  Fr msg[2];                   // (a, b) of the last published round
   volatile uint32_t msg_seq;   // device -> host: messages published so far
-  volatile uint32_t chal_seq;  // host -> device: challenges published so far
-  volatile uint32_t abort;     // host -> device
-  volatile uint32_t status;    // device -> host: 0 running, 1 finished, 2 gave up waiting for the host
-  uint32_t pad[36];            // 256 bytes
+  uint32_t pad0[15];
+  Fr scratch[2];               // 64-byte D2H slot of the calls that do copy (final foldings)
+  uint32_t pad1[16];           // 256 bytes: mailboxes of different provers never share a cache line
 };
 static_assert(sizeof(ScMailbox) == 256, "mailbox layout");
 
@@ -50,11 +47,6 @@ int fr_spmv_dev(gm_ctx* ctx, const uint32_t* d_rowptr, const uint32_t* d_col, co
 size_t fr_div_scratch_elems(size_t n);
 int fr_div_linear_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& a, Fr* d_q, Fr* d_rem, Fr* d_scratch);
 
-// The last rounds of a sumcheck as ONE persistent single-CTA kernel: `rounds` x (wait for a challenge in the mailbox,
-// fold f and g, publish the message of the folded vectors), ping-ponging between the cur / alt buffers.  `twist` is the
-// prover's twist BEFORE the first of these rounds.
-int sc_tail_dev(const Lane& ln, Fr* f_cur, Fr* f_alt, Fr* g_cur, Fr* g_alt, size_t nf, size_t ng, const Fr& twist, bool use_twist, int rounds,
-                ScMailbox* mbox, uint32_t msg_seq0);
 // host side of the mailbox: spin until the device has published message `seq` (false: the kernel died or 10 s passed)
 bool sc_wait_message(cudaStream_t stream, ScMailbox* mb, uint32_t seq);
 static constexpr size_t SC_TAIL_MAX = (size_t)1 << 13;   // vectors of at most this many elements finish in the tail kernel
@@ -78,8 +70,8 @@ struct gm_sumcheck {
   gm::Fr* d_partials = nullptr;
   unsigned int* d_ticket = nullptr;
   gm::Fr* d_out = nullptr;   // 2 Fr
-  gm::Fr* h_out = nullptr;   // pinned, 2 Fr (= mbox->msg)
-  gm::ScMailbox* mbox = nullptr;   // pinned, device-visible (UVA): round messages land here, the tail kernel reads challenges from it
+  gm::Fr* h_out = nullptr;   // pinned, 2 Fr (= mbox->scratch)
+  gm::ScMailbox* mbox = nullptr;   // pinned, device-visible (UVA): round messages land here
   uint32_t seq = 0;                // messages published so far (mbox->msg_seq after the last round)
 };
 

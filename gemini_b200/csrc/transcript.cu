@@ -218,69 +218,14 @@ int gm_transcript_get_challenge_fr(gm_transcript* t, const uint8_t* label, size_
 }
 
 
-// The last rounds through the persistent tail kernel (k_sc_tail, fr.cu): `c` is the challenge drawn after message k - 1,
-// R = messages still to come.  The kernel is launched once; per round the host writes the challenge into the mailbox,
-// spins until the message appears, feeds it to the transcript and draws the next challenge.  On return `c` is the
-// challenge the final fold still needs.
-static int prove_tail(gm_sumcheck* p, gm_transcript* t, uint64_t* out_msgs, uint64_t* out_challenges, size_t capacity, size_t& k, Fr& c) {
-  static const uint8_t L_EVAL[] = "evaluations", L_CHAL[] = "challenge";
-  const int R = (int)(p->tot_rounds - p->round);
-  ScMailbox* mb = p->mbox;
-  mb->chal_seq = 0; mb->abort = 0; mb->status = 0;
-  std::atomic_thread_fence(std::memory_order_seq_cst);
-  const uint32_t seq0 = p->seq;
-  const bool use_twist = p->flavour != GM_SUMCHECK_HERRING_F && p->twist != Fr::one();
-  const Lane ln{p->stream, &p->ctx->launches};
-  const int nxt = p->cur ^ 1;
-  GM_TRY(sc_tail_dev(ln, p->f[p->cur], p->f[nxt], p->g[p->cur], p->g[nxt], p->nf, p->ng, p->twist, use_twist, R, mb, seq0));
-  int rc = GM_OK;
-  for (int j = 0; j < R && rc == GM_OK; j++) {
-    memcpy(&mb->chal, c.v, 32);
-    std::atomic_thread_fence(std::memory_order_release);
-    mb->chal_seq = (uint32_t)j + 1u;
-    if (!sc_wait_message(p->stream, mb, seq0 + (uint32_t)j + 1u)) {
-      set_error(mb->status == 2 ? "sumcheck tail kernel timed out waiting for the host" : "sumcheck tail: the message never arrived");
-      rc = GM_ERR_STATE;
-    }
-    if (rc != GM_OK) break;
-    std::atomic_thread_fence(std::memory_order_acquire);
-    if (k >= capacity) { set_error("gm_sumcheck_prove: more than %zu rounds", capacity); rc = GM_ERR_ARG; break; }
-    Fr ab[2];
-    memcpy(ab[0].v, (const void*)&mb->msg[0], 32);
-    memcpy(ab[1].v, (const void*)&mb->msg[1], 32);
-    t->append_fr(L_EVAL, sizeof(L_EVAL) - 1, ab, 2);
-    c = t->get_challenge(L_CHAL, sizeof(L_CHAL) - 1);
-    memcpy(out_msgs + 8 * k, ab[0].v, 32);
-    memcpy(out_msgs + 8 * k + 4, ab[1].v, 32);
-    memcpy(out_challenges + 4 * k, c.v, 32);
-    k++;
-  }
-  if (rc != GM_OK) { mb->abort = 1; std::atomic_thread_fence(std::memory_order_seq_cst); }
-  cudaError_t e = cudaStreamSynchronize(p->stream);
-  if (rc == GM_OK && e != cudaSuccess) { set_error("sumcheck tail: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
-  if (rc != GM_OK) return rc;
-  // the state the R rounds left behind: R folds of both vectors, R squarings of the twist
-  for (int j = 0; j < R; j++) {
-    p->nf = (p->nf + 1) / 2;
-    p->ng = (p->ng + 1) / 2;
-    p->twist = p->twist.sqr();
-  }
-  p->cur ^= (R & 1);
-  p->round += (size_t)R;
-  p->seq = seq0 + (uint32_t)R;
-  return GM_OK;
-}
-
 // Sumcheck::prove (sumcheck/proof.rs:36-66) for any prover handle.  out_msgs: rounds x (a | b), out_challenges:
 // rounds x Fr, both in Montgomery limbs; *out_rounds = number of messages; out_final = the final foldings (f | g),
-// which are appended to the transcript as the reference does.  Long vectors run one kernel per round; once they are
-// at most SC_TAIL_MAX elements long the remaining rounds run in the persistent tail kernel (GM_SC_TAIL=0 disables it).
+// which are appended to the transcript as the reference does.  One kernel per round; the message reaches the host through
+// the prover's pinned mailbox (fr.cuh), the challenge goes down as a kernel argument of the next launch.
 int gm_sumcheck_prove(gm_sumcheck* p, gm_transcript* t, uint64_t* out_msgs, uint64_t* out_challenges, size_t capacity, size_t* out_rounds,
                       uint64_t out_final[8]) {
   GM_ARG(p && t && out_rounds && out_final && ((out_msgs && out_challenges) || capacity == 0), "NULL argument");
   static const uint8_t L_EVAL[] = "evaluations", L_CHAL[] = "challenge", L_FINAL[] = "final-folding";
-  const char* tail_env = getenv("GM_SC_TAIL");
-  const bool tail_on = !(tail_env && atoi(tail_env) == 0);
   GM_CUDA(cudaSetDevice(p->ctx->device));
   size_t k = 0;
   uint64_t msg[8], ch[4];
@@ -296,8 +241,6 @@ int gm_sumcheck_prove(gm_sumcheck* p, gm_transcript* t, uint64_t* out_msgs, uint
     memcpy(out_msgs + 8 * k, msg, 64);
     memcpy(out_challenges + 4 * k, c.v, 32);
     k++;
-    if (tail_on && p->round < p->tot_rounds && p->tot_rounds - p->round <= 26 && std::max(p->nf, p->ng) <= SC_TAIL_MAX && p->nf && p->ng)
-      GM_TRY(prove_tail(p, t, out_msgs, out_challenges, capacity, k, c));
     memcpy(ch, c.v, 32);
     GM_TRY(gm_sumcheck_next_message(p, ch, msg, &has));
   }

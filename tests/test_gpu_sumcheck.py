@@ -151,23 +151,19 @@ def test_native_prove_loop_equals_python_loop(ctx):
 
 
 @pytest.mark.parametrize("nf,ng,tw", [(1 << 15, 1 << 15, 3), ((1 << 14) + 1, 1 << 14, 1), (5000, 4097, 77), (8192, 8192, 1), (64, 64, 9), (2, 2, 5), (1, 1, 5)])
-def test_persistent_tail_kernel_and_ordinary_rounds_agree(ctx, monkeypatch, nf, ng, tw):
-    """gm_sumcheck_prove finishes short vectors in the persistent tail kernel (k_sc_tail: one CTA, challenges and messages
-    through a pinned-memory mailbox); GM_SC_TAIL=0 runs every round as its own launch.  Both against the oracle, for
-    ragged lengths and twist = 1, and the herring flavour through the same two paths."""
+def test_native_prove_loop_sizes_and_flavours(ctx, nf, ng, tw):
+    """gm_sumcheck_prove (every round's message arrives through the prover's pinned mailbox) against the oracle driven by
+    the oracle's own Merlin, for ragged lengths, twist = 1 and degenerate sizes; the herring flavour against its
+    round-by-round Python-driven twin."""
     from gemini_b200.transcript import MerlinTranscript
 
     f, g = rand_scalars(nf, 400 + nf), rand_scalars(ng, 401 + ng)
     want = o.sumcheck_prove_transcript(o.TimeProver(f, g, tw), o.MerlinTranscript())
-    for tail in ("1", "0"):
-        monkeypatch.setenv("GM_SC_TAIL", tail)
-        t = MerlinTranscript()
-        got = gm.Sumcheck.prove_transcript(gm.TimeProver(ctx, f, g, tw), t)
-        assert got.messages == want["messages"] and got.challenges == want["challenges"], f"tail={tail}"
-        assert [tuple(x) for x in got.final_foldings] == [tuple(x) for x in want["final_foldings"]]
+    got = gm.Sumcheck.prove_transcript(gm.TimeProver(ctx, f, g, tw), MerlinTranscript())
+    assert got.messages == want["messages"] and got.challenges == want["challenges"]
+    assert [tuple(x) for x in got.final_foldings] == [tuple(x) for x in want["final_foldings"]]
     if min(nf, ng) >= 2:
-        monkeypatch.setenv("GM_SC_TAIL", "1")
         h = gm.Sumcheck.prove_transcript(gm.HerringTimeProver(ctx, f, g, tw), MerlinTranscript())
-        monkeypatch.setenv("GM_SC_TAIL", "0")
-        h0 = gm.Sumcheck.prove_transcript(gm.HerringTimeProver(ctx, f, g, tw), MerlinTranscript())
-        assert h.messages == h0.messages and h.final_foldings == h0.final_foldings
+        it = iter(h.challenges)
+        h0 = gm.Sumcheck.prove(gm.HerringTimeProver(ctx, f, g, tw), lambda m: next(it))
+        assert h.messages == h0.messages and [tuple(x) for x in h.final_foldings] == [tuple(x) for x in h0.final_foldings]
