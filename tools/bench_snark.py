@@ -14,6 +14,52 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def run_elastic(ctx, logn, reps=1):
+    """`examples/snark -i LOGSIZE` (the elastic prover, src/examples/snark.rs:55-67 with max_msm_buffer = 1 << 20) on one
+    GPU: snark::Proof::new_elastic over device-resident streams, and its proof must equal new_time's on the same
+    instance (the reference's strongest test, src/snark/tests.rs:13-58)."""
+    import numpy as np
+
+    import gemini_b200 as gm
+    from gemini_b200 import snark
+    from gemini_b200.transcript import MerlinTranscript
+
+    n = 1 << logn
+    t0 = time.perf_counter()
+    srs = ctx.srs_generate(n, first_multiple=1)
+    le = srs.read()
+    srs_be = ctx.srs_load(np.ascontiguousarray(le[::-1]))      # Reverse(powers_of_g), kzg/space.rs:288-297
+    del le
+    srs.precompute()
+    srs_be.precompute()
+    ctx.synchronize()
+    setup_s = time.perf_counter() - t0
+    ck, cks = gm.CommitterKey(ctx, srs), gm.CommitterKeyStream(ctx, srs_be)
+    e = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % gm.field.R
+    r1cs = snark.R1cs.dummy(ctx, n, e)
+    want = snark.new_time(ctx, r1cs, ck, MerlinTranscript())
+    best = None
+    for _ in range(reps):
+        timers = {}
+        l0 = ctx.launch_count
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        proof = snark.new_elastic(ctx, r1cs, cks, MerlinTranscript(), 1 << 20, timers)
+        ctx.synchronize()
+        wall = time.perf_counter() - t0
+        if best is None or wall < best[0]:
+            best = (wall, timers, ctx.launch_count - l0)
+    wall, timers, launches = best
+    res = {"metric": "snark_elastic_prover_wall_s", "value": wall, "unit": "s", "logsize": logn, "n_gpus": 1,
+           "workload": "examples/snark (elastic prover, MAX_MSM_BUFFER_LOG = 20): dummy_r1cs, big-endian streams resident on the device, Merlin on host",
+           "phases_s": {k: round(v, 6) for k, v in timers.items()}, "gpu_launches": launches, "srs_setup_s": setup_s,
+           "elastic proof == time proof": proof == want}
+    assert proof == want, "elastic proof differs from the time proof"
+    srs.free()
+    srs_be.free()
+    return res
+
+
 def run(ctx, logn, reps, no_precompute=False):
     import gemini_b200 as gm
     from gemini_b200 import snark
