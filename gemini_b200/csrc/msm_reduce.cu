@@ -43,36 +43,51 @@ k_bucket_chunks(const XYZZ* __restrict__ buckets, const uint32_t* __restrict__ c
 // 8. The chunk sums S_t (t < T) still carry the weights t*L.  View t = hi*L2 + lo as an H2 x L2 matrix:
 //      sum_t t*S_t = sum_lo lo * C_lo + L2 * sum_hi hi * R_hi,   C_lo / R_hi = plain column / row sums,
 //    so the weighting needs one short double-and-add per ROW and per COLUMN (H2 + L2 of them) instead
-//    of one per chunk.  CTA roles by blockIdx.x: [0,H2) rows of S, [H2,2*H2) rows of W (plain sums of
+//    of one per chunk.  Warp roles by index: [0,H2) rows of S, [H2,2*H2) rows of W (plain sums of
 //    the locally weighted chunk sums), [2*H2, 2*H2+L2) columns of S.
+//    One WARP per row / column (lane-strided loads, then a shuffle tree): 2 H2 + L2 warps fit the chip in one wave,
+//    where one 128-thread CTA per row needed three (ncu r02: 0.41 ms at 2^20, 8.6 warps per issue waiting at barriers).
+__device__ __forceinline__ XYZZ shfl_down_xyzz_r(const XYZZ& v, int delta) {
+  XYZZ r;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < 48; k++) dst[k] = __shfl_down_sync(0xffffffffu, src[k], delta);
+  return r;
+}
+
 __global__ void __launch_bounds__(RED_THREADS)
 k_rowcol(const XYZZ* __restrict__ chunk_s, const XYZZ* __restrict__ chunk_w, uint32_t T, uint32_t H2, uint32_t L2,
          XYZZ* __restrict__ row_sum, XYZZ* __restrict__ wrow_sum, XYZZ* __restrict__ col_sum) {
-  extern __shared__ uint4 sh_raw[];
-  XYZZ* sh = reinterpret_cast<XYZZ*>(sh_raw);
   const int w = blockIdx.y;
-  const uint32_t bx = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t bx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per row / column
+  if (bx >= 2 * H2 + L2) return;
   const XYZZ* src = (bx >= H2 && bx < 2 * H2) ? chunk_w : chunk_s;
   src += (size_t)w * T;
   XYZZ acc = XYZZ::identity();
   if (bx < 2 * H2) {
     const uint32_t row = bx < H2 ? bx : bx - H2;
-    for (uint32_t lo = threadIdx.x; lo < L2; lo += blockDim.x) {
+    for (uint32_t lo = lane; lo < L2; lo += 32u) {
       XYZZ v = load_rw(src + (size_t)row * L2 + lo);
       xyzz_add(acc, v);
     }
   } else {
     const uint32_t col = bx - 2 * H2;
-    for (uint32_t hi = threadIdx.x; hi < H2; hi += blockDim.x) {
+    for (uint32_t hi = lane; hi < H2; hi += 32u) {
       XYZZ v = load_rw(src + (size_t)hi * L2 + col);
       xyzz_add(acc, v);
     }
   }
-  XYZZ tot = block_sum_xyzz(acc, sh);
-  if (threadIdx.x == 0) {
-    if (bx < H2) store_rw(row_sum + (size_t)w * H2 + bx, tot);
-    else if (bx < 2 * H2) store_rw(wrow_sum + (size_t)w * H2 + (bx - H2), tot);
-    else store_rw(col_sum + (size_t)w * L2 + (bx - 2 * H2), tot);
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) {
+    XYZZ other = shfl_down_xyzz_r(acc, d);
+    if (lane + d < 32) xyzz_add(acc, other);
+  }
+  if (lane == 0) {
+    if (bx < H2) store_rw(row_sum + (size_t)w * H2 + bx, acc);
+    else if (bx < 2 * H2) store_rw(wrow_sum + (size_t)w * H2 + (bx - H2), acc);
+    else store_rw(col_sum + (size_t)w * L2 + (bx - 2 * H2), acc);
   }
 }
 
@@ -224,7 +239,7 @@ int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_
   XYZZ* win_sum = reinterpret_cast<XYZZ*>(sm + off_ws);
   const size_t red_sh = RED_THREADS * sizeof(XYZZ);
   LAUNCH(ctx, k_bucket_chunks, dim3((P.nchunks + 127) / 128, Weff), 128, 0, buckets, valid, P.nb, P.L, P.nchunks, Weff, chunk_s, chunk_w);
-  LAUNCH(ctx, k_rowcol, dim3(2 * H2 + L2, Weff), RED_THREADS, red_sh, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
+  LAUNCH(ctx, k_rowcol, dim3((2 * H2 + L2 + RED_THREADS / 32 - 1) / (RED_THREADS / 32), Weff), RED_THREADS, 0, chunk_s, chunk_w, P.nchunks, H2, L2, row_sum, wrow_sum, col_sum);
   LAUNCH(ctx, k_weighted, dim3(nparts, Weff), RED_THREADS, red_sh, row_sum, col_sum, H2, L2, log_l2, ctas_c, part);
   LAUNCH(ctx, k_window_total, Weff, 2 * RED_THREADS, 2 * red_sh, part, nparts, wrow_sum, H2, log_l, P.c, merged ? 1 : 0, win_sum);
   LAUNCH(ctx, k_final, 1, 32, 0, win_sum, Weff, d_acc);
