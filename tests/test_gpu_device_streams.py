@@ -59,7 +59,7 @@ def test_device_chunking_does_not_change_results(ctx, monkeypatch):
     want = o.kzg_commit(srs, poly)
     chals = rand_scalars(5, 76)
     want_fold = o.kzg_commit_folding(srs[::-1], poly[::-1], chals, 20)
-    for floor in (1, 7, 64, 1 << 16):
+    for floor in (1, 7, 64, 1 << 27):
         monkeypatch.setattr(kzg, "MIN_DEVICE_CHUNK", floor)
         assert cks.commit(ReverseStream(dv), 3) == want
         assert cks.commit_folding(ReverseStream(dv), chals, 20) == want_fold
