@@ -29,6 +29,8 @@ R = field.R
 # So a resident vector is pushed in pieces of max(max_msm_buffer, MIN_DEVICE_CHUNK) terms - one piece unless the
 # vector exceeds the 2^27-term pass limit; tests lower the floor to walk chunk boundaries (the result does not depend on it).
 MIN_DEVICE_CHUNK = 1 << 27
+# batch_commit of resident polynomials on two lanes (see CommitterKey.batch_commit); False = the reference's sequential map
+CONCURRENT_COMMITS = True
 
 
 def vanishing_polynomial(points: Sequence[int]) -> List[int]:
@@ -150,8 +152,47 @@ class CommitterKey:
         return CommitterKey(self.ctx, out)
 
     def batch_commit(self, polynomials) -> List[field.Point]:
-        """time.rs:98-107."""
-        return [self.commit(p) for p in polynomials]
+        """time.rs:98-107 (a sequential map of ``commit`` in the reference).  Resident polynomials are committed on TWO
+        lanes - this context and a helper context of the same GPU, each with its own stream and scratch arena, driven
+        from two host threads: an MSM ends in a latency-bound reduction tail that uses a handful of SMs (a quarter of
+        the call at 2^20 terms), and the tail of one commitment then overlaps the bucket accumulation of
+        the next.  Results are in input order and identical to the sequential map."""
+        polys = list(polynomials)
+        if len(polys) < 2 or not all(isinstance(p, DeviceFr) for p in polys) or not CONCURRENT_COMMITS:
+            return [self.commit(p) for p in polys]
+        import threading
+
+        helper = self._helper_context()
+        self.ctx.synchronize()                  # the polynomials were produced on this context's stream
+        order = sorted(range(len(polys)), key=lambda i: -polys[i].n)
+        out: List = [None] * len(polys)
+        errors: List = []
+        lanes = (self.ctx, helper)
+
+        def work(lane: int) -> None:
+            try:
+                ctx = lanes[lane]
+                for i in order[lane::2]:
+                    v = polys[i]
+                    out[i] = field.jacobian_to_affine(ctx.msm_dev(self.srs, v.ptr, v.n)) if v.n else None
+            except Exception as exc:  # pragma: no cover
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in (0, 1)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out
+
+    def _helper_context(self) -> Context:
+        h = getattr(self, "_helper", None)
+        if h is None or not h._h:
+            h = Context(self.ctx.device_id)
+            self._helper = h
+        return h
 
     def open(self, polynomial, evaluation_point: int) -> Tuple[int, field.Point]:
         """time.rs:112-131: (evaluation, proof).  The reference runs a serial Horner recurrence and builds the quotient

@@ -155,3 +155,26 @@ def test_elastic_equals_time_proof_dummy_2_14(ctx):
     a = snark.new_time(ctx, r1cs, ck, HashTranscript())
     b = snark.new_elastic(ctx, r1cs, cks, HashTranscript(), 1 << 20)
     assert a == b
+
+
+def test_batch_commit_two_lanes_equals_sequential(ctx, monkeypatch):
+    """CommitterKey.batch_commit of resident polynomials runs on two contexts from two host threads (the reduction
+    tail of one MSM overlaps the accumulation of the next); order and values are those of the sequential map"""
+    srs = rand_points(600, 95)
+    ck = gm.CommitterKey(ctx, srs)
+    sizes = [600, 1, 300, 0, 17, 512, 2, 129, 64]
+    polys = [rand_scalars(n, 96 + n) for n in sizes]
+    dev = [DeviceFr.from_host(ctx, p) for p in polys]
+    want = [o.kzg_commit(srs, p) for p in polys]
+    assert ck.batch_commit(dev) == want
+    monkeypatch.setattr(kzg, "CONCURRENT_COMMITS", False)
+    assert ck.batch_commit(dev) == want
+    assert ck.batch_commit(polys) == want          # host inputs: the plain sequential map
+    # against a precomputed key at a size where both lanes carry real work
+    ck2 = gm.CommitterKey.new(ctx, (1 << 16) - 1, 3, random.Random(4), precompute=True)
+    monkeypatch.setattr(kzg, "CONCURRENT_COMMITS", True)
+    f = DeviceFr.random(ctx, 1 << 16, 55)
+    levels = f.fold_chain(rand_scalars(12, 97))
+    got = ck2.batch_commit(levels)
+    monkeypatch.setattr(kzg, "CONCURRENT_COMMITS", False)
+    assert got == ck2.batch_commit(levels)
