@@ -4,7 +4,7 @@
 #include "../../gemini_b200/csrc/fp.cuh"
 #include "../../gemini_b200/csrc/g1.cuh"
 #include "../../gemini_b200/csrc/g1_affine.cuh"
-#include "../../gemini_b200/csrc/fq_f64.cuh"
+#include "../../tools/fq_f64.cuh"
 #include "../../gemini_b200/csrc/fp_inv_fast.cuh"
 #include <string.h>
 using namespace gm;
