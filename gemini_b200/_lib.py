@@ -74,6 +74,8 @@ SIGNATURES = {
     "gm_msm_g1_sharded": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
     "gm_msm_g1_sharded_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _vp]),
     "gm_msm_stream_finalize_sharded": (_i, [_vp, _vp]),
+    "gm_msm_g1_strided_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i, _i, _vp]),
+    "gm_srs_subsample": (_i, [_vp, _vp, _sz, _sz, _sz, _pp]),
     "gm_fr_fold": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "gm_fr_fold_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "gm_fr_fold_chain": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),

@@ -150,6 +150,18 @@ class Context:
         check(lib.gm_msm_g1_sharded(self._h, srs._h, base_offset, _ptr(arr), cnt, int(bigint), _ptr(out)))
         return out
 
+    def msm_strided_dev(self, srs: "Srs", scalars_dev_ptr: int, n: int, stride: int, sharded: bool = False, base_offset: int = 0,
+                        bigint: bool = False) -> np.ndarray:
+        """term i uses the scalar at scalars_dev_ptr + 32 * i * stride (gm_msm_g1_strided_dev)"""
+        out = np.empty(18, dtype=np.uint64)
+        check(lib.gm_msm_g1_strided_dev(self._h, srs._h, base_offset, C.c_void_p(scalars_dev_ptr), n, stride, int(bigint), int(sharded), _ptr(out)))
+        return out
+
+    def srs_subsample(self, srs: "Srs", first: int, stride: int, count: int) -> "Srs":
+        h = C.c_void_p()
+        check(lib.gm_srs_subsample(self._h, srs._h, first, stride, count, C.byref(h)))
+        return Srs(self, h.value)
+
     def msm_sharded_dev(self, srs: "Srs", scalars_dev_ptr: int, n: int, base_offset: int = 0, bigint: bool = False) -> np.ndarray:
         out = np.empty(18, dtype=np.uint64)
         check(lib.gm_msm_g1_sharded_dev(self._h, srs._h, base_offset, C.c_void_p(scalars_dev_ptr), n, int(bigint), _ptr(out)))

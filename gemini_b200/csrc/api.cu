@@ -544,6 +544,39 @@ int gm_msm_g1_sharded_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, co
                     out_jacobian, /*sharded=*/true);
 }
 
+// General device-scalar entry: term i uses scalars_dev[i * scalar_stride].  With a world of W ranks dealing points out
+// cyclically (rank r holds P_r, P_{r+W}, ...: every vector, whatever its length, splits evenly - the fold levels of
+// tensorcheck halve 23 times), rank r passes scalars_dev = v + r, scalar_stride = W, n = ceil((len - r) / W).
+int gm_msm_g1_strided_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n, size_t scalar_stride,
+                          int scalars_are_bigint, int sharded, uint64_t out_jacobian[18]) {
+  GM_ARG(ctx && srs && out_jacobian && (scalars_dev || n == 0), "NULL argument");
+  GM_ARG(base_offset <= srs->n && scalar_stride >= 1, "base_offset beyond the SRS, or a zero stride");
+  GM_ENTER(ctx);
+  n = std::min(n, srs->n - base_offset);
+  GM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  ctx->msm.scalar_stride = scalar_stride;
+  const int rc = msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, reinterpret_cast<const uint32_t*>(scalars_dev), n,
+                            scalars_are_bigint != 0, out_jacobian, sharded != 0);
+  ctx->msm.scalar_stride = 1;
+  return rc;
+}
+
+// every `stride`-th point of an SRS, starting at `first`: the cyclic shard of one rank, cut from a resident key
+int gm_srs_subsample(gm_ctx* ctx, const gm_srs* srs, size_t first, size_t stride, size_t count, gm_srs** out_srs) {
+  GM_ARG(ctx && srs && out_srs && stride >= 1, "bad argument");
+  GM_ARG(count == 0 || first + (count - 1) * stride < srs->n, "range outside the SRS");
+  GM_ENTER(ctx);
+  gm_srs* s = nullptr;
+  GM_TRY(srs_alloc(ctx, count, &s));
+  cudaError_t e = count ? cudaMemcpy2DAsync(s->d_points, sizeof(Affine), reinterpret_cast<const Affine*>(srs->d_points) + first,
+                                            stride * sizeof(Affine), sizeof(Affine), count, cudaMemcpyDeviceToDevice, ctx->stream)
+                        : cudaSuccess;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { set_error("srs subsample: %s", cudaGetErrorString(e)); gm_srs_free(s); return GM_ERR_CUDA; }
+  *out_srs = s;
+  return GM_OK;
+}
+
 int gm_msm_g1_sharded(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
                       int scalars_are_bigint, uint64_t out_jacobian[18]) {
   GM_ARG(ctx && srs && out_jacobian && (scalars || n == 0), "NULL argument");

@@ -64,6 +64,7 @@ struct DevBuf {
 };
 
 struct MsmScratch {
+  size_t scalar_stride = 1;   // scalars of the running call are `stride` Fr elements apart (cyclic sharding across GPUs); set per call
   DevBuf scalars;    // staged scalars (host-call path)
   DevBuf digits;     // W*n digit codes
   DevBuf sorted;     // W*n point references grouped by bucket

@@ -84,13 +84,14 @@ struct Meta {
 // -------------------------------------------------------------------------------------------
 // 1. digits + histogram
 // -------------------------------------------------------------------------------------------
-__global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, int is_bigint, int c, int W, int merged,
+// stride: term i reads scalar i * stride (1 = dense; world size when a vector is dealt out cyclically to the ranks)
+__global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, size_t stride, int is_bigint, int c, int W, int merged,
                               uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
   Fr s = Fr::zero();
   if (live) {
-    const uint4* p = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + (size_t)i * stride * 8);
     uint4 lo = __ldg(p), hi = __ldg(p + 1);
     s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
     s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
@@ -768,7 +769,7 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   const uint32_t* counts = S.counts.as<uint32_t>();
   const uint32_t* starts = S.starts.as<uint32_t>();
   GM_CUDA(cudaEventRecord(ctx->ev[2], st));
-  LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
+  LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, S.scalar_stride, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
   LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, counts, S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32, pad);
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
   LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
@@ -857,7 +858,7 @@ int msm_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uin
     const MsmPlan P = plan_for(B, m);
     const size_t M = (size_t)(P.merged ? 1 : P.W) * P.nb;
     GM_TRY(ctx->msm.buckets.reserve(M * sizeof(XYZZ)));
-    GM_TRY(msm_sort_accumulate(ctx, B, base_offset + off, d_scalars + off * 8, m, bigint, P, ctx->msm.buckets.as<XYZZ>(), nullptr));
+    GM_TRY(msm_sort_accumulate(ctx, B, base_offset + off, d_scalars + off * 8 * ctx->msm.scalar_stride, m, bigint, P, ctx->msm.buckets.as<XYZZ>(), nullptr));
     GM_TRY(msm_reduce(ctx, P, ctx->msm.buckets.as<XYZZ>(), ctx->msm.counts.as<uint32_t>(), d_acc));
   }
   return GM_OK;

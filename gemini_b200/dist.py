@@ -190,3 +190,65 @@ class ShardedTimeProver:
 
     def final_foldings(self):
         return self.tail.final_foldings() if self.tail is not None else None
+
+
+# ---------------------------------------------------------------------------------------------------
+# KZG across ranks: snark::Proof::new_time on N GPUs (BASELINE config 4)
+# ---------------------------------------------------------------------------------------------------
+class ShardedCommitterKey:
+    """``CommitterKey`` (/root/reference/src/kzg/time.rs:24-160) whose ``powers_of_g`` are dealt out CYCLICALLY to the ranks
+    of the library communicator: rank r holds g^(tau^r), g^(tau^(r+W)), ...  A commitment to a vector of any length m
+    then costs every rank an MSM of ceil((m - r) / W) terms - the 23 fold levels of tensorcheck halve each time, and
+    contiguous ranges would leave all but the first rank idle from the third level on - plus ONE all-gather of 192-byte
+    partial sums inside the library (gm_msm_g1_strided_dev with sharded = 1).
+
+    The vectors themselves are replicated: every rank runs the prover's Fr work (sumchecks, folds, quotients) on the full
+    vectors and draws the same challenges, so no collective touches them.  The methods take resident ``DeviceFr``
+    polynomials and mirror ``kzg.CommitterKey``."""
+
+    def __init__(self, ctx, srs_shard, rank: int = None, world: int = None):
+        self.ctx, self.srs = ctx, srs_shard
+        self.rank = ctx.comm_rank if rank is None else rank
+        self.world = ctx.comm_world if world is None else world
+
+    @classmethod
+    def from_full_key(cls, ctx, full_srs, precompute: bool = True) -> "ShardedCommitterKey":
+        """cut this rank's shard out of a resident full key (a deployment loads the shard straight from the host:
+        gm_srs_load_g1 with stride_bytes = W * 104 and the pointer advanced by r records)"""
+        rank, world = ctx.comm_rank, ctx.comm_world
+        n = len(full_srs)
+        count = (n - rank + world - 1) // world if n > rank else 0
+        shard = ctx.srs_subsample(full_srs, rank, world, count)
+        if precompute and count:
+            shard.precompute()
+        return cls(ctx, shard, rank, world)
+
+    def max_degree(self) -> int:
+        return len(self.srs) * self.world - 1        # upper bound; the exact length lives with whoever cut the shards
+
+    def commit_raw(self, v) -> np.ndarray:
+        m = v.n
+        local = (m - self.rank + self.world - 1) // self.world if m > self.rank else 0
+        return self.ctx.msm_strided_dev(self.srs, v.ptr + 32 * self.rank, local, self.world, sharded=True)
+
+    def commit(self, v):
+        from . import field
+
+        return field.jacobian_to_affine(self.commit_raw(v))
+
+    def batch_commit(self, polynomials):
+        return [self.commit(p) for p in polynomials]      # every rank issues the same sequence of collectives
+
+    def open(self, polynomial, evaluation_point: int):
+        from . import field
+
+        if polynomial.n == 0:
+            return 0, None
+        q, evaluation = polynomial.div_linear(evaluation_point % field.R)
+        return evaluation, self.commit(q)
+
+    def open_multi_points(self, polynomial, eval_points):
+        from .kzg import _divide_by_points
+
+        q, _ = _divide_by_points(polynomial, eval_points)
+        return self.commit(q)

@@ -96,7 +96,7 @@ def tensorcheck_new_time(transcript, ck: CommitterKey, base_polynomials: Sequenc
     q = batched
     for pt in (eval_chal2, eval_chal, minus):
         q, _ = q.div_linear(pt)
-    proof = field.jacobian_to_affine(ctx.msm_dev(ck.srs, q.ptr, q.n)) if q.n else None
+    proof = ck.commit(q) if q.n else None
     return {"base_polynomials_evaluations": base_evals, "folded_polynomials_evaluations": fold_evals,
             "evaluation_proof": proof, "folded_polynomials_commitments": commitments}
 
@@ -115,7 +115,7 @@ def new_time(ctx: Context, r1cs: R1cs, ck: CommitterKey, transcript, timers: Opt
     lap("matrix-vector products", t0)
 
     t0 = time.perf_counter()
-    witness_commitment = field.jacobian_to_affine(ctx.msm_dev(ck.srs, r1cs.w.ptr, r1cs.w.n))
+    witness_commitment = ck.commit(r1cs.w)
     lap("Commitment to w", t0)
     transcript.append_g1(b"witness", witness_commitment)
     alpha = transcript.get_challenge(b"alpha")

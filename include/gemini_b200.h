@@ -147,6 +147,13 @@ int gm_msm_g1_sharded(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const 
                       int scalars_are_bigint, uint64_t out_jacobian[18]);
 int gm_msm_g1_sharded_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
                           int scalars_are_bigint, uint64_t out_jacobian[18]);
+/* term i uses scalars_dev[i * scalar_stride]; sharded != 0 adds the exchange.  Cyclic sharding (rank r holds every world-th
+ * point from r on) splits a vector of ANY length evenly: rank r passes scalars_dev = v + r, scalar_stride = world,
+ * n = ceil((len - r) / world) - the shape of a multi-GPU CommitterKey::commit (src/kzg/time.rs:81-83) */
+int gm_msm_g1_strided_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n, size_t scalar_stride,
+                          int scalars_are_bigint, int sharded, uint64_t out_jacobian[18]);
+/* every stride-th point of a resident SRS from `first` on, as a new SRS handle (a rank's cyclic shard) */
+int gm_srs_subsample(gm_ctx* ctx, const gm_srs* srs, size_t first, size_t stride, size_t count, gm_srs** out_srs);
 /* msm_chunks across ranks (config 5): every rank streams its own range; the exchange happens once, here.  The handle
  * must not be pushed to afterwards. */
 int gm_msm_stream_finalize_sharded(gm_msm_stream* s, uint64_t out_jacobian[18]);

@@ -27,6 +27,8 @@ def plan(job, args):
         out.append(("sumcheck_2^24_config3", lambda: sumcheck_rows(job, 24)))
         out.append(("snark_time_prover_config4", lambda: snark_line(job, args.extras_logn)))
         out.append(("snark_elastic_prover_1gpu", lambda: elastic_line(job, args.extras_logn)))
+    else:
+        out.append(("snark_time_prover_config4_sharded", lambda: sharded_snark_line(job, args.extras_logn)))
     out.append(("streamed_msm_config5", lambda: streamed_line(job, 24 if job.world == 1 else 25, 20)))
     out.append(("strong_scaling_msm_2^24", lambda: strong_line(job, 24, 5)))
     out.append(("strong_scaling_msm_2^26", lambda: strong_line(job, 26, 3)))
@@ -167,6 +169,12 @@ def snark_line(job, logn):
     import bench_snark
 
     return bench_snark.run(job.ctx, logn, 2)
+
+
+def sharded_snark_line(job, logn):
+    import bench_snark
+
+    return bench_snark.run_sharded(job, logn, 2)
 
 
 def elastic_line(job, logn):

@@ -59,6 +59,25 @@ def main():
     it = iter(ch)
     want = o.sumcheck_prove(o.TimeProver(f, g, tw), lambda msg: next(it))
     assert got.messages == want[0] and tuple(got.final_foldings[0]) == tuple(want[2]), "sharded sumcheck differs"
+    # snark::Proof::new_time with the key dealt out cyclically over the ranks == the single-GPU proof == the oracle
+    from gemini_b200 import snark
+    from gemini_b200.transcript import MerlinTranscript
+
+    nn = 64
+    srs_pts = rand_points(2 * nn + 5, 21)
+    full = ctx.srs_load(srs_pts)
+    sck = gdist.ShardedCommitterKey.from_full_key(ctx, full)
+    r1 = snark.R1cs.dummy(ctx, nn, 424242)
+    got_p = snark.new_time(ctx, r1, sck, MerlinTranscript())
+    want_p = snark.new_time(ctx, r1, gm.CommitterKey(ctx, full), MerlinTranscript())
+    assert got_p == want_p, "sharded time prover differs from the single-GPU one"
+    if rank == 0:
+        assert got_p == o.snark_new_time(o.dummy_r1cs(424242, nn), srs_pts, o.MerlinTranscript()), "time prover differs from the oracle"
+    # strided scalars without the exchange: rank r's share of a commitment, summed by hand
+    v = gm.DeviceFr.from_host(ctx, sc[:300])
+    part = ctx.msm_strided_dev(sck.srs, v.ptr + 32 * rank, (300 - rank + world - 1) // world, world, sharded=False)
+    tot = ctx.g1_sum(ctx.comm_allgather(part))
+    assert gm.field.jacobian_to_affine(tot) == o.naive_msm(srs_pts[:300], sc[:300]) == sck.commit(v)
     ctx.comm_barrier()
     if rank == 0:
         print(f"comm_check ok: world={world} nccl={gm.lib.gm_comm_nccl_version()}")
