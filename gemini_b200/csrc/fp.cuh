@@ -20,6 +20,7 @@ namespace gm {
 // ---------------------------------------------------------------------------
 struct FqParams {
   static constexpr int N = 12;
+  static constexpr bool LOW_LIMBS_1_FFFFFFFF = false;
   static constexpr uint32_t INV = 0xfffcfffdu;  // -q^{-1} mod 2^32
   GM_HD static constexpr uint32_t inv() { return INV; }
   GM_HD static constexpr uint32_t mod(int j) {
@@ -51,6 +52,7 @@ static __constant__ uint32_t FR_INV_BANK = 0xffffffffu;
 
 struct FrParams {
   static constexpr int N = 8;
+  static constexpr bool LOW_LIMBS_1_FFFFFFFF = true;   // mod(0) = 1, mod(1) = 0xffffffff, inv = -1: see mont_reduce_step
   static constexpr uint32_t INV = 0xffffffffu;  // -r^{-1} mod 2^32
   GM_HD static uint32_t inv() {
 #if defined(__CUDA_ARCH__)
@@ -92,15 +94,29 @@ GM_HD void row_first(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t w) {
 }
 
 // Montgomery step: add m*p with m chosen so that column 0 (E[0]) becomes zero.
+// P::LOW_LIMBS_1_FFFFFFFF (Fr: r = ... ffffffff 00000001): m * p_0 = m and m * p_1 = m 2^32 - m need no multiplier -
+// with m = -E[0] the low word of the latter is the old E[0] itself - so the first product of either chain becomes two
+// additions on the ALU pipe: 6 IMAD.WIDE per row instead of 8.
 template <class P>
 GM_HD void mont_reduce_step(uint32_t* E, uint32_t* O) {
   constexpr int N = P::N;
   const uint32_t m = E[0] * P::inv();
-  mad_wide_cc(O[0], O[1], m, P::mod(1), O[0], O[1]);
+  if constexpr (P::LOW_LIMBS_1_FFFFFFFF) {
+    const uint32_t hi = m - (m != 0u ? 1u : 0u);   // (m 2^32 - m) >> 32
+    O[0] = add_cc(O[0], E[0]);                      // (m 2^32 - m) mod 2^32 = -m = E[0]
+    O[1] = addc_cc(O[1], hi);
+  } else {
+    mad_wide_cc(O[0], O[1], m, P::mod(1), O[0], O[1]);
+  }
 #pragma unroll
   for (int j = 3; j < N; j += 2) madc_wide_cc(O[j - 1], O[j], m, P::mod(j), O[j - 1], O[j]);
   // (no carry out of the odd chain: the running value is < 2^(32(N+1)))
-  mad_wide_cc(E[0], E[1], m, P::mod(0), E[0], E[1]);
+  if constexpr (P::LOW_LIMBS_1_FFFFFFFF) {
+    E[0] = add_cc(E[0], m);                         // = 0, carry = (m != 0)
+    E[1] = addc_cc(E[1], 0);
+  } else {
+    mad_wide_cc(E[0], E[1], m, P::mod(0), E[0], E[1]);
+  }
 #pragma unroll
   for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], m, P::mod(j), E[j], E[j + 1]);
   O[N - 1] = addc(O[N - 1], 0);  // even chain's carry sits at column N
@@ -132,6 +148,33 @@ GM_HD void cond_sub_p(uint32_t* r, const uint32_t* a) {
   const uint32_t borrow = subc(0, 0);  // 0xffffffff if a < p
 #pragma unroll
   for (int j = 0; j < N; j++) r[j] = borrow ? a[j] : t[j];
+}
+
+}  // namespace detail
+
+namespace detail {
+
+// t[0..2N) = a * b, N even: the rows of the CIOS schedule without its reduction steps - the lowest column of the
+// running sum is final after every row and leaves through t[i] where the CIOS would have made it zero.
+template <int N>
+GM_HD void mul_full(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  uint32_t x[N], y[N];
+  row_first<N>(x, y, a, b[0]);
+  t[0] = x[0];
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    row_next<N>(x, y, a, b[i]);  // even = y, odd = x
+    t[i] = y[0];
+    if (i + 1 < N) {
+      row_next<N>(y, x, a, b[i + 1]);
+      t[i + 1] = x[0];
+    }
+  }
+  // even = y (y[0] already emitted), odd = x: column k of what is left = y[k] + x[k-1]
+  t[N] = add_cc(x[0], y[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[N + k] = addc_cc(x[k], y[k + 1]);
+  t[2 * N - 1] = addc(x[N - 1], 0);
 }
 
 }  // namespace detail
@@ -202,6 +245,7 @@ GM_HD void fp_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 // ---------------------------------------------------------------------------
 template <class P>
 struct Fp {
+  using Params = P;
   static constexpr int N = P::N;
   uint32_t v[N];
 
@@ -263,26 +307,25 @@ struct FpAcc {
     for (int j = 0; j < 2 * N; j++) r.v[j] = 0;
     return r;
   }
-  // acc += a * b   (a, b < p)
-  GM_HD void mul_add(const Fp<P>& a, const Fp<P>& b) {
-    uint32_t c0 = 0, c1 = 0, c2 = 0;
+  // acc += a * b WITHOUT touching the invariant: the product comes from the row schedule of the Montgomery product
+  // (detail::mul_full: N^2 IMAD.WIDE.X on aligned carry chains, ~2N additions) and is added with one 2N-limb carry chain -
+  // a third of the ALU instructions of column-wise product scanning (measured, round 2: the message kernels spent
+  // 450 of 628 instructions per pair on the three-word column accumulators).  Bound: with acc < p 2^(32N) on entry, k products
+  // leave acc < p 2^(32N) + k p^2, which is < 2 p 2^(32N) (no overflow, and ONE conditional subtraction restores the
+  // invariant) as long as k p < 2^(32N): k <= 2 for Fr (2^256 / r = 2.2), k <= 9 for Fq.
+  static constexpr int UNREDUCED_RUN = (N == 8) ? 2 : 9;
+  GM_HD void mul_add_unreduced(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t t[2 * N];
+    detail::mul_full<N>(t, a.v, b.v);
+    v[0] = add_cc(v[0], t[0]);
 #pragma unroll
-    for (int k = 0; k < 2 * N; k++) {
-      // column k: previous limb of the accumulator plus all a[i] * b[k - i]
-      c0 = add_cc(c0, v[k]);
-      c1 = addc_cc(c1, 0);
-      c2 = addc(c2, 0);
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        const int j = k - i;
-        if (j >= 0 && j < N) mad_acc3(c0, c1, c2, a.v[i], b.v[j]);
-      }
-      v[k] = c0;
-      c0 = c1; c1 = c2; c2 = 0;
-    }
-    // acc < p 2^(32N) + p^2 < 2 p 2^(32N): one conditional subtraction of p from the top half restores the invariant
-    detail::cond_sub_p<P>(v + N, v + N);
+    for (int k = 1; k < 2 * N - 1; k++) v[k] = addc_cc(v[k], t[k]);
+    v[2 * N - 1] = addc(v[2 * N - 1], t[2 * N - 1]);
   }
+  // after at most UNREDUCED_RUN calls of mul_add_unreduced: top half back below p
+  GM_HD void normalize() { detail::cond_sub_p<P>(v + N, v + N); }
+  // acc += a * b   (a, b < p), invariant kept
+  GM_HD void mul_add(const Fp<P>& a, const Fp<P>& b) { mul_add_unreduced(a, b); normalize(); }
   // (acc / 2^(32N)) mod p as a field element: top half + REDC(bottom half)
   GM_HD Fp<P> reduce() const {
     Fp<P> lo, hi, one;

@@ -13,6 +13,8 @@
 //   herring : the same with twist = 1 (herring/time_prover.rs:91-123 applies the twist only in fold)
 // Missing elements (odd tails, unequal lengths) read as zero, exactly like the reference's
 // `unwrap_or(&zero)` / zip-to-shorter (a product with a zero partner vanishes).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -150,17 +152,20 @@ __device__ __forceinline__ Fr sc_acc_value(const ScAcc& a) { return a.reduce(); 
 template <bool TW>
 __device__ __forceinline__ void pair_contrib(ScAcc& a, ScAcc& b, const Fr& fe, const Fr& fo, const Fr& ge, const Fr& go,
                                              const Fr& t, const Fr& tt) {
+  static_assert(ScAcc::UNREDUCED_RUN >= 2, "b takes two unreduced products per pair");
   if (TW) {
     const Fr u = fe * t;
     const Fr v = ge * tt;
-    a.mul_add(u, ge);
-    b.mul_add(u, go);
-    b.mul_add(v, fo);
+    a.mul_add_unreduced(u, ge);
+    b.mul_add_unreduced(u, go);
+    b.mul_add_unreduced(v, fo);
   } else {
-    a.mul_add(fe, ge);
-    b.mul_add(fe, go);
-    b.mul_add(ge, fo);
+    a.mul_add_unreduced(fe, ge);
+    b.mul_add_unreduced(fe, go);
+    b.mul_add_unreduced(ge, fo);
   }
+  a.normalize();
+  b.normalize();
 }
 
 template <bool TW>
@@ -216,6 +221,138 @@ k_sc_fold_message(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g,
     pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
     if (TW) { t = t * step; tt = tt * step; }
   }
+  sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out, mb, seq);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged variants of the two round kernels for long vectors.  ncu (profiles/r02_ncu_sumcheck_summary.txt) shows the
+// register-fed kernels above at 63-73 % of the multiplier pipe with 16 warps per SM: whenever a warp waits for its
+// loads (long scoreboard, 29 % of the stall cycles) the three others cannot cover the dependent IMAD.WIDE chains.
+// Here every WARP streams its own slices of f and g through a private ring of shared-memory buffers with
+// cp.async (LDGSTS, 16 bytes per lane, 512 contiguous bytes per instruction): the copies of the next two half-steps
+// are in flight while the current one is multiplied, they cost no registers, and because a buffer is only ever read
+// by the warp that filled it the only synchronisation is cp.async.wait_group + __syncwarp.  Elements beyond the end
+// of a vector are zero-filled by the copy (src-size 0), which is the reference's `unwrap_or(zero)` / zip-to-shorter.
+//   EPP = elements of one vector per "pair": 2 (message) or 4 (fold + message); a half-step = 32 * EPP elements.
+//   Layout of a buffer: thread t's 2*EPP chunks of 16 bytes are contiguous, chunk index XOR-swizzled by t so that
+//   the LDS.128 of a quarter warp touch all 32 banks.
+// ---------------------------------------------------------------------------------------------
+template <int EPP>
+struct ScStage {
+  static constexpr int C = 2 * EPP;                       // 16-byte chunks per thread and half-step
+  static constexpr uint32_t BYTES = 32u * C * 16u;        // one half-step of one warp
+  __device__ __forceinline__ static uint32_t slot(uint32_t t, uint32_t c) {
+    const uint32_t sw = (C == 8) ? (t & 7u) : ((t >> 1) & 3u);
+    return (t * C + (c ^ sw)) * 16u;
+  }
+};
+
+// the warp copies elements [e0, e0 + 32 * EPP) of v (n elements; zero beyond) into the buffer at shared address `buf`
+template <int EPP>
+__device__ __forceinline__ void sc_stage_issue(uint32_t buf, const Fr* __restrict__ v, size_t n, size_t e0, uint32_t lane) {
+  using St = ScStage<EPP>;
+#pragma unroll
+  for (int j = 0; j < St::C; j++) {
+    const uint32_t q = (uint32_t)j * 32u + lane;          // chunk of the slice: lanes copy 512 contiguous bytes
+    const size_t e = e0 + (q >> 1);
+    const bool ok = e < n;
+    const char* src = reinterpret_cast<const char*>(v + (ok ? e : 0)) + (q & 1u) * 16u;
+    const uint32_t dst = buf + St::slot(q / St::C, q % St::C);
+    const uint32_t sz = ok ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+  }
+}
+__device__ __forceinline__ void sc_stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void sc_stage_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+  __syncwarp();
+}
+// element k (0 <= k < EPP) of this lane's part of a landed half-step
+template <int EPP>
+__device__ __forceinline__ Fr sc_stage_read(uint32_t buf, uint32_t lane, int k) {
+  using St = ScStage<EPP>;
+  Fr r;
+  uint4 lo, hi;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(buf + St::slot(lane, 2 * k)));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(buf + St::slot(lane, 2 * k + 1)));
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+
+static constexpr int SC_RING = 3;   // half-step buffers per warp: two copies in flight while one is consumed
+
+// FOLD = false: message of (f, g).  FOLD = true: fold by (rf, rg), write the folded vectors, message of the folded
+// vectors (nf / ng are the lengths BEFORE the fold, npairs counts pairs of the vectors the message is taken of).
+template <bool TW, bool FOLD>
+__global__ void __launch_bounds__(SC_THREADS, 2)
+k_sc_staged(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr rf, Fr rg, Fr* __restrict__ f_out,
+            Fr* __restrict__ g_out, size_t npairs, Fr twist, PowTable tab, int kpt, Fr* partials, unsigned int* ticket, Fr* out,
+            ScMailbox* mb, uint32_t seq) {
+  constexpr int EPP = FOLD ? 4 : 2;
+  using St = ScStage<EPP>;
+  extern __shared__ uint4 sc_ring_raw[];
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sc_ring_raw) + wid * (SC_RING * St::BYTES);
+  const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;   // this thread's first pair
+  const size_t w0 = i0 - lane;                                             // the warp's first pair
+  // iterations of this warp (uniform across its lanes): pairs w0 + k * SC_THREADS < npairs
+  int iters = 0;
+  if (w0 < npairs) iters = (int)min((size_t)kpt, (npairs - w0 + SC_THREADS - 1) / SC_THREADS);
+  const int hsteps = 2 * iters;                                            // f slice, g slice, f slice, ...
+  auto issue = [&](int h) {
+    if (h < hsteps) {
+      const size_t e0 = (w0 + (size_t)(h >> 1) * SC_THREADS) * EPP;
+      if (h & 1) sc_stage_issue<EPP>(ring + (uint32_t)(h % SC_RING) * St::BYTES, g, ng, e0, lane);
+      else sc_stage_issue<EPP>(ring + (uint32_t)(h % SC_RING) * St::BYTES, f, nf, e0, lane);
+    }
+    sc_stage_commit();   // (possibly empty) group: keeps the wait_group distance constant
+  };
+  issue(0);
+  issue(1);
+  ScAcc a = ScAcc::zero(), b = ScAcc::zero();
+  Fr t = Fr::one(), tt = Fr::one(), step = Fr::one();
+  if (TW && iters > 0) { t = pow_from_table(tab, i0); tt = t * twist; step = tab.p[8]; }
+  const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) {
+    const size_t i = i0 + (size_t)k * SC_THREADS;
+    Fr fe, fo, ge, go;
+    // ---- f slice
+    sc_stage_wait<1>();
+    issue(2 * k + 2);
+    {
+      const uint32_t buf = ring + (uint32_t)((2 * k) % SC_RING) * St::BYTES;
+      if (FOLD) {
+        fe = sc_stage_read<EPP>(buf, lane, 0) + rf * sc_stage_read<EPP>(buf, lane, 1);
+        fo = sc_stage_read<EPP>(buf, lane, 2) + rf * sc_stage_read<EPP>(buf, lane, 3);
+        if (2 * i < nf2) store_fr(f_out + 2 * i, fe);
+        if (2 * i + 1 < nf2) store_fr(f_out + 2 * i + 1, fo);
+      } else {
+        fe = sc_stage_read<EPP>(buf, lane, 0);
+        fo = sc_stage_read<EPP>(buf, lane, 1);
+      }
+    }
+    // ---- g slice
+    sc_stage_wait<1>();
+    issue(2 * k + 3);
+    {
+      const uint32_t buf = ring + (uint32_t)((2 * k + 1) % SC_RING) * St::BYTES;
+      if (FOLD) {
+        ge = sc_stage_read<EPP>(buf, lane, 0) + rg * sc_stage_read<EPP>(buf, lane, 1);
+        go = sc_stage_read<EPP>(buf, lane, 2) + rg * sc_stage_read<EPP>(buf, lane, 3);
+        if (2 * i < ng2) store_fr(g_out + 2 * i, ge);
+        if (2 * i + 1 < ng2) store_fr(g_out + 2 * i + 1, go);
+      } else {
+        ge = sc_stage_read<EPP>(buf, lane, 0);
+        go = sc_stage_read<EPP>(buf, lane, 1);
+      }
+    }
+    pair_contrib<TW>(a, b, fe, fo, ge, go, t, tt);
+    if (TW) { t = t * step; tt = tt * step; }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   sc_reduce_and_publish(sc_acc_value(a), sc_acc_value(b), partials, ticket, out, mb, seq);
 }
 
@@ -461,16 +598,44 @@ size_t sc_max_ctas(size_t nf, size_t ng) {
   return std::max<size_t>(1024, (npairs + SC_TILE - 1) / SC_TILE);  // >= the largest grid of any later round
 }
 
+// Vectors of more than 2^sc_staged_min_log() pairs go through k_sc_staged (GM_SC_STAGED_MIN_LOG=64 switches it off).
+static int sc_staged_min_log() {
+  static const int v = [] {
+    const char* e = getenv("GM_SC_STAGED_MIN_LOG");
+    return e ? atoi(e) : 19;
+  }();
+  return v;
+}
+template <bool TW, bool FOLD>
+static int sc_staged_launch(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg, Fr* d_f_out,
+                            Fr* d_g_out, size_t npairs, const Fr& twist, const PowTable& tab, int kpt, unsigned grid, Fr* d_partials,
+                            unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq) {
+  constexpr size_t shmem = (size_t)(SC_THREADS / 32) * SC_RING * ScStage<FOLD ? 4 : 2>::BYTES;
+  // per device and cheap next to a round of this size: set on every launch rather than cached per process
+  GM_CUDA(cudaFuncSetAttribute(k_sc_staged<TW, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+  LAUNCH_LN(ctx, (k_sc_staged<TW, FOLD>), grid, SC_THREADS, shmem, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, twist, tab, kpt,
+            d_partials, d_ticket, d_out, mb, seq);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
 int sc_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& twist, bool use_twist,
                    Fr* d_partials, unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq) {
   const size_t npairs = std::min((nf + 1) / 2, (ng + 1) / 2);
   const int kpt = sc_pairs_per_thread(npairs);
   const unsigned grid = sc_grid(npairs, kpt);
+  const bool staged = sc_staged_min_log() < 63 && npairs > ((size_t)1 << sc_staged_min_log());
   if (use_twist) {
     PowTable tab = make_pow_table(twist, npairs);
+    if (staged)
+      return sc_staged_launch<true, false>(ctx, d_f, nf, d_g, ng, twist, twist, nullptr, nullptr, npairs, twist, tab, kpt, grid, d_partials,
+                                           d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out, mb, seq);
   } else {
     PowTable tab;  // unused
+    if (staged)
+      return sc_staged_launch<false, false>(ctx, d_f, nf, d_g, ng, twist, twist, nullptr, nullptr, npairs, twist, tab, kpt, grid, d_partials,
+                                            d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out, mb, seq);
   }
   GM_CUDA(cudaGetLastError());
@@ -484,12 +649,19 @@ int sc_fold_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g
   const size_t npairs = std::max((nf2 + 1) / 2, (ng2 + 1) / 2);
   const int kpt = sc_pairs_per_thread(npairs);
   const unsigned grid = sc_grid(npairs, kpt);
+  const bool staged = sc_staged_min_log() < 63 && npairs > ((size_t)1 << sc_staged_min_log());
   if (use_twist) {
     PowTable tab = make_pow_table(new_twist, npairs);
+    if (staged)
+      return sc_staged_launch<true, true>(ctx, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, new_twist, tab, kpt, grid, d_partials,
+                                          d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out, mb, seq);
   } else {
     PowTable tab;
+    if (staged)
+      return sc_staged_launch<false, true>(ctx, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, new_twist, tab, kpt, grid, d_partials,
+                                           d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out, mb, seq);
   }

@@ -5,6 +5,7 @@
 #include "../../gemini_b200/csrc/g1.cuh"
 #include "../../gemini_b200/csrc/g1_affine.cuh"
 #include "../../tools/fq_f64.cuh"
+#include "../../tools/fq_karatsuba.cuh"
 #include "../../gemini_b200/csrc/fp_inv_fast.cuh"
 #include <string.h>
 using namespace gm;
@@ -26,15 +27,41 @@ template <class F> static void f_redc(F& z, const F& x, const F&) { z = x.from_m
 template <class F> static void f_tom(F& z, const F& x, const F&) { z = x.to_mont(); }
 template <class F> static void f_sqr(F& z, const F& x, const F&) { z = x.sqr(); }
 static void f_mul_f64(Fq& z, const Fq& x, const Fq& y) { f64::fq_mul_f64(z.v, x.v, y.v); }
+template <class F> static void f_mul_k(F& z, const F& x, const F& y) { mont_mul_karatsuba<typename F::Params>(z.v, x.v, y.v); }
+template <class F> static void f_mul_k2(F& z, const F& x, const F& y) { mont_mul_karatsuba<typename F::Params, 2>(z.v, x.v, y.v); }
 
 extern "C" {
 void hc_fq(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
-  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64, f_inv_fast<Fq>};
+  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64, f_inv_fast<Fq>, f_mul_k<Fq>, f_mul_k2<Fq>};
   bin<Fq>(ops[op], a, b, r, n);
 }
 void hc_fr(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
-  void (*ops[])(Fr&, const Fr&, const Fr&) = {f_mul<Fr>, f_add<Fr>, f_sub<Fr>, f_inv<Fr>, f_redc<Fr>, f_tom<Fr>, f_sqr<Fr>, f_sqr<Fr>, f_inv_fast<Fr>};
+  void (*ops[])(Fr&, const Fr&, const Fr&) = {f_mul<Fr>, f_add<Fr>, f_sub<Fr>, f_inv<Fr>, f_redc<Fr>, f_tom<Fr>, f_sqr<Fr>, f_sqr<Fr>, f_inv_fast<Fr>, f_mul_k<Fr>, f_mul_k2<Fr>};
   bin<Fr>(ops[op], a, b, r, n);
+}
+// plain 2N-limb products of ARBITRARY N-limb operands (the building blocks of mont_mul_karatsuba); which: 0 = schoolbook
+// rows (mul_full), 1 = one Karatsuba level; nl = 4, 6, 8 or 12 limbs
+void hc_mul_full(int which, int nl, const uint32_t* a, const uint32_t* b, uint32_t* t, int n) {
+  for (int i = 0; i < n; i++) {
+    const uint32_t* x = a + i * nl; const uint32_t* y = b + i * nl; uint32_t* z = t + 2 * i * nl;
+    if (which == 0) {
+      if (nl == 4) detail::mul_full<4>(z, x, y); else if (nl == 6) detail::mul_full<6>(z, x, y);
+      else if (nl == 8) detail::mul_full<8>(z, x, y); else detail::mul_full<12>(z, x, y);
+    } else if (which == 1) {
+      if (nl == 8) detail::mul_full_karatsuba<8, 1>(z, x, y); else detail::mul_full_karatsuba<12, 1>(z, x, y);
+    } else if (which == 2) {
+      if (nl == 8) detail::mul_full_karatsuba<8, 2>(z, x, y); else detail::mul_full_karatsuba<12, 2>(z, x, y);
+    } else {
+      if (nl == 3) detail::mul_full_ps<3>(z, x, y); else if (nl == 6) detail::mul_full_karatsuba<6, 1>(z, x, y);
+      else detail::mul_full_ps<5>(z, x, y);
+    }
+  }
+}
+// u = lo * 2^(-32 N) mod p (<= p) for arbitrary N-limb lo
+void hc_redc_half(int is_fr, const uint32_t* lo, uint32_t* u, int n) {
+  for (int i = 0; i < n; i++) {
+    if (is_fr) detail::redc_half<FrParams>(u + 8 * i, lo + 8 * i); else detail::redc_half<FqParams>(u + 12 * i, lo + 12 * i);
+  }
 }
 // XYZZ accumulator (48 u32) (+)= affine point (24 u32, (0,0) = identity), optionally negated
 void hc_xyzz_madd(uint32_t* acc, const uint32_t* aff, int neg, int n) {
@@ -100,8 +127,11 @@ void hc_fr_sum_of_products(const uint32_t* a, const uint32_t* b, int n, uint32_t
   FrAcc acc = FrAcc::zero();
   for (int i = 0; i < n; i++) {
     Fr x, y; memcpy(x.v, a + 8 * i, 32); memcpy(y.v, b + 8 * i, 32);
-    acc.mul_add(x, y);
+    // the schedule of pair_contrib (fr.cu): UNREDUCED_RUN = 2 products, then one normalisation
+    acc.mul_add_unreduced(x, y);
+    if (i & 1) acc.normalize();
   }
+  acc.normalize();
   Fr r = acc.reduce();
   memcpy(out, r.v, 32);
 }

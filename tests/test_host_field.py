@@ -183,3 +183,52 @@ def test_fast_inverse_divsteps(hc, name, p, n):
     want = [pow(x * Ri % p, -1, p) * Rm % p for x in A]
     assert unpack(slow) == want
     assert unpack(fast) == want
+
+
+# ---- Karatsuba / separated-operand-scanning Montgomery product (tools/fq_karatsuba.cuh, an experiment; detail::mul_full is the product of FpAcc) ------------------------
+def _edge_ints(nl, rng, k):
+    full = (1 << (32 * nl)) - 1
+    e = [0, 1, full, full - 1, 1 << (32 * nl - 1), (1 << (16 * nl)) - 1, full ^ ((1 << (16 * nl)) - 1), 0xFFFFFFFF,
+         full ^ 0xFFFFFFFF, int("0000ffff" * nl, 16), int("ffff0000" * nl, 16)]
+    return e + [rng.randrange(full + 1) for _ in range(k)]
+
+
+@pytest.mark.parametrize("which,nl", [(0, 4), (0, 6), (0, 8), (0, 12), (1, 8), (1, 12), (2, 8), (2, 12), (3, 3), (3, 5), (3, 6)])
+def test_plain_products_on_arbitrary_limbs(hc, which, nl):
+    rng = random.Random(100 * which + nl)
+    E = _edge_ints(nl, rng, 0)
+    A = [x for x in E for _ in E] + _edge_ints(nl, rng, 600)
+    B = [y for _ in E for y in E] + _edge_ints(nl, rng, 600)[::-1]
+    a, b = pack(A, nl), pack(B, nl)
+    t = np.zeros((len(A), 2 * nl), dtype=np.uint32)
+    hc.hc_mul_full(which, nl, P(a), P(b), P(t), len(A))
+    assert unpack(t) == [x * y for x, y in zip(A, B)]
+
+
+@pytest.mark.parametrize("is_fr,p,n", [(0, o.Q, 12), (1, o.R, 8)])
+def test_redc_half_on_arbitrary_limbs(hc, is_fr, p, n):
+    rng = random.Random(7 + is_fr)
+    L = _edge_ints(n, rng, 1500) + [p, p - 1, p + 1, 2 * p, (1 << (32 * n)) - p]
+    lo = pack(L, n)
+    u = np.zeros_like(lo)
+    hc.hc_redc_half(is_fr, P(lo), P(u), len(L))
+    Ri = pow(1 << (32 * n), -1, p)
+    got = unpack(u)
+    assert all(g <= p for g in got)
+    assert [g % p for g in got] == [x * Ri % p for x in L]
+
+
+@pytest.mark.parametrize("name,p,n", [("hc_fq", o.Q, 12), ("hc_fr", o.R, 8)])
+def test_karatsuba_montgomery_product(hc, name, p, n):
+    fn = getattr(hc, name)
+    rng = random.Random(11)
+    Rm = (1 << (32 * n)) % p
+    Ri = pow(Rm, -1, p)
+    edge = [0, 1, p - 1, p - 2, Rm, (p - 1) // 2, (1 << (32 * n - 3)) % p, (1 << (16 * n)) - 1, (1 << (16 * n))]
+    A = [x for x in edge for _ in edge] + [rng.randrange(p) for _ in range(3000)]
+    B = [y for _ in edge for y in edge] + [rng.randrange(p) for _ in range(3000)]
+    a, b = pack(A, n), pack(B, n)
+    r = np.zeros_like(a)
+    for op in (9, 10):   # one and two Karatsuba levels
+        fn(op, P(a), P(b), P(r), len(A))
+        assert unpack(r) == [x * y * Ri % p for x, y in zip(A, B)], op

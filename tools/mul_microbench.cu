@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "fq_f64.cuh"
+#include "fq_karatsuba.cuh"
 using namespace gm;
 
 #define ITERS 512
@@ -14,7 +15,17 @@ __global__ void __launch_bounds__(128) bench(const Fq* in, Fq* out, int mode, in
   Fq x = in[tid & 1023], y = in[(tid + 7) & 1023], b = in[(tid + 13) & 1023];
   const int warp = threadIdx.x >> 5;
   const bool fp = mode == 1 || (mode == 2 && (warp % den) < num);
-  if (fp) {
+  if (mode == 3) {
+    for (int it = 0; it < ITERS; it++) {
+      mont_mul_karatsuba<FqParams>(x.v, x.v, b.v);
+      mont_mul_karatsuba<FqParams>(y.v, y.v, b.v);
+    }
+  } else if (mode == 4) {
+    for (int it = 0; it < ITERS; it++) {
+      mont_mul_karatsuba<FqParams, 2>(x.v, x.v, b.v);
+      mont_mul_karatsuba<FqParams, 2>(y.v, y.v, b.v);
+    }
+  } else if (fp) {
     for (int it = 0; it < ITERS; it++) {
       f64::fq_mul_f64(x.v, x.v, b.v);
       f64::fq_mul_f64(y.v, y.v, b.v);
@@ -38,7 +49,8 @@ int main() {
   cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
   struct { const char* name; int mode, num, den; } cfg[] = {
       {"integer only (IMAD.WIDE)", 0, 0, 1}, {"FP64 only (DFMA)", 1, 0, 1}, {"split 1/4 FP64", 2, 1, 4},
-      {"split 2/4 FP64", 2, 2, 4}, {"split 3/4 FP64", 2, 3, 4}};
+      {"split 2/4 FP64", 2, 2, 4}, {"split 3/4 FP64", 2, 3, 4}, {"integer, Karatsuba (1 level)", 3, 0, 1},
+      {"integer, Karatsuba (2 levels)", 4, 0, 1}};
   Fq ref[4];
   for (auto& c : cfg) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
