@@ -288,22 +288,26 @@ static constexpr int SC_RING = 3;   // half-step buffers per warp: two copies in
 template <bool TW, bool FOLD>
 __global__ void __launch_bounds__(SC_THREADS, 2)
 k_sc_staged(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_t ng, Fr rf, Fr rg, Fr* __restrict__ f_out,
-            Fr* __restrict__ g_out, size_t npairs, Fr twist, PowTable tab, int kpt, Fr* partials, unsigned int* ticket, Fr* out,
+            Fr* __restrict__ g_out, size_t npairs, Fr twist, PowTable tab, Fr step, Fr* partials, unsigned int* ticket, Fr* out,
             ScMailbox* mb, uint32_t seq) {
   constexpr int EPP = FOLD ? 4 : 2;
   using St = ScStage<EPP>;
   extern __shared__ uint4 sc_ring_raw[];
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sc_ring_raw) + wid * (SC_RING * St::BYTES);
-  const size_t i0 = (size_t)blockIdx.x * SC_THREADS * kpt + threadIdx.x;   // this thread's first pair
+  // PERSISTENT grid (two CTAs per SM): CTA b takes the tiles b, b + gridDim.x, ... of SC_THREADS pairs, so the two
+  // Montgomery reductions, the shuffle trees and the ticket of the epilogue are paid once per CTA and not once per
+  // 8 pairs (they were a quarter of the instructions of the 8-pairs-per-thread grid), and the tiles divide evenly.
+  const size_t stride = (size_t)gridDim.x * SC_THREADS;                    // pairs between two tiles of this CTA
+  const size_t i0 = (size_t)blockIdx.x * SC_THREADS + threadIdx.x;         // this thread's first pair
   const size_t w0 = i0 - lane;                                             // the warp's first pair
-  // iterations of this warp (uniform across its lanes): pairs w0 + k * SC_THREADS < npairs
+  // iterations of this warp (uniform across its lanes): pairs w0 + k * stride < npairs
   int iters = 0;
-  if (w0 < npairs) iters = (int)min((size_t)kpt, (npairs - w0 + SC_THREADS - 1) / SC_THREADS);
+  if (w0 < npairs) iters = (int)((npairs - w0 + stride - 1) / stride);
   const int hsteps = 2 * iters;                                            // f slice, g slice, f slice, ...
   auto issue = [&](int h) {
     if (h < hsteps) {
-      const size_t e0 = (w0 + (size_t)(h >> 1) * SC_THREADS) * EPP;
+      const size_t e0 = (w0 + (size_t)(h >> 1) * stride) * EPP;
       if (h & 1) sc_stage_issue<EPP>(ring + (uint32_t)(h % SC_RING) * St::BYTES, g, ng, e0, lane);
       else sc_stage_issue<EPP>(ring + (uint32_t)(h % SC_RING) * St::BYTES, f, nf, e0, lane);
     }
@@ -312,12 +316,12 @@ k_sc_staged(const Fr* __restrict__ f, size_t nf, const Fr* __restrict__ g, size_
   issue(0);
   issue(1);
   ScAcc a = ScAcc::zero(), b = ScAcc::zero();
-  Fr t = Fr::one(), tt = Fr::one(), step = Fr::one();
-  if (TW && iters > 0) { t = pow_from_table(tab, i0); tt = t * twist; step = tab.p[8]; }
+  Fr t = Fr::one(), tt = Fr::one();
+  if (TW && iters > 0) { t = pow_from_table(tab, i0); tt = t * twist; }    // step = (twist^2)^stride, from the host
   const size_t nf2 = (nf + 1) / 2, ng2 = (ng + 1) / 2;
 #pragma unroll 1
   for (int k = 0; k < iters; k++) {
-    const size_t i = i0 + (size_t)k * SC_THREADS;
+    const size_t i = i0 + (size_t)k * stride;
     Fr fe, fo, ge, go;
     // ---- f slice
     sc_stage_wait<1>();
@@ -599,21 +603,36 @@ size_t sc_max_ctas(size_t nf, size_t ng) {
 }
 
 // Vectors of more than 2^sc_staged_min_log() pairs go through k_sc_staged (GM_SC_STAGED_MIN_LOG=64 switches it off).
+// Measured at 2^24 (profiles/r02_sumcheck_staged_ab.txt): whole sumcheck 1.877 ms without it, 1.749 / 1.731 / 1.722 ms
+// with the threshold at 2^19 / 2^17 / 2^15 pairs.
 static int sc_staged_min_log() {
   static const int v = [] {
     const char* e = getenv("GM_SC_STAGED_MIN_LOG");
-    return e ? atoi(e) : 19;
+    return e ? atoi(e) : 15;
   }();
   return v;
 }
+static int sc_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  return sms;
+}
 template <bool TW, bool FOLD>
 static int sc_staged_launch(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, size_t ng, const Fr& rf, const Fr& rg, Fr* d_f_out,
-                            Fr* d_g_out, size_t npairs, const Fr& twist, const PowTable& tab, int kpt, unsigned grid, Fr* d_partials,
-                            unsigned int* d_ticket, Fr* d_out, ScMailbox* mb, uint32_t seq) {
+                            Fr* d_g_out, size_t npairs, const Fr& twist, const PowTable& tab, Fr* d_partials, unsigned int* d_ticket,
+                            Fr* d_out, ScMailbox* mb, uint32_t seq) {
   constexpr size_t shmem = (size_t)(SC_THREADS / 32) * SC_RING * ScStage<FOLD ? 4 : 2>::BYTES;
   // per device and cheap next to a round of this size: set on every launch rather than cached per process
   GM_CUDA(cudaFuncSetAttribute(k_sc_staged<TW, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-  LAUNCH_LN(ctx, (k_sc_staged<TW, FOLD>), grid, SC_THREADS, shmem, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, twist, tab, kpt,
+  const size_t tiles = (npairs + SC_THREADS - 1) / SC_THREADS;
+  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)2 * sc_sm_count());   // <= 1024 = the partials' capacity
+  Fr step = Fr::one();
+  if (TW) {   // (twist^2)^(grid * SC_THREADS) from the table of (twist^2)^(2^k)
+    const uint64_t e = (uint64_t)grid * SC_THREADS;
+    for (int k = 0; k < 40 && (e >> k); k++)
+      if ((e >> k) & 1ull) step = step * tab.p[k];
+  }
+  LAUNCH_LN(ctx, (k_sc_staged<TW, FOLD>), grid, SC_THREADS, shmem, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, twist, tab, step,
             d_partials, d_ticket, d_out, mb, seq);
   GM_CUDA(cudaGetLastError());
   return GM_OK;
@@ -628,13 +647,13 @@ int sc_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g, siz
   if (use_twist) {
     PowTable tab = make_pow_table(twist, npairs);
     if (staged)
-      return sc_staged_launch<true, false>(ctx, d_f, nf, d_g, ng, twist, twist, nullptr, nullptr, npairs, twist, tab, kpt, grid, d_partials,
+      return sc_staged_launch<true, false>(ctx, d_f, nf, d_g, ng, twist, twist, nullptr, nullptr, npairs, twist, tab, d_partials,
                                            d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out, mb, seq);
   } else {
     PowTable tab;  // unused
     if (staged)
-      return sc_staged_launch<false, false>(ctx, d_f, nf, d_g, ng, twist, twist, nullptr, nullptr, npairs, twist, tab, kpt, grid, d_partials,
+      return sc_staged_launch<false, false>(ctx, d_f, nf, d_g, ng, twist, twist, nullptr, nullptr, npairs, twist, tab, d_partials,
                                             d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, twist, tab, kpt, d_partials, d_ticket, d_out, mb, seq);
   }
@@ -653,14 +672,14 @@ int sc_fold_message_dev(const Lane& ctx, const Fr* d_f, size_t nf, const Fr* d_g
   if (use_twist) {
     PowTable tab = make_pow_table(new_twist, npairs);
     if (staged)
-      return sc_staged_launch<true, true>(ctx, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, new_twist, tab, kpt, grid, d_partials,
+      return sc_staged_launch<true, true>(ctx, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, new_twist, tab, d_partials,
                                           d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_fold_message<true>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out, mb, seq);
   } else {
     PowTable tab;
     if (staged)
-      return sc_staged_launch<false, true>(ctx, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, new_twist, tab, kpt, grid, d_partials,
+      return sc_staged_launch<false, true>(ctx, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, npairs, new_twist, tab, d_partials,
                                            d_ticket, d_out, mb, seq);
     LAUNCH_LN(ctx, k_sc_fold_message<false>, grid, SC_THREADS, 0, d_f, nf, d_g, ng, rf, rg, d_f_out, d_g_out, new_twist, tab, kpt,
            d_partials, d_ticket, d_out, mb, seq);

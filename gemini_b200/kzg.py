@@ -12,6 +12,8 @@ passed as host sequences / limb arrays (uploaded once) or as resident :class:`De
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -31,6 +33,7 @@ R = field.R
 MIN_DEVICE_CHUNK = 1 << 27
 # batch_commit of resident polynomials on two lanes (see CommitterKey.batch_commit); False = the reference's sequential map
 CONCURRENT_COMMITS = True
+COMMIT_LANES = int(os.environ.get("GM_COMMIT_LANES", "4"))   # host threads / streams of CommitterKey.batch_commit
 
 
 def vanishing_polynomial(points: Sequence[int]) -> List[int]:
@@ -152,33 +155,40 @@ class CommitterKey:
         return CommitterKey(self.ctx, out)
 
     def batch_commit(self, polynomials) -> List[field.Point]:
-        """time.rs:98-107 (a sequential map of ``commit`` in the reference).  Resident polynomials are committed on TWO
-        lanes - this context and a helper context of the same GPU, each with its own stream and scratch arena, driven
-        from two host threads: an MSM ends in a latency-bound reduction tail that uses a handful of SMs (a quarter of
-        the call at 2^20 terms), and the tail of one commitment then overlaps the bucket accumulation of
-        the next.  Results are in input order and identical to the sequential map."""
+        """time.rs:98-107 (a sequential map of ``commit`` in the reference).  Resident polynomials are committed on
+        COMMIT_LANES lanes - this context and helper contexts of the same GPU, each with its own stream and scratch
+        arena, driven from one host thread each: an MSM ends in a latency-bound reduction tail that uses a handful of SMs
+        (a quarter of the call at 2^20 terms, 0.6 - 1.2 ms whatever the size below 2^15: DESIGN.md 4.2), and the tails of
+        the short commitments then overlap the bucket accumulation of the long ones.  The lanes pull from one queue,
+        longest polynomial first.  Results are in input order and identical to the sequential map."""
         polys = list(polynomials)
         if len(polys) < 2 or not all(isinstance(p, DeviceFr) for p in polys) or not CONCURRENT_COMMITS:
             return [self.commit(p) for p in polys]
         import threading
 
-        helper = self._helper_context()
+        lanes = [self.ctx] + self._helper_contexts(min(COMMIT_LANES, len(polys)) - 1)
         self.ctx.synchronize()                  # the polynomials were produced on this context's stream
         order = sorted(range(len(polys)), key=lambda i: -polys[i].n)
         out: List = [None] * len(polys)
         errors: List = []
-        lanes = (self.ctx, helper)
+        lock = threading.Lock()
+        cursor = [0]
 
         def work(lane: int) -> None:
             try:
                 ctx = lanes[lane]
-                for i in order[lane::2]:
-                    v = polys[i]
-                    out[i] = field.jacobian_to_affine(ctx.msm_dev(self.srs, v.ptr, v.n)) if v.n else None
+                while True:
+                    with lock:
+                        k = cursor[0]
+                        cursor[0] += 1
+                    if k >= len(order):
+                        return
+                    v = polys[order[k]]
+                    out[order[k]] = field.jacobian_to_affine(ctx.msm_dev(self.srs, v.ptr, v.n)) if v.n else None
             except Exception as exc:  # pragma: no cover
                 errors.append(exc)
 
-        threads = [threading.Thread(target=work, args=(k,)) for k in (0, 1)]
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(lanes))]
         for t in threads:
             t.start()
         for t in threads:
@@ -187,12 +197,12 @@ class CommitterKey:
             raise errors[0]
         return out
 
-    def _helper_context(self) -> Context:
-        h = getattr(self, "_helper", None)
-        if h is None or not h._h:
-            h = Context(self.ctx.device_id)
-            self._helper = h
-        return h
+    def _helper_contexts(self, count: int) -> List[Context]:
+        hs = [h for h in getattr(self, "_helpers", []) if h._h]
+        while len(hs) < count:
+            hs.append(Context(self.ctx.device_id))
+        self._helpers = hs
+        return hs[:count]
 
     def open(self, polynomial, evaluation_point: int) -> Tuple[int, field.Point]:
         """time.rs:112-131: (evaluation, proof).  The reference runs a serial Horner recurrence and builds the quotient
