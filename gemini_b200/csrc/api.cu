@@ -41,6 +41,9 @@ using namespace gm;
 struct ResultSlot {  // device-side result area of a context
   XYZZ acc;
   Jacobian out;
+  Affine sum_point;      // constant-scalar path: sum of the bases as one affine point
+  uint32_t one[8];       // the scalar 1 as a plain integer
+  uint32_t flag[4];
 };
 
 struct gm_msm_stream {
@@ -411,7 +414,11 @@ int gm_srs_free(gm_srs* srs) {
 
 // ---- MSM ---------------------------------------------------------------------------------
 static int ensure_result(gm_ctx* ctx, ResultSlot** slot) {
-  if (!ctx->d_result) GM_CUDA(cudaMalloc(&ctx->d_result, sizeof(ResultSlot)));
+  if (!ctx->d_result) {
+    GM_CUDA(cudaMalloc(&ctx->d_result, sizeof(ResultSlot)));
+    const uint32_t one[8] = {1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    GM_CUDA(cudaMemcpy(reinterpret_cast<ResultSlot*>(ctx->d_result)->one, one, sizeof(one), cudaMemcpyHostToDevice));
+  }
   *slot = reinterpret_cast<ResultSlot*>(ctx->d_result);
   return GM_OK;
 }
@@ -456,12 +463,43 @@ static int exchange_partials(gm_ctx* ctx, XYZZ* d_acc) {
   return msm_acc_set_sum_xyzz(ctx, d_all, (size_t)comm_world(ctx), sizeof(XYZZ), d_acc);
 }
 
+// Constant scalar vectors (the reference's dummy_r1cs witness, circuit.rs:349-365): sum_i s P_i = s * (sum_i P_i) - n
+// additions and one scalar multiplication instead of n * windows additions that all land in one bucket per window.
+// Both steps run through the ordinary pipeline: the sum of the bases is the MSM with every scalar = 1 (scalar stride 0
+// over a device constant), its result becomes a one-point base, and s * S is the MSM of that point with scalars[0].
+// GM_CONST_SCALAR_MIN: smallest n that is tested for it (0 = never); the test costs one 4-byte round trip.
+static size_t const_scalar_min() {
+  static const size_t v = [] {
+    const char* e = getenv("GM_CONST_SCALAR_MIN");
+    return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)1 << 16);
+  }();
+  return v;
+}
+
 static int msm_common(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, uint64_t out[18],
                       bool sharded = false) {
   ResultSlot* slot;
   GM_TRY(ensure_result(ctx, &slot));
+  bool constant = false;
+  if (const_scalar_min() && n >= const_scalar_min())
+    GM_TRY(msm_scalars_all_equal(ctx, d_scalars, n, ctx->msm.scalar_stride, slot->flag, reinterpret_cast<uint32_t*>(ctx->pinned) + 64, &constant));
   GM_TRY(msm_acc_reset(ctx, &slot->acc));
-  GM_TRY(msm_accumulate(ctx, bases, base_offset, d_scalars, n, bigint, &slot->acc));
+  if (constant) {
+    const size_t stride = ctx->msm.scalar_stride;
+    ctx->msm.scalar_stride = 0;                                   // every term reads the same scalar: 1
+    int rc = msm_accumulate(ctx, bases, base_offset, slot->one, n, /*bigint=*/true, &slot->acc);
+    ctx->msm.scalar_stride = 1;
+    if (rc == GM_OK) rc = msm_acc_to_affine(ctx, &slot->acc, &slot->sum_point);
+    if (rc == GM_OK) rc = msm_acc_reset(ctx, &slot->acc);
+    MsmBases one_point;
+    one_point.points = &slot->sum_point;
+    one_point.n = 1;
+    if (rc == GM_OK) rc = msm_accumulate(ctx, one_point, 0, d_scalars, 1, bigint, &slot->acc);
+    ctx->msm.scalar_stride = stride;
+    GM_TRY(rc);
+  } else {
+    GM_TRY(msm_accumulate(ctx, bases, base_offset, d_scalars, n, bigint, &slot->acc));
+  }
   if (sharded) GM_TRY(exchange_partials(ctx, &slot->acc));
   GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
   GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));

@@ -41,6 +41,9 @@ void msm_describe_plan(size_t n, bool with_table, int sm_count, int out[8]);
 int msm_acc_reset(gm_ctx* ctx, XYZZ* d_acc);
 int msm_acc_add_jacobians(gm_ctx* ctx, const Jacobian* d_in, size_t k, XYZZ* d_acc);
 int msm_acc_normalize(gm_ctx* ctx, const XYZZ* d_acc, Jacobian* d_out);
+// constant scalar vectors (msm_reduce.cu): host-synchronising test, and the accumulator as one affine base point
+int msm_scalars_all_equal(gm_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t stride, uint32_t* d_flag, uint32_t* pinned_flag, bool* out);
+int msm_acc_to_affine(gm_ctx* ctx, const XYZZ* d_acc, Affine* d_out);
 // *d_acc = sum of k XYZZ points laid out `stride_bytes` apart (the gathered per-rank partials)
 int msm_acc_set_sum_xyzz(gm_ctx* ctx, const void* d_in, size_t k, size_t stride_bytes, XYZZ* d_acc);
 

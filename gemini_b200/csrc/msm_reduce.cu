@@ -204,6 +204,59 @@ __global__ void k_sum_xyzz(const uint8_t* __restrict__ in, uint32_t k, uint32_t 
   store_rw(acc, a);
 }
 
+// ---- constant scalar vectors -----------------------------------------------------------------------------------
+// sum_i s P_i = s * sum_i P_i.  The reference's own example inputs are constant vectors (circuit.rs:349-365 dummy_r1cs: every
+// witness entry is the same field element; examples/snark.rs:62-65), for which arkworks' Pippenger - and ours - puts all n
+// points of a window into ONE bucket: n * windows additions where n + one scalar multiplication do.  gm_msm_g1_dev asks
+// k_scalars_equal first (a strided sample, then - only if the sample is constant - every scalar).
+// flag (pre-set to 1) is cleared when some scalar differs from scalars[0]; term i is read at i * stride * 8 words
+__global__ void k_scalars_equal(const uint32_t* __restrict__ scalars, size_t n, size_t stride, size_t step, uint32_t* flag) {
+  const uint4* p0 = reinterpret_cast<const uint4*>(scalars);
+  const uint4 a0 = __ldg(p0), a1 = __ldg(p0 + 1);
+  bool same = true;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * step; i < n; i += (size_t)gridDim.x * blockDim.x * step) {
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + i * stride * 8);
+    const uint4 b0 = __ldg(p), b1 = __ldg(p + 1);
+    same = same && a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+  }
+  if (!same) *flag = 0u;
+}
+__global__ void k_acc_to_affine(const XYZZ* __restrict__ acc, Affine* __restrict__ out) {
+  if (threadIdx.x || blockIdx.x) return;
+  const Jacobian j = xyzz_to_jacobian_normalized(load_rw(acc));
+  Affine a;
+  if (j.z.is_zero()) { a.x = Fq::zero(); a.y = Fq::zero(); }   // (0, 0) = identity
+  else { a.x = j.x; a.y = j.y; }
+  store_rw(out, a);
+}
+
+// host-synchronising: *out = every one of the n scalars (stride apart) equals the first one.  d_flag: one device word.
+int msm_scalars_all_equal(gm_ctx* ctx, const uint32_t* d_scalars, size_t n, size_t stride, uint32_t* d_flag, uint32_t* pinned_flag, bool* out) {
+  *out = false;
+  if (n < 2) { *out = true; return GM_OK; }
+  // 1. a sample of <= 4096 scalars spread over the vector: non-constant vectors (every real witness) stop here
+  for (int pass = 0; pass < 2; pass++) {
+    const size_t step = pass == 0 ? std::max<size_t>(1, n / 4096) : 1;
+    if (pass == 1 && n / 4096 <= 1) break;             // the sample already was the whole vector
+    const size_t items = (n + step - 1) / step;
+    const unsigned grid = (unsigned)std::min<size_t>((items + 255) / 256, (size_t)ctx->sm_count * 8);
+    *pinned_flag = 1u;
+    GM_CUDA(cudaMemcpyAsync(d_flag, pinned_flag, 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_scalars_equal, grid, 256, 0, d_scalars, n, stride, step, d_flag);
+    GM_CUDA(cudaMemcpyAsync(pinned_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*pinned_flag == 0u) return GM_OK;
+  }
+  *out = true;
+  return GM_OK;
+}
+
+int msm_acc_to_affine(gm_ctx* ctx, const XYZZ* d_acc, Affine* d_out) {
+  LAUNCH(ctx, k_acc_to_affine, 1, 32, 0, d_acc, d_out);
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
 // Phase B: bucket reduction (running sums, weights, windows) and *d_acc += result.  `valid[gb] != 0` marks the
 // buckets that hold a point (per-call counts, or the persistent live flags of a stream).
 int msm_reduce(gm_ctx* ctx, const MsmPlan& P, const XYZZ* buckets, const uint32_t* valid, XYZZ* d_acc) {

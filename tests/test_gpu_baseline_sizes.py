@@ -173,3 +173,30 @@ def test_fold_2_24_against_c_port(ctx, clib):  # noqa: F811
     assert np.array_equal(got, want)
     ctx.dev_free(d_f)
     ctx.dev_free(d_o)
+
+
+@pytest.mark.parametrize("odd_one_out", [None, 0, 12345, (1 << 17) + 4])
+def test_msm_constant_scalar_path_and_its_near_misses(ctx, odd_one_out):
+    """gm_msm_g1_dev computes a CONSTANT scalar vector as s * (sum of the bases) (api.cu: msm_common).  The vector is
+    recognised by a strided sample followed by a full comparison: a vector that is constant except for one entry - at the
+    reference position 0, at an index the sample skips, at the very end - must take the general path and still be right."""
+    n = (1 << 17) + 5
+    srs = ctx.srs_generate(n, first_multiple=1)
+    srs.precompute()
+    s = fr_random_limbs(2, 99)
+    val = lambda row: (int(row[0]) | int(row[1]) << 64 | int(row[2]) << 128 | int(row[3]) << 192) * RINV % R
+    scal = np.ascontiguousarray(np.broadcast_to(s[:1], (n, 4))).copy()
+    tot = val(s[0]) * (n * (n + 1) // 2)
+    if odd_one_out is not None:
+        scal[odd_one_out] = s[1]
+        tot += (val(s[1]) - val(s[0])) * (odd_one_out + 1)
+    want = o.g1_mul(o.G1_GEN, tot % R)
+    assert field.jacobian_to_affine(ctx.msm(srs, scal)) == want
+    d = ctx.dev_alloc(n * 32)
+    ctx.dev_upload(d, scal)
+    assert field.jacobian_to_affine(ctx.msm_dev(srs, d, n)) == want
+    # zero everywhere: the sum of the bases times 0
+    scal[:] = 0
+    assert field.jacobian_to_affine(ctx.msm(srs, scal)) is None
+    ctx.dev_free(d)
+    srs.free()
