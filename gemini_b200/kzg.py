@@ -270,8 +270,13 @@ class CommitterKeyStream:
         assert m <= len(self), "polynomial longer than the SRS"
         be = le.reversed()
         chunk = max(max_msm_buffer, MIN_DEVICE_CHUNK, 1)
-        st = _DeviceStream(self.ctx, self.srs_be, min(chunk, m))
         off = len(self) - m
+        if m <= chunk:
+            # one piece: the one-shot entry point (its own plan for m terms, constant-vector test included)
+            out = field.jacobian_to_affine(self.ctx.msm_dev(self.srs_be, be.ptr, m, base_offset=off))
+            be.free()
+            return out
+        st = _DeviceStream(self.ctx, self.srs_be, min(chunk, m))
         for s0 in range(0, m, chunk):
             st.push_dev(off + s0, be.ptr + 32 * s0, min(chunk, m - s0))
         out = st.finalize()
