@@ -88,6 +88,53 @@ def _divide_by_points(poly: DeviceFr, points: Sequence[int]):
     return q, rem[::-1]
 
 
+def _msm_on_lanes(owner, srs: Srs, jobs) -> List[field.Point]:
+    """jobs: (device pointer of the scalars, n, base_offset) per MSM against ``srs``; results in job order.  The MSMs run
+    on COMMIT_LANES lanes - the owner's context and helper contexts of the same GPU (kept on ``owner``), each with its own
+    stream and scratch arena and one host thread - that pull from one queue, longest job first."""
+    import threading
+
+    ctx = owner.ctx
+    lanes = [ctx] + owner._helper_contexts(min(COMMIT_LANES, len(jobs)) - 1)
+    ctx.synchronize()                       # the scalars were produced on this context's stream
+    order = sorted(range(len(jobs)), key=lambda i: -jobs[i][1])
+    out: List = [None] * len(jobs)
+    errors: List = []
+    lock = threading.Lock()
+    cursor = [0]
+
+    def work(lane: int) -> None:
+        try:
+            c = lanes[lane]
+            while True:
+                with lock:
+                    k = cursor[0]
+                    cursor[0] += 1
+                if k >= len(order):
+                    return
+                ptr, n, off = jobs[order[k]]
+                out[order[k]] = field.jacobian_to_affine(c.msm_dev(srs, ptr, n, base_offset=off)) if n else None
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(lanes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+def _helper_contexts_of(owner, count: int) -> List[Context]:
+    hs = [h for h in getattr(owner, "_helpers", []) if h._h]
+    while len(hs) < count:
+        hs.append(Context(owner.ctx.device_id))
+    owner._helpers = hs
+    return hs[:count]
+
+
 class CommitterKey:
     """``CommitterKey<E>``: ``powers_of_g`` resident on the device."""
 
@@ -164,45 +211,10 @@ class CommitterKey:
         polys = list(polynomials)
         if len(polys) < 2 or not all(isinstance(p, DeviceFr) for p in polys) or not CONCURRENT_COMMITS:
             return [self.commit(p) for p in polys]
-        import threading
-
-        lanes = [self.ctx] + self._helper_contexts(min(COMMIT_LANES, len(polys)) - 1)
-        self.ctx.synchronize()                  # the polynomials were produced on this context's stream
-        order = sorted(range(len(polys)), key=lambda i: -polys[i].n)
-        out: List = [None] * len(polys)
-        errors: List = []
-        lock = threading.Lock()
-        cursor = [0]
-
-        def work(lane: int) -> None:
-            try:
-                ctx = lanes[lane]
-                while True:
-                    with lock:
-                        k = cursor[0]
-                        cursor[0] += 1
-                    if k >= len(order):
-                        return
-                    v = polys[order[k]]
-                    out[order[k]] = field.jacobian_to_affine(ctx.msm_dev(self.srs, v.ptr, v.n)) if v.n else None
-            except Exception as exc:  # pragma: no cover
-                errors.append(exc)
-
-        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(lanes))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        return out
+        return _msm_on_lanes(self, self.srs, [(p.ptr, p.n, 0) for p in polys])
 
     def _helper_contexts(self, count: int) -> List[Context]:
-        hs = [h for h in getattr(self, "_helpers", []) if h._h]
-        while len(hs) < count:
-            hs.append(Context(self.ctx.device_id))
-        self._helpers = hs
-        return hs[:count]
+        return _helper_contexts_of(self, count)
 
     def open(self, polynomial, evaluation_point: int) -> Tuple[int, field.Point]:
         """time.rs:112-131: (evaluation, proof).  The reference runs a serial Horner recurrence and builds the quotient
@@ -321,7 +333,18 @@ class CommitterKeyStream:
                 return []
             levels = self._le(polynomials_be).fold_chain([c % R for c in challenges])
         n_levels = max(len(levels), 1)
+        chunk = max(max_msm_buffer // n_levels, MIN_DEVICE_CHUNK, 1)
+        if CONCURRENT_COMMITS and len(levels) >= 2 and all(0 < lvl.n <= chunk for lvl in levels):
+            # every level is one resident piece: the independent MSMs share the GPU on several lanes (batch_commit's scheme)
+            be = [lvl.reversed() for lvl in levels]
+            out = _msm_on_lanes(self, self.srs_be, [(v.ptr, v.n, len(self) - v.n) for v in be])
+            for v in be:
+                v.free()
+            return out
         return [self._commit_le(lvl, max_msm_buffer // n_levels) for lvl in levels]
+
+    def _helper_contexts(self, count: int) -> List[Context]:
+        return _helper_contexts_of(self, count)
 
     def open_folding(self, polynomials, points: Sequence[int], etas: Sequence[int], max_msm_buffer: int = 0):
         """space.rs:229-285 -> (remainders per level, evaluation proof).  ``polynomials``: tensorcheck.FoldedPolynomialTree.
