@@ -6,6 +6,7 @@
 #include "../../gemini_b200/csrc/g1_affine.cuh"
 #include "../../tools/fq_f64.cuh"
 #include "../../tools/fq_karatsuba.cuh"
+#include "../../tools/fq_f64v2.cuh"
 #include "../../gemini_b200/csrc/fp_inv_fast.cuh"
 #include <string.h>
 using namespace gm;
@@ -27,12 +28,13 @@ template <class F> static void f_redc(F& z, const F& x, const F&) { z = x.from_m
 template <class F> static void f_tom(F& z, const F& x, const F&) { z = x.to_mont(); }
 template <class F> static void f_sqr(F& z, const F& x, const F&) { z = x.sqr(); }
 static void f_mul_f64(Fq& z, const Fq& x, const Fq& y) { f64::fq_mul_f64(z.v, x.v, y.v); }
+static void f_mul_f64v2(Fq& z, const Fq& x, const Fq& y) { f64v2::fq_mul(z.v, x.v, y.v); }
 template <class F> static void f_mul_k(F& z, const F& x, const F& y) { mont_mul_karatsuba<typename F::Params>(z.v, x.v, y.v); }
 template <class F> static void f_mul_k2(F& z, const F& x, const F& y) { mont_mul_karatsuba<typename F::Params, 2>(z.v, x.v, y.v); }
 
 extern "C" {
 void hc_fq(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
-  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64, f_inv_fast<Fq>, f_mul_k<Fq>, f_mul_k2<Fq>};
+  void (*ops[])(Fq&, const Fq&, const Fq&) = {f_mul<Fq>, f_add<Fq>, f_sub<Fq>, f_inv<Fq>, f_redc<Fq>, f_tom<Fq>, f_sqr<Fq>, f_mul_f64, f_inv_fast<Fq>, f_mul_k<Fq>, f_mul_k2<Fq>, f_mul_f64v2};
   bin<Fq>(ops[op], a, b, r, n);
 }
 void hc_fr(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {

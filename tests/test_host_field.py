@@ -19,7 +19,7 @@ def hc():
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
     so = os.path.join(ROOT, "build", "libhostcheck.so")
     src = os.path.join(ROOT, "tests", "csrc", "host_check.cpp")
-    subprocess.run(["g++", "-O2", "-x", "c++", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
+    subprocess.run(["g++", "-O2", "-frounding-math", "-x", "c++", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
     return C.CDLL(so)
 
 
@@ -232,3 +232,21 @@ def test_karatsuba_montgomery_product(hc, name, p, n):
     for op in (9, 10):   # one and two Karatsuba levels
         fn(op, P(a), P(b), P(r), len(A))
         assert unpack(r) == [x * y * Ri % p for x, y in zip(A, B)], op
+
+
+def test_fq_product_on_the_fp64_pipe_48_bit_limbs(hc):
+    """tools/fq_f64v2.cuh (experiment): the Fq Montgomery product from 48-bit limbs in doubles, every partial product split
+    exactly by two fused multiply-adds (one rounding toward zero).  Same limbs in, same limbs out as mont_mul."""
+    p, n = o.Q, 12
+    rng = random.Random(48)
+    Rm = (1 << 384) % p
+    Ri = pow(Rm, -1, p)
+    lim = (1 << 48) - 1
+    edge = [0, 1, p - 1, p - 2, Rm, (p - 1) // 2, (1 << 381) % p, (1 << 380), lim, lim << 48, (lim << 336) % p,
+            sum(lim << (48 * k) for k in range(7)), sum(1 << (48 * k) for k in range(8)) % p, (1 << 192) - 1, 1 << 192]
+    A = [x for x in edge for _ in edge] + [rng.randrange(p) for _ in range(4000)]
+    B = [y for _ in edge for y in edge] + [rng.randrange(p) for _ in range(4000)]
+    a, b = pack(A, n), pack(B, n)
+    r = np.zeros_like(a)
+    hc.hc_fq(11, P(a), P(b), P(r), len(A))
+    assert unpack(r) == [x * y * Ri % p for x, y in zip(A, B)]
