@@ -81,12 +81,24 @@ __device__ __forceinline__ Fr warp_sum_fr(Fr v) {
   return v;
 }
 
-// CTA sum of (a, b); then the last CTA to arrive sums all CTA partials into out[0..1].
-// mb != nullptr: the message also goes straight into the prover's pinned mailbox (msg, then msg_seq = seq), where the
-// host is spinning for it - no D2H copy and no stream synchronisation on the round's critical path (measured at 2^24:
-// 2.37 -> 1.98 ms for the 24 rounds).  A persistent single-CTA kernel for the last rounds, fed challenges through the
+// (a, b) leave the device: result slot in HBM and, when the prover has one, its pinned mailbox (msg, then msg_seq = seq),
+// where the host is spinning for it - no D2H copy and no stream synchronisation on the round's critical path (measured at
+// 2^24: 2.37 -> 1.98 ms for the 24 rounds).  A persistent single-CTA kernel for the last rounds, fed challenges through the
 // same mailbox, was measured on top of this and did not pay (2.03 ms: one CTA is slower than a small grid, and the
 // launch it saves is all that was left): removed.
+__device__ __forceinline__ void sc_publish(const Fr& x, const Fr& y, Fr* out, ScMailbox* mb, uint32_t seq) {
+  store_fr(out, x);
+  store_fr(out + 1, y);
+  if (mb != nullptr) {
+    volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(&mb->msg[0]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { dst[j] = x.v[j]; dst[8 + j] = y.v[j]; }
+    __threadfence_system();
+    mb->msg_seq = seq;
+  }
+}
+
+// CTA sum of (a, b); then the last CTA to arrive sums all CTA partials and publishes the message.
 __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, unsigned int* ticket, Fr* out, ScMailbox* mb = nullptr,
                                                       uint32_t seq = 0) {
   __shared__ Fr sh[2 * (SC_THREADS / 32)];
@@ -102,13 +114,20 @@ __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, 
     x = warp_sum_fr(x);
     y = warp_sum_fr(y);
     if (lane == 0) {
-      store_fr(partials + 2 * blockIdx.x, x);
-      store_fr(partials + 2 * blockIdx.x + 1, y);
-      __threadfence();
-      unsigned int tk = atomicAdd(ticket, 1u);
-      is_last = (tk == gridDim.x - 1);
+      if (gridDim.x == 1) {
+        // the last rounds of every sumcheck run on one CTA: its sum IS the message - no partials, no fence, no ticket
+        // (they are half of the dependency chain of a round that short)
+        sc_publish(x, y, out, mb, seq);
+      } else {
+        store_fr(partials + 2 * blockIdx.x, x);
+        store_fr(partials + 2 * blockIdx.x + 1, y);
+        __threadfence();
+        unsigned int tk = atomicAdd(ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+      }
     }
   }
+  if (gridDim.x == 1) return;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
@@ -128,16 +147,8 @@ __device__ __forceinline__ void sc_reduce_and_publish(Fr a, Fr b, Fr* partials, 
     x = warp_sum_fr(x);
     y = warp_sum_fr(y);
     if (lane == 0) {
-      store_fr(out, x);
-      store_fr(out + 1, y);
       *ticket = 0;  // re-arm for the next round
-      if (mb != nullptr) {
-        volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(&mb->msg[0]);
-#pragma unroll
-        for (int j = 0; j < 8; j++) { dst[j] = x.v[j]; dst[8 + j] = y.v[j]; }
-        __threadfence_system();
-        mb->msg_seq = seq;
-      }
+      sc_publish(x, y, out, mb, seq);
     }
   }
 }
