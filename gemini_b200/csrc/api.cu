@@ -463,6 +463,18 @@ static int exchange_partials(gm_ctx* ctx, XYZZ* d_acc) {
   return msm_acc_set_sum_xyzz(ctx, d_all, (size_t)comm_world(ctx), sizeof(XYZZ), d_acc);
 }
 
+// the accumulator of the running call -> (exchange between ranks) -> normalised 144-byte result on the host
+static int msm_finish(gm_ctx* ctx, ResultSlot* slot, size_t n, uint64_t out[18], bool sharded) {
+  if (sharded) GM_TRY(exchange_partials(ctx, &slot->acc));
+  GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
+  GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  GM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->pinned, sizeof(Jacobian));
+  if (n) record_phases(ctx); else cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+  return GM_OK;
+}
+
 // Constant scalar vectors (the reference's dummy_r1cs witness, circuit.rs:349-365): sum_i s P_i = s * (sum_i P_i) - n
 // additions and one scalar multiplication instead of n * windows additions that all land in one bucket per window.
 // Both steps run through the ordinary pipeline: the sum of the bases is the MSM with every scalar = 1 (scalar stride 0
@@ -500,14 +512,7 @@ static int msm_common(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, co
   } else {
     GM_TRY(msm_accumulate(ctx, bases, base_offset, d_scalars, n, bigint, &slot->acc));
   }
-  if (sharded) GM_TRY(exchange_partials(ctx, &slot->acc));
-  GM_TRY(msm_acc_normalize(ctx, &slot->acc, &slot->out));
-  GM_CUDA(cudaMemcpyAsync(ctx->pinned, &slot->out, sizeof(Jacobian), cudaMemcpyDeviceToHost, ctx->stream));
-  GM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-  GM_CUDA(cudaStreamSynchronize(ctx->stream));
-  memcpy(out, ctx->pinned, sizeof(Jacobian));
-  if (n) record_phases(ctx); else cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
-  return GM_OK;
+  return msm_finish(ctx, slot, n, out, sharded);
 }
 
 int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
@@ -540,6 +545,21 @@ static int msm_host(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const ui
     GM_TRY(ctx->msm.scalars.reserve(std::max<size_t>(n, 1) * 32));
     if (n) GM_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return msm_common(ctx, bases_of_srs(srs, base_offset, n), base_offset, ctx->msm.scalars.as<uint32_t>(), n, bigint, out, sharded);
+  }
+  // PINNED host memory: one-shot pipeline fed piecewise - the digits of a piece are extracted while the next piece is on
+  // the bus, and nothing else waits for the transfer (measured at 2^24: 77.3 -> see profiles/r02_summary.md)
+  if (!getenv("GM_E2E_CHUNKS")) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      ResultSlot* slot;
+      GM_TRY(ensure_result(ctx, &slot));
+      GM_TRY(msm_acc_reset(ctx, &slot->acc));
+      const int rc = msm_accumulate_pinned(ctx, bases_of_srs(srs, base_offset, n), base_offset, scalars, n, bigint, /*pieces=*/8, &slot->acc);
+      if (rc == GM_OK) return msm_finish(ctx, slot, n, out, sharded);
+      if (rc != GM_ERR_ARG) return rc;          // GM_ERR_ARG: several passes needed - the streamed path below handles any size
+    } else {
+      cudaGetLastError();
+    }
   }
   if (!ctx->host_stream) GM_TRY(stream_create(ctx, nullptr, 0, /*holds_ctx_ref=*/false, &ctx->host_stream));
   gm_msm_stream* s = ctx->host_stream;

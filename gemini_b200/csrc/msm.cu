@@ -85,10 +85,11 @@ struct Meta {
 // 1. digits + histogram
 // -------------------------------------------------------------------------------------------
 // stride: term i reads scalar i * stride (1 = dense; world size when a vector is dealt out cyclically to the ranks)
-__global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t n, size_t stride, int is_bigint, int c, int W, int merged,
-                              uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
+// [i0, i1): the terms this launch converts (the whole vector, or the piece of a host vector that has just arrived)
+__global__ void k_digits_hist(const uint32_t* __restrict__ scalars, uint32_t i0, uint32_t i1, uint32_t n, size_t stride, int is_bigint, int c, int W,
+                              int merged, uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
+  const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < i1;
   Fr s = Fr::zero();
   if (live) {
     const uint4* p = reinterpret_cast<const uint4*>(scalars + (size_t)i * stride * 8);
@@ -691,8 +692,16 @@ static size_t affine_scratch_bytes(size_t refs, size_t M, int levels) {
 // Phase A: digits, counting sort, affine levels, work list, bucket accumulation.  Buckets go to `buckets`; when `live` is
 // given the buckets persist across calls (streamed MSM) and are updated in place, otherwise they are (re)written and the
 // per-call counts (ctx->msm.counts) tell which ones are valid.
+// `feed` (optional): the scalars are still in PINNED host memory.  They are copied in `feed->pieces` pieces on the context's
+// copy stream, and the digits / histogram kernel of a piece starts as soon as that piece has landed: the conversion of the
+// scalars and all the allocation-free set-up of the call hide behind the PCIe transfer, and the rest of the pipeline
+// (scan, scatter, levels, ...) starts the moment the last piece is in.
+struct HostFeed {
+  const uint64_t* host = nullptr;
+  int pieces = 1;
+};
 static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint,
-                               const MsmPlan& P, XYZZ* buckets, uint32_t* live) {
+                               const MsmPlan& P, XYZZ* buckets, uint32_t* live, const HostFeed* feed = nullptr) {
   if (n == 0) return GM_OK;
   MsmScratch& S = ctx->msm;
   const bool merged = P.merged;
@@ -769,7 +778,23 @@ static int msm_sort_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offse
   const uint32_t* counts = S.counts.as<uint32_t>();
   const uint32_t* starts = S.starts.as<uint32_t>();
   GM_CUDA(cudaEventRecord(ctx->ev[2], st));
-  LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, n32, S.scalar_stride, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
+  if (feed != nullptr && feed->pieces > 1) {
+    // the copy stream starts after everything queued on the main stream so far (the previous call may still read d_scalars)
+    GM_CUDA(cudaEventRecord(ctx->ev_join, st));
+    GM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));
+    const size_t step = (((n + feed->pieces - 1) / feed->pieces) + 255) & ~(size_t)255;
+    for (size_t off = 0; off < n; off += step) {
+      const size_t m = std::min(step, n - off);
+      GM_CUDA(cudaMemcpyAsync(const_cast<uint32_t*>(d_scalars) + off * 8, feed->host + off * 4, m * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+      GM_CUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+      GM_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+      LAUNCH(ctx, k_digits_hist, (unsigned)((m + 255) / 256), 256, 0, d_scalars, (uint32_t)off, (uint32_t)(off + m), n32, S.scalar_stride, bigint ? 1 : 0, P.c,
+             P.W, merged ? 1 : 0, S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
+    }
+  } else {
+    LAUNCH(ctx, k_digits_hist, (n32 + 255) / 256, 256, 0, d_scalars, 0u, n32, n32, S.scalar_stride, bigint ? 1 : 0, P.c, P.W, merged ? 1 : 0,
+           S.digits.as<uint32_t>(), S.counts.as<uint32_t>());
+  }
   LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, counts, S.starts.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32, pad);
   LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, S.scan_tmp.as<uint32_t>(), (uint32_t)ntiles);
   LAUNCH(ctx, k_scan_add, (unsigned)((M + 255) / 256), 256, 0, S.starts.as<uint32_t>(), S.cursor.as<uint32_t>(), S.scan_tmp.as<uint32_t>(), M32);
@@ -862,6 +887,23 @@ int msm_accumulate(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uin
     GM_TRY(msm_reduce(ctx, P, ctx->msm.buckets.as<XYZZ>(), ctx->msm.counts.as<uint32_t>(), d_acc));
   }
   return GM_OK;
+}
+
+// *d_acc += sum_i scalars[i] * bases[i] with the scalars in PINNED host memory (see HostFeed); GM_ERR_ARG when the input
+// needs several passes (the caller then falls back to the streamed path)
+int msm_accumulate_pinned(gm_ctx* ctx, const MsmBases& B, size_t base_offset, const uint64_t* h_scalars, size_t n, bool bigint, int pieces,
+                          XYZZ* d_acc) {
+  if (n == 0) return GM_OK;
+  if (n > msm_pass_size(ctx, B, n) || ctx->msm.scalar_stride != 1) return GM_ERR_ARG;
+  GM_TRY(ctx->msm.scalars.reserve(n * 32));
+  const MsmPlan P = plan_for(B, n);
+  const size_t M = (size_t)(P.merged ? 1 : P.W) * P.nb;
+  GM_TRY(ctx->msm.buckets.reserve(M * sizeof(XYZZ)));
+  HostFeed feed;
+  feed.host = h_scalars;
+  feed.pieces = pieces;
+  GM_TRY(msm_sort_accumulate(ctx, B, base_offset, ctx->msm.scalars.as<uint32_t>(), n, bigint, P, ctx->msm.buckets.as<XYZZ>(), nullptr, &feed));
+  return msm_reduce(ctx, P, ctx->msm.buckets.as<XYZZ>(), ctx->msm.counts.as<uint32_t>(), d_acc);
 }
 
 // ---- streamed MSM with device-resident buckets: chunks only sort + accumulate, the reduction runs once ----

@@ -27,6 +27,10 @@ struct MsmBases {
 
 // *d_acc (XYZZ, device) += sum_i scalars[i] * bases[i]; asynchronous on ctx->stream
 int msm_accumulate(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint32_t* d_scalars, size_t n, bool bigint, XYZZ* d_acc);
+// the same with the scalars in PINNED host memory: copied in `pieces` pieces, each converted to digits as it lands
+// (GM_ERR_ARG: the input needs several passes - use the streamed path)
+int msm_accumulate_pinned(gm_ctx* ctx, const MsmBases& bases, size_t base_offset, const uint64_t* h_scalars, size_t n, bool bigint, int pieces,
+                          XYZZ* d_acc);
 // streamed MSM: buckets (msm_plan_buckets(P) XYZZ) and live flags (same count of u32, zero-initialised) persist
 // across pushes; every push must use the same plan and the same kind of bases
 MsmPlan msm_stream_plan(const MsmBases& bases, size_t chunk_cap);

@@ -73,10 +73,17 @@ def test_msm_2_24_closed_form(ctx, with_table):
     assert field.jacobian_to_affine(got) == o.g1_mul(o.G1_GEN, tot)
     # the host entry point (H2D inside the call) returns the same bytes
     assert np.array_equal(ctx.msm(srs, limbs), got)
+    # ... and from PINNED host memory (msm_accumulate_pinned: the scalars arrive in pieces, digits extracted per piece),
+    # whole vector and a ragged prefix whose last piece is short
+    import torch
+
+    pinned = torch.from_numpy(limbs.view(np.int64).reshape(-1)).pin_memory()
+    assert np.array_equal(ctx.msm(srs, pinned), got)
     # a prefix that is not a power of two, against the same key
     m = (1 << 23) + 12345
     tot_m = weighted_sum(limbs[:m]) % R * RINV % R
     assert field.jacobian_to_affine(ctx.msm_dev(srs, d, m)) == o.g1_mul(o.G1_GEN, tot_m)
+    assert field.jacobian_to_affine(ctx.msm(srs, pinned, n=m)) == o.g1_mul(o.G1_GEN, tot_m)
     ctx.dev_free(d)
     srs.free()
 
