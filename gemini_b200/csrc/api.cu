@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 #include "fr.cuh"
@@ -32,6 +34,7 @@ void ctx_release(gm_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->bounce) cudaFreeHost(ctx->bounce);
   delete ctx;
 }
 }  // namespace gm
@@ -137,6 +140,9 @@ int gm_shutdown(gm_ctx* ctx) {
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     ctx->d_result = ctx->d_flush = nullptr;
+    if (ctx->bounce) cudaFreeHost(ctx->bounce);
+    ctx->bounce = nullptr;
+    ctx->bounce_bytes = 0;
     ctx->fr_red.release();
     ctx->fr_div.release();
   }
@@ -568,9 +574,40 @@ static int msm_host(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const ui
   GM_CUDA(cudaMemsetAsync(s->d_acc, 0, sizeof(XYZZ), ctx->stream));
   s->srs = srs;
   s->chunk_cap = step;
+  // PAGEABLE memory (what an arkworks &[Fr] is): the driver's own bounce copy runs at about 11 GB/s on one thread.  Each
+  // chunk is instead gathered into a pinned bounce buffer of the context by a few host threads and DMA'd from there -
+  // both behind the kernels of the previous chunk.  GM_HOST_COPY_THREADS = 0 leaves the copy to the driver.
+  static const int copy_threads = [] {
+    const char* e = getenv("GM_HOST_COPY_THREADS");
+    const int hw = (int)std::thread::hardware_concurrency();
+    return e ? atoi(e) : std::max(1, std::min(8, hw / 2));
+  }();
+  uint64_t* bounce = nullptr;
+  if (copy_threads > 0) {
+    if (ctx->bounce_bytes < step * 32) {
+      if (ctx->bounce) cudaFreeHost(ctx->bounce);
+      ctx->bounce = nullptr;
+      ctx->bounce_bytes = 0;
+      if (cudaHostAlloc(&ctx->bounce, step * 32, cudaHostAllocDefault) == cudaSuccess) ctx->bounce_bytes = step * 32;
+      else cudaGetLastError();               // no pinned memory to spare: the driver's path still works
+    }
+    bounce = reinterpret_cast<uint64_t*>(ctx->bounce);
+  }
   for (size_t off = 0; off < n; off += step) {
     const size_t m = std::min(step, n - off);
-    GM_TRY(gm_msm_stream_push(s, nullptr, 0, -1, base_offset + off, scalars + 4 * off, m, bigint ? 1 : 0));
+    const uint64_t* src = scalars + 4 * off;
+    if (bounce != nullptr) {
+      const size_t bytes = m * 32, per = (bytes / copy_threads + 4095) & ~(size_t)4095;
+      std::vector<std::thread> pool;
+      for (int t = 1; t < copy_threads; t++) {
+        const size_t b0 = std::min(bytes, (size_t)t * per), b1 = std::min(bytes, b0 + per);
+        if (b1 > b0) pool.emplace_back([=] { memcpy(reinterpret_cast<uint8_t*>(bounce) + b0, reinterpret_cast<const uint8_t*>(src) + b0, b1 - b0); });
+      }
+      memcpy(bounce, src, std::min(bytes, per));
+      for (auto& th : pool) th.join();
+      src = bounce;                          // gm_msm_stream_push returns once its copy has left the buffer
+    }
+    GM_TRY(gm_msm_stream_push(s, nullptr, 0, -1, base_offset + off, src, m, bigint ? 1 : 0));
   }
   const int rc = sharded ? gm_msm_stream_finalize_sharded(s, out) : gm_msm_stream_finalize(s, out);
   s->srs = nullptr;

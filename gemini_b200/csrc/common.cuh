@@ -114,6 +114,8 @@ struct gm_ctx {
   gm::MsmScratch msm;
   void* pinned = nullptr;  // pinned staging block: first 4 KB call results, then 64-byte message slots of sumcheck handles
   size_t pinned_bytes = 0;
+  void* bounce = nullptr;  // pinned bounce buffer of gm_msm_g1 for pageable host scalars (one chunk)
+  size_t bounce_bytes = 0;
   std::vector<uint32_t> free_slots;  // free 64-byte pinned slots (guarded by mu)
   void* d_result = nullptr;  // device result slot (accumulator + normalised output)
   void* d_flush = nullptr;   // 256 MB scratch written by gm_l2_flush
