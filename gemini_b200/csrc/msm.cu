@@ -211,7 +211,10 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ co
 // (they return the position the store depends on); 4 independent atomics per thread, and a two-pass variant that first groups
 // the references by the top 8 bits of the bucket index so that the scatter works inside an L2-sized window, were both
 // measured and gave 6.2 and 7.5 ms: the rate of returning L2 atomics is the bound, not latency or DRAM traffic.  A
-// register-free prefetch.global.L2 ring for the table gathers of the first affine level was measured too: 65.8 vs 55.1 ms.
+// register-free prefetch.global.L2 ring for the table gathers of the first affine level was measured too: 65.8 vs 55.1 ms,
+// and so was staging those gathers through shared memory with cp.async, four slots per thread in flight instead of one
+// (k_aff_prepare_staged, parity green): 58.9 vs 54.8 ms at 2^24, 4.52 vs 4.28 ms at 2^20.  More requests in flight make
+// the first level SLOWER: its 2 x 10^8 random 48-byte reads run at the rate the memory system takes them, not at a latency.
 __global__ void k_scatter(const uint32_t* __restrict__ digits, uint32_t n, int W, uint32_t nb, int merged, uint32_t ref_offset,
                           uint32_t ref_stride, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
