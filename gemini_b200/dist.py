@@ -252,3 +252,70 @@ class ShardedCommitterKey:
 
         q, _ = _divide_by_points(polynomial, eval_points)
         return self.commit(q)
+
+
+class ShardedCommitterKeyStream:
+    """``CommitterKeyStream`` (/root/reference/src/kzg/space.rs:59-297) over a :class:`ShardedCommitterKey`: the elastic
+    prover (snark::Proof::new_elastic, BASELINE config 5) on N GPUs.
+
+    The reference's stream key pairs the big-endian coefficient stream with ``Reverse(powers_of_g)`` so that the coefficient
+    of degree d meets g^(tau^d) (space.rs:22-55: the leading surplus bases are skipped).  The streams are resident
+    little-endian vectors here, so every stream commitment IS the time commitment of the little-endian vector, and the
+    cyclically dealt key serves it with one MSM of len / N terms per rank + one all-gather (``ShardedCommitterKey.commit``).
+    Everything else - quotients, remainders, the eta-combination of ``open_folding`` - is ``kzg.CommitterKeyStream``'s own
+    code: this class only replaces where the MSMs run.  Commitments are issued one after the other in the same order on
+    every rank (each is a collective)."""
+
+    def __init__(self, sharded_key: ShardedCommitterKey, length: int):
+        self.sck, self.ctx, self._n = sharded_key, sharded_key.ctx, length
+
+    def __len__(self) -> int:
+        return self._n
+
+    def _le(self, stream_be):
+        from .streams import as_le_device
+
+        return as_le_device(self.ctx, stream_be)
+
+    def _commit_le(self, le, max_msm_buffer: int):
+        if le.n == 0:
+            return None
+        assert le.n <= len(self), "polynomial longer than the SRS"
+        return self.sck.commit(le)
+
+    def commit(self, polynomial_be, step: int = 1 << 20):
+        return self._commit_le(self._le(polynomial_be), step)
+
+    def open(self, polynomial_be, alpha: int, max_msm_buffer: int):
+        from . import field
+
+        le = self._le(polynomial_be)
+        if le.n == 0:
+            return 0, None
+        q, evaluation = le.div_linear(alpha % field.R)
+        return evaluation, self._commit_le(q, max_msm_buffer)
+
+    def open_multi_points(self, polynomial_be, points, max_msm_buffer: int):
+        from .kzg import _divide_by_points
+
+        le = self._le(polynomial_be)
+        assert le.n >= len(points)
+        q, rem = _divide_by_points(le, points)
+        return rem, self._commit_le(q, max_msm_buffer)
+
+    def commit_folding(self, polynomials_be, challenges, max_msm_buffer: int):
+        from . import field
+        from .tensorcheck import FoldedPolynomialTree
+
+        if isinstance(polynomials_be, FoldedPolynomialTree):
+            levels = polynomials_be.levels
+        else:
+            if len(challenges) == 0:
+                return []
+            levels = self._le(polynomials_be).fold_chain([c % field.R for c in challenges])
+        return [self._commit_le(lvl, max_msm_buffer) for lvl in levels]
+
+    def open_folding(self, polynomials, points, etas, max_msm_buffer: int = 0):
+        from .kzg import CommitterKeyStream
+
+        return CommitterKeyStream.open_folding(self, polynomials, points, etas, max_msm_buffer)

@@ -29,6 +29,7 @@ def plan(job, args):
         out.append(("snark_elastic_prover_1gpu", lambda: elastic_line(job, args.extras_logn)))
     else:
         out.append(("snark_time_prover_config4_sharded", lambda: sharded_snark_line(job, args.extras_logn)))
+        out.append(("snark_elastic_prover_config5_sharded", lambda: sharded_elastic_line(job, args.extras_logn)))
     out.append(("streamed_msm_config5", lambda: streamed_line(job, 24 if job.world == 1 else 25, 20)))
     out.append(("strong_scaling_msm_2^24", lambda: strong_line(job, 24, 5)))
     out.append(("strong_scaling_msm_2^26", lambda: strong_line(job, 26, 3)))
@@ -175,6 +176,12 @@ def sharded_snark_line(job, logn):
     import bench_snark
 
     return bench_snark.run_sharded(job, logn, 2)
+
+
+def sharded_elastic_line(job, logn):
+    import bench_snark
+
+    return bench_snark.run_sharded_elastic(job, logn, 1)
 
 
 def elastic_line(job, logn):
