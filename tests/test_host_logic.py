@@ -219,3 +219,65 @@ def test_msm_planner_decisions(monkeypatch):
     assert plan(1 << 12, True)["levels"] == 5
     monkeypatch.setenv("GM_MSM_AFFINE", "0")
     assert plan(1 << 24, True)["levels"] == 0
+
+
+@pytest.mark.parametrize("world,sizes", [(4, [1 << 20, 300, 5000, 7, 1, 64, 2, 900, 33, 12, 100]), (8, [9, 8, 7, 6, 5, 4, 3, 2, 1]), (2, [5])])
+def test_sharded_batch_commit_deals_short_polynomials_out(world, sizes):
+    """dist.ShardedCommitterKey.batch_commit (host logic, no GPU): polynomials longer than the replicated prefix take the
+    sharded commit, in order, on every rank; the short ones are dealt out whole - longest first, snake order - and every
+    rank ends up with every commitment after one all-gather per round.  Ranks run as threads over a fake context whose
+    'MSM' of polynomial k is [k + 1]G and whose all-gather is a barrier."""
+    import threading
+
+    points = [o.g1_mul(o.G1_GEN, k + 1) for k in range(len(sizes))]
+    barrier = threading.Barrier(world)
+    board = [None] * world
+    local_calls = [[] for _ in range(world)]
+    sharded_calls = [[] for _ in range(world)]
+
+    class Poly:
+        def __init__(self, k, n):
+            self.k, self.n, self.ptr = k, n, k          # ptr doubles as the identity of the polynomial
+
+    class FakeSrs:
+        def __len__(self):
+            return 1024
+
+    class FakeCtx:
+        def __init__(self, rank):
+            self.rank = rank
+
+        def msm_dev(self, srs, ptr, n, base_offset=0):
+            local_calls[self.rank].append(ptr)
+            return field.affine_to_jacobian_limbs(points[ptr])
+
+        def comm_allgather(self, row):
+            board[self.rank] = np.array(row, dtype=np.uint64).copy()
+            barrier.wait()
+            rows = np.stack(board)
+            barrier.wait()
+            return rows
+
+    class Key(gdist.ShardedCommitterKey):
+        def commit(self, v):                            # the sharded path: recorded, answered without a collective
+            sharded_calls[self.rank].append(v.k)
+            return points[v.k]
+
+    results = [None] * world
+
+    def run(rank):
+        key = Key(FakeCtx(rank), None, rank=rank, world=world, prefix=FakeSrs())
+        results[rank] = key.batch_commit([Poly(k, n) for k, n in enumerate(sizes)])
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    assert all(res == points for res in results)
+    long_ones = [k for k, n in enumerate(sizes) if n > 1024]
+    assert all(calls == long_ones for calls in sharded_calls)
+    dealt = sorted(k for calls in local_calls for k in calls)
+    assert dealt == [k for k, n in enumerate(sizes) if n <= 1024]          # every short one committed exactly once
+    loads = [sum(sizes[k] for k in calls) for calls in local_calls]
+    assert max(len(c) for c in local_calls) - min(len(c) for c in local_calls) <= 1, loads
