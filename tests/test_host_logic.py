@@ -281,3 +281,46 @@ def test_sharded_batch_commit_deals_short_polynomials_out(world, sizes):
     assert dealt == [k for k, n in enumerate(sizes) if n <= 1024]          # every short one committed exactly once
     loads = [sum(sizes[k] for k in calls) for calls in local_calls]
     assert max(len(c) for c in local_calls) - min(len(c) for c in local_calls) <= 1, loads
+
+
+def test_commit_lanes_return_results_in_job_order(monkeypatch):
+    """kzg._msm_on_lanes (host logic, no GPU): the lanes pull from one queue, longest job first; every job runs exactly
+    once, on some lane, and the results come back in JOB order whatever lane finished first."""
+    import threading
+    import time
+
+    points = [o.g1_mul(o.G1_GEN, k + 1) for k in range(9)]
+    ran = []
+    lock = threading.Lock()
+
+    class FakeCtx:
+        def __init__(self, name):
+            self.name, self._h, self.device_id = name, 1, 0
+
+        def synchronize(self):
+            pass
+
+        def msm_dev(self, srs, ptr, n, base_offset=0):
+            time.sleep(0.001 * (n % 7))                 # lanes finish out of order
+            with lock:
+                ran.append((self.name, ptr, base_offset))
+            return field.affine_to_jacobian_limbs(points[ptr])
+
+    class Owner:
+        def __init__(self):
+            self.ctx = FakeCtx("main")
+            self.made = 0
+
+        def _helper_contexts(self, count):
+            self.made = max(self.made, count)
+            return [FakeCtx(f"helper{k}") for k in range(count)]
+
+    monkeypatch.setattr(kzg, "COMMIT_LANES", 3)
+    owner = Owner()
+    jobs = [(k, n, 100 + k) for k, n in enumerate([5, 900, 33, 0, 12, 4096, 7, 64, 1])]
+    out = kzg._msm_on_lanes(owner, object(), jobs)
+    assert out == [points[k] if n else None for k, n, _ in jobs]
+    assert owner.made == 2                                                   # main context + two helpers
+    assert sorted(p for _, p, _ in ran) == [k for k, n, _ in jobs if n]      # empty polynomials never reach a lane
+    assert all(off == 100 + p for _, p, off in ran)
+    assert ran[0][1] == 5 or ran[1][1] == 5 or ran[2][1] == 5                # the longest job starts first
