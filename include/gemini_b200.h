@@ -99,7 +99,12 @@ int gm_srs_free(gm_srs* srs);
 /* ---- MSM: ark_ec::VariableBaseMSM (called at src/kzg/time.rs:82,129; src/kzg/space.rs:52) ---- */
 /* msm_unchecked / msm_bigint: sum_{i<n} scalars[i] * srs[base_offset + i].
  * n is clamped to the bases available (min(len) truncation of msm_unchecked).
- * scalars_are_bigint = 0: Montgomery Fr (msm_unchecked); 1: canonical BigInt<4> (msm_bigint). */
+ * scalars_are_bigint = 0: Montgomery Fr (msm_unchecked); 1: canonical BigInt<4> (msm_bigint).
+ * `scalars` is ordinary host memory.  Pageable memory (a Rust &[Fr]) is gathered chunk by chunk into a pinned bounce
+ * buffer of the context by a few host threads, behind the kernels of the previous chunk; memory that is already pinned
+ * (cudaHostAlloc / cudaHostRegister) is recognised and copied piecewise, the digits of a piece extracted while the next one
+ * is on the bus.  The result is the same group element either way; a constant scalar vector (>= 2^16 terms, device entry
+ * points) is computed as s * (sum of the bases). */
 int gm_msm_g1(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
               int scalars_are_bigint, uint64_t out_jacobian[18]);
 int gm_msm_g1_dev(gm_ctx* ctx, const gm_srs* srs, size_t base_offset, const void* scalars_dev, size_t n,
