@@ -31,7 +31,7 @@ R = field.R
 # So a resident vector is pushed in pieces of max(max_msm_buffer, MIN_DEVICE_CHUNK) terms - one piece unless the
 # vector exceeds the 2^27-term pass limit; tests lower the floor to walk chunk boundaries (the result does not depend on it).
 MIN_DEVICE_CHUNK = 1 << 27
-# batch_commit of resident polynomials on two lanes (see CommitterKey.batch_commit); False = the reference's sequential map
+# batch_commit of resident polynomials on COMMIT_LANES lanes (see CommitterKey.batch_commit); False = the reference's sequential map
 CONCURRENT_COMMITS = True
 COMMIT_LANES = int(os.environ.get("GM_COMMIT_LANES", "4"))   # host threads / streams of CommitterKey.batch_commit
 

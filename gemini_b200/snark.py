@@ -70,7 +70,7 @@ def tensorcheck_new_time(transcript, ck: CommitterKey, base_polynomials: Sequenc
         for p, c in zip(polys, batch_challenges):
             lc.axpy(c, p)
         foldings += lc.fold_chain(list(chals)[:-1])
-    commitments = ck.batch_commit(foldings)          # 23 independent MSMs at logsize 24: two lanes, tails overlapped
+    commitments = ck.batch_commit(foldings)          # 23 independent MSMs at logsize 24: four lanes, tails overlapped
     for c in commitments:
         transcript.append_g1(b"commitment", c)
     eval_chal = transcript.get_challenge(b"evaluation-chal")
