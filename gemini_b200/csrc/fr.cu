@@ -515,15 +515,26 @@ k_fr_spmv(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col,
 //   S_i = sum_{k>=i} f_k a^(k-i):  quotient q_j = S_{j+1}, remainder = S_0.
 // up-sweep:  next[j] = sum_{k<DIV_K} cur[j*DIV_K + k] * a_l^k        (a_l = a^(DIV_K^level))
 // down-sweep: within run j start from the carry S_next[j+1] and Horner down, writing every S.
-static constexpr int DIV_K = 32;
+// A run is DIV_K = 8 consecutive elements = 256 contiguous bytes per thread: the whole run is loaded up front with
+// 128-bit accesses (two full 128-byte lines per thread, nothing left to the L1) and the dependent Horner chain is 8 long.
+// Round 2 started with runs of 32 walked by a load-multiply loop: neighbouring threads 1 KB apart, one load in flight per
+// thread, 2.7 ms per division at 2^24 against 0.7 ms of memory time (profiles/r02_prover_pieces.txt: three_divisions).
+static constexpr int DIV_K = 8;
+static constexpr int DIV_K_LOG = 3;
+__device__ __forceinline__ void div_load_run(Fr* run, const Fr* __restrict__ cur, size_t lo, size_t n) {
+#pragma unroll
+  for (int k = 0; k < DIV_K; k++) run[k] = lo + k < n ? load_fr(cur + lo + k) : Fr::zero();
+}
 __global__ void __launch_bounds__(128)
 k_fr_div_up(const Fr* __restrict__ cur, size_t n, Fr a_l, Fr* __restrict__ next) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t lo = j * DIV_K;
   if (lo >= n) return;
-  const size_t hi = min(lo + (size_t)DIV_K, n);
-  Fr acc = Fr::zero();
-  for (size_t k = hi; k-- > lo;) acc = load_fr(cur + k) + a_l * acc;
+  Fr run[DIV_K];
+  div_load_run(run, cur, lo, n);       // elements beyond n are zero: they add nothing to the aggregate
+  Fr acc = run[DIV_K - 1];
+#pragma unroll
+  for (int k = DIV_K - 2; k >= 0; k--) acc = run[k] + a_l * acc;
   store_fr(next + j, acc);
 }
 // suffix: S of the next level (nullptr at the top level); out_shift = 1 at level 0 (q_j = S_{j+1}) else 0
@@ -533,15 +544,18 @@ k_fr_div_down(const Fr* __restrict__ cur, size_t n, Fr a_l, const Fr* __restrict
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t lo = j * DIV_K;
   if (lo >= n) return;
-  const size_t hi = min(lo + (size_t)DIV_K, n);
+  Fr run[DIV_K];
+  div_load_run(run, cur, lo, n);
   Fr acc = (suffix_next != nullptr && j + 1 < n_next) ? load_fr(suffix_next + j + 1) : Fr::zero();
-  for (size_t k = hi; k-- > lo;) {
-    acc = load_fr(cur + k) + a_l * acc;
+#pragma unroll
+  for (int k = DIV_K - 1; k >= 0; k--) {
+    if (lo + k >= n) continue;          // the last run of a level may be short (acc is still the carry = 0 there)
+    acc = run[k] + a_l * acc;
     if (out_shift) {
-      if (k >= 1) store_fr(out + k - 1, acc);
+      if (lo + k >= 1) store_fr(out + lo + k - 1, acc);
       else store_fr(rem, acc);
     } else {
-      store_fr(out + k, acc);
+      store_fr(out + lo + k, acc);
     }
   }
 }
@@ -780,7 +794,7 @@ int fr_div_linear_dev(gm_ctx* ctx, const Fr* d_f, size_t n, const Fr& a, Fr* d_q
   while (sizes.back() > 1) {
     sizes.push_back((sizes.back() + DIV_K - 1) / DIV_K);
     Fr p = apow.back();
-    for (int k = 0; k < 5; k++) p = p.sqr();  // ^32 = DIV_K
+    for (int k = 0; k < DIV_K_LOG; k++) p = p.sqr();  // ^DIV_K
     apow.push_back(p);
   }
   const int levels = (int)sizes.size() - 1;
