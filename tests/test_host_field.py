@@ -250,3 +250,15 @@ def test_fq_product_on_the_fp64_pipe_48_bit_limbs(hc):
     r = np.zeros_like(a)
     hc.hc_fq(11, P(a), P(b), P(r), len(A))
     assert unpack(r) == [x * y * Ri % p for x, y in zip(A, B)]
+
+
+def test_unreduced_run_bound_of_the_lazy_accumulator():
+    """FpAcc::mul_add_unreduced (fp.cuh): with the top half below p on entry, k maximal products keep the accumulator below
+    2 p 2^(32N) - no overflow of the 2N limbs, and ONE conditional subtraction of the top half restores the invariant -
+    exactly while k p < 2^(32N).  The constants in the header (2 for Fr, 9 for Fq) must be the largest such k."""
+    for p, n, run in ((o.R, 8, 2), (o.Q, 12, 9)):
+        Rr = 1 << (32 * n)
+        worst = lambda k: (p - 1) * Rr + (Rr - 1) + k * (p - 1) ** 2        # top half p - 1, bottom half all ones
+        assert run * p < Rr <= (run + 1) * p
+        assert worst(run) < 2 * p * Rr < Rr * Rr
+        assert worst(run + 1) >= 2 * p * Rr or (run + 1) * p >= Rr
